@@ -1,0 +1,121 @@
+"""Shared helpers for the test-suite (fixtures, oracle access, output comparison rules of SURVEY.md App. B)."""
+import ctypes
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+ORACLE_DIR = os.path.join(REPO, "oracle")
+ORACLE_EXE = os.path.join(ORACLE_DIR, "_build", "indexlr_oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "_build", "libntl_oracle.so")
+
+if ORACLE_DIR not in sys.path:
+    sys.path.insert(0, ORACLE_DIR)
+
+
+def ensure_oracle():
+    if not (os.path.exists(ORACLE_EXE) and os.path.exists(ORACLE_LIB)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR])
+
+
+def manifest():
+    with open(os.path.join(GOLD, "manifest.json")) as fin:
+        return json.load(fin)
+
+
+def gunzip_bytes(path):
+    with gzip.open(path, "rb") as fin:
+        return fin.read()
+
+
+def fixture_file(tmpdir, name):
+    "Materialise tests/golden/inputs/<name>.gz as tmpdir/<name>; returns the path"
+    dst = os.path.join(str(tmpdir), name)
+    if not os.path.exists(dst):
+        with open(dst, "wb") as fout:
+            fout.write(gunzip_bytes(os.path.join(GOLD, "inputs", name + ".gz")))
+    return dst
+
+
+def golden_case(case, what):
+    return gunzip_bytes(os.path.join(GOLD, "cases", case, what + ".gz"))
+
+
+def expected_output(name):
+    return gunzip_bytes(os.path.join(GOLD, "expected_outputs", name + ".gz"))
+
+
+def oracle_indexlr(path, k, w, length=False, threads=4, pos=True, strand=True):
+    ensure_oracle()
+    cmd = [ORACLE_EXE, "--long", "-k", str(k), "-w", str(w), "-t", str(threads)]
+    if pos:
+        cmd.append("--pos")
+    if strand:
+        cmd.append("--strand")
+    if length:
+        cmd.append("--len")
+    cmd.append(path)
+    return subprocess.check_output(cmd)
+
+
+_lib = None
+
+
+def oracle_lib():
+    global _lib
+    if _lib is None:
+        ensure_oracle()
+        lib = ctypes.CDLL(ORACLE_LIB)
+        lib.ntl_oracle_sketch.restype = ctypes.c_size_t
+        lib.ntl_oracle_sketch.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        lib.ntl_oracle_sketch_batch.restype = ctypes.c_size_t
+        lib.ntl_oracle_sketch_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint,
+                                                ctypes.c_uint, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        lib.ntl_oracle_kmer_hashes.restype = None
+        lib.ntl_oracle_kmer_hashes.argtypes = [ctypes.c_char_p, ctypes.c_uint] + [ctypes.POINTER(ctypes.c_uint64)] * 4
+        lib.ntl_oracle_srol.restype = ctypes.c_uint64
+        lib.ntl_oracle_srol.argtypes = [ctypes.c_uint64, ctypes.c_uint]
+        _lib = lib
+    return _lib
+
+
+def oracle_sketch_batch(seq_bytes, offsets, k, w, threads=4):
+    """seq_bytes: uint8 array of concatenated sequences; offsets: uint64[nseq+1].
+    Returns (hash u64[], pos u32[], strand u8[], mx_off u64[nseq+1])."""
+    lib = oracle_lib()
+    seq = np.ascontiguousarray(seq_bytes, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    nseq = len(offsets) - 1
+    cap = max(1024, int(len(seq) * 2.5 / max(1, w) + 4 * nseq) + 1024)
+    while True:
+        h = np.empty(cap, np.uint64)
+        p = np.empty(cap, np.uint32)
+        s = np.empty(cap, np.uint8)
+        off = np.empty(nseq + 1, np.uint64)
+        n = lib.ntl_oracle_sketch_batch(seq.ctypes.data, offsets.ctypes.data, nseq, k, w, threads,
+                                        h.ctypes.data, p.ctypes.data, s.ctypes.data, cap, off.ctypes.data)
+        if n != ctypes.c_size_t(-1).value:
+            return h[:n], p[:n], s[:n], off
+        cap *= 4
+
+
+def dot_parts(data):
+    "Split a .scaffold.dot into (header lines, sorted node lines, ordered edge lines, tail) per SURVEY App. B"
+    lines = data.decode().splitlines()
+    head = lines[:2]
+    nodes = sorted(l for l in lines[2:] if "->" not in l and l != "}")
+    edges = [l for l in lines[2:] if "->" in l]
+    return head, nodes, edges, lines[-1]
+
+
+def is_ordered_subsequence(small_lines, big_lines):
+    it = iter(big_lines)
+    return all(any(x == y for y in it) for x in small_lines)
