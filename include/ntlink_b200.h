@@ -1,0 +1,215 @@
+/*
+ * ntlink_b200.h -- C ABI of libntlink_b200.so: the B200-native (sm_100a) implementation of ntLink's
+ * data-parallel hot path (minimizer sketching + minimizer mapping).
+ *
+ * Plain C, pointers and sizes only; every entry point names the reference interface it replaces
+ * (paths relative to bcgsc/ntLink v1.3.11). The reference has no FFI of its own: its seams are two
+ * executables (`indexlr` from btllib, `bin/ntlink_pair.py`) and the Python functions inside the latter.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds to bin/ntlink_pair.py.
+ *
+ * Conventions
+ *   - one ntl_ctx per GPU, not thread-safe per ctx; ctypes releases the GIL during calls;
+ *   - all calls return NTL_OK (0) or a negative NTL_ERR_* code; ntl_last_error() gives the text;
+ *   - inputs are caller-owned HOST pointers; outputs point into ctx-owned pinned host memory that stays
+ *     valid until the next call producing the same output struct on that ctx (or ntl_destroy);
+ *   - positions and strands are packed as  pos | (strand == '+' ? 1u << 31 : 0)  ("pos_strand");
+ *   - there is no CPU fallback: without a CUDA device ntl_init fails with NTL_ERR_CUDA.
+ */
+#ifndef NTLINK_B200_H
+#define NTLINK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTL_OK 0
+#define NTL_ERR_CUDA (-1)       /* CUDA runtime error (no device, out of memory, launch failure) */
+#define NTL_ERR_ARG (-2)        /* invalid argument */
+#define NTL_ERR_WORKSPACE (-3)  /* a device-side capacity was exceeded even after growing it */
+#define NTL_ERR_STATE (-4)      /* call order violated, e.g. mapping before an index was built */
+#define NTL_ERR_ASSERT (-5)     /* an assertion of the reference would have failed (e.g. paf:127-129) */
+
+#define NTL_STRAND_BIT 0x80000000u
+#define NTL_POS_MASK 0x7FFFFFFFu
+
+typedef struct ntl_ctx ntl_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+int ntl_init(int device, ntl_ctx** out);
+void ntl_destroy(ntl_ctx* ctx);
+const char* ntl_last_error(const ntl_ctx* ctx);
+int ntl_version(void);
+/* tuning knobs: "strip_len" (k-mer positions per thread, multiple of 8), "cand_c" (candidate threshold,
+ * expected candidates per window), "batch_bases" (bases per device batch) */
+int ntl_set_option(ntl_ctx* ctx, const char* name, double value);
+
+/* ---- sketch -------------------------------------------------------------------------------------
+ * Replaces the external sketcher   indexlr --long --pos --strand [--len] -k K -w W -t T FILE
+ * (btllib <= 1.6.2; invoked at ntLink:198-199 for the target and ntLink:221-225 for the reads): ntHash
+ * canonical hash, windowed minimizers over valid k-mers, second hash printed. `seq` holds nseq sequences
+ * back to back (ASCII, any case, any non-ACGT byte is an invalid base), offsets[nseq+1] delimit them.
+ * Output order = input order; minimizers of sequence i are [seq_off[i], seq_off[i+1]). */
+typedef struct {
+    uint64_t n_mx;
+    uint32_t nseq;
+    uint32_t reserved;
+    const uint64_t* hash;        /* [n_mx]  the hash indexlr prints */
+    const uint32_t* pos_strand;  /* [n_mx]  k-mer start | strand bit */
+    const uint64_t* seq_off;     /* [nseq+1] */
+} ntl_sketch_out;
+int ntl_sketch(ntl_ctx* ctx, const char* seq, const uint64_t* offsets, uint32_t nseq, int k, int w,
+               ntl_sketch_out* out);
+
+/* ---- target index -------------------------------------------------------------------------------
+ * Replaces NtLink.read_minimizers (bin/ntlink_pair.py:189-211): hash -> (contig, position, strand); a hash
+ * that occurs two or more times anywhere in the target is dropped entirely. contig[] are ids 0..ncontig-1
+ * in target FASTA order; contig_len[] their lengths (bin/ntlink_utils.py:65-73); name_rank[] the rank of
+ * each contig NAME under Python string comparison (normalize_pair, bin/ntlink_pair.py:213-219). */
+int ntl_index_build(ntl_ctx* ctx, const uint64_t* hash, const uint32_t* contig, const uint32_t* pos_strand,
+                    uint64_t n, const uint32_t* contig_len, const uint32_t* name_rank, uint32_t ncontig);
+/* Same, but sketches the target on the device first (ntLink:198-199 + the above in one call, the sketch never
+ * leaves the GPU). If sketch_out is not NULL the target sketch is also returned (for writing target.tsv). */
+int ntl_index_build_from_sequences(ntl_ctx* ctx, const char* seq, const uint64_t* offsets, uint32_t ncontig,
+                                   int k, int w, const uint32_t* name_rank, ntl_sketch_out* sketch_out);
+int ntl_index_stats(ntl_ctx* ctx, uint64_t* n_inserted, uint64_t* n_unique, uint64_t* table_slots);
+/* Replicated index for multi-GPU runs: raw target minimizer triples of this rank (device pointers, for an NCCL
+ * all-gather by the caller) -- see ntlink_b200/dist.py. */
+int ntl_device_sketch_arrays(ntl_ctx* ctx, uint64_t* n_mx, void** d_hash, void** d_pos_strand, void** d_seq_off);
+int ntl_index_build_device(ntl_ctx* ctx, const void* d_hash, const void* d_contig, const void* d_pos_strand,
+                           uint64_t n, const uint32_t* contig_len, const uint32_t* name_rank, uint32_t ncontig);
+
+/* ---- mapping ------------------------------------------------------------------------------------
+ * Replaces the read loop of NtLink.find_scaffold_pairs (bin/ntlink_pair.py:336-414) with
+ * ntlink_utils.get_accepted_anchor_contigs (bin/ntlink_utils.py:200-294) and tally_pairs_from_mappings /
+ * add_pair / calculate_pair_info / calculate_gap_size (bin/ntlink_pair.py:157-187,213-239,315-334,416-435). */
+typedef struct {
+    int32_t k, w;
+    int32_t z;              /* -z  minimum contig length */
+    int32_t f;              /* -f  max contigs in a run for full transitive edges */
+    double x;               /* -x  fudge factor (0 = off) */
+    int32_t sensitive;      /* --sensitive */
+    int32_t repeat_filter;  /* --repeat-filter */
+} ntl_params;
+
+typedef struct {            /* one accepted minimizer hit, 12 bytes */
+    uint32_t ctg;           /* contig id */
+    uint32_t ctg_pos_strand;
+    uint32_t read_pos_strand;
+} ntl_hit;
+
+typedef struct {            /* one accepted contig run of a read (a verbose_mapping.tsv line), 12 bytes */
+    uint32_t ctg;
+    uint32_t start;         /* first hit, relative to the read's hit region */
+    uint32_t count;         /* hit_count */
+} ntl_run;
+
+typedef struct {            /* one contig-pair observation (an add_pair call that was accepted), 24 bytes */
+    uint32_t read;          /* global read ordinal */
+    uint32_t ord;           /* insertion order within the read */
+    uint32_t src, tgt;      /* contig ids, normalised: lexicographically smaller name first */
+    int32_t gap;
+    uint32_t flags;         /* bit0 src '+', bit1 tgt '+', bit2 both runs have hit_count > 1 (anchor) */
+} ntl_event;
+
+typedef struct {
+    uint32_t n_reads;
+    uint32_t reserved;
+    uint64_t n_mx;            /* read minimizers sketched / received */
+    uint64_t n_hits;          /* minimizers found in the index */
+    uint64_t n_runs;          /* total accepted runs */
+    uint64_t n_events;        /* total pair observations */
+    /* per read r: its hit region is [hit_off[r], hit_off[r+1]); after chaining the first nruns[r] entries of
+     * runs[hit_off[r] ..] are its accepted runs in output order and hits[hit_off[r] + run.start ..] their hits */
+    const uint32_t* hit_off;  /* [n_reads+1] */
+    const uint32_t* nruns;    /* [n_reads] */
+    const ntl_run* runs;      /* [n_hits] */
+    const ntl_hit* hits;      /* [n_hits] */
+    /* per read r: events [ev_off[r], ev_off[r] + ev_cnt[r]) in reference insertion order */
+    const uint32_t* ev_off;   /* [n_reads+1] */
+    const uint32_t* ev_cnt;   /* [n_reads] */
+    const ntl_event* events;  /* [ev_off[n_reads]] */
+} ntl_map_out;
+
+/* sketch + map nreads reads given as sequences (the fused path: gzip -cd reads | indexlr ... | ntlink_pair.py).
+ * first_read_ordinal numbers the reads globally (multi-batch / multi-GPU order). Events are also appended to the
+ * ctx's device-side event log for ntl_pairs_finish. */
+int ntl_map_reads(ntl_ctx* ctx, const char* seq, const uint64_t* offsets, uint32_t nreads,
+                  uint64_t first_read_ordinal, const ntl_params* prm, ntl_map_out* out);
+/* map reads given as an indexlr sketch (ntlink_pair.py reading the TSV of `indexlr --len`): mx_off[nreads+1] */
+int ntl_map_sketch(ntl_ctx* ctx, const uint64_t* hash, const uint32_t* pos_strand, const uint64_t* mx_off,
+                   const uint32_t* read_len, uint32_t nreads, uint64_t first_read_ordinal,
+                   const ntl_params* prm, ntl_map_out* out);
+
+/* ---- pair tally ---------------------------------------------------------------------------------
+ * Replaces the `pairs` accumulator of find_scaffold_pairs (bin/ntlink_pair.py:327-332): per normalised pair the
+ * gap estimates in read order, the anchor count, and the order in which pairs were first seen. */
+typedef struct {
+    uint32_t src, tgt;
+    uint32_t flags;           /* bit0 src '+', bit1 tgt '+' */
+    uint32_t n;               /* supporting reads = len(gap_estimates) */
+    uint32_t anchor;
+    uint32_t reserved;
+    uint64_t gap_off;         /* gaps[gap_off .. gap_off+n) in read order */
+    uint64_t first_key;       /* (read << 24 | ord) of the first observation; pairs are returned sorted by it */
+} ntl_pair;
+typedef struct {
+    uint64_t n_pairs;
+    uint64_t n_gaps;
+    const ntl_pair* pairs;
+    const int32_t* gaps;
+} ntl_pairs_out;
+int ntl_events_reset(ntl_ctx* ctx);
+int ntl_events_append(ntl_ctx* ctx, const ntl_event* events, uint64_t n);    /* e.g. gathered from other ranks */
+int ntl_events_count(ntl_ctx* ctx, uint64_t* n);
+int ntl_events_device(ntl_ctx* ctx, uint64_t* n, void** d_events);            /* device pointer for NCCL */
+int ntl_events_append_device(ntl_ctx* ctx, const void* d_events, uint64_t n);
+int ntl_pairs_finish(ntl_ctx* ctx, ntl_pairs_out* out);
+
+/* ---- host text emitters (byte-identical to the reference's files) -------------------------------
+ * Each returns the number of bytes written to a malloc'ed buffer (*out_buf, release with ntl_buf_free) or a
+ * negative error. names: concatenated NUL-free names with name_off[n+1]. */
+int64_t ntl_format_sketch_tsv(const ntl_sketch_out* sk, const char* names, const uint64_t* name_off,
+                              const uint64_t* seq_len /* NULL = no --len column */, int with_pos, int with_strand,
+                              int threads, char** out_buf);
+/* verbose_mapping.tsv lines (bin/ntlink_pair.py:382-388) */
+int64_t ntl_format_verbose(const ntl_map_out* m, const char* read_names, const uint64_t* read_name_off,
+                           const char* ctg_names, const uint64_t* ctg_name_off, int threads, char** out_buf);
+/* PAF-like lines (bin/ntlink_paf_output.py:103-135); returns NTL_ERR_ASSERT where the reference asserts */
+int64_t ntl_format_paf(const ntl_map_out* m, const char* read_names, const uint64_t* read_name_off,
+                       const uint32_t* read_len, const char* ctg_names, const uint64_t* ctg_name_off,
+                       const uint32_t* ctg_len, int k, int threads, char** out_buf);
+void ntl_buf_free(char* buf);
+/* FASTA/FASTQ (plain or gzip, multi-line) reader: id = header up to the first whitespace (bin/read_fasta.py).
+ * Returns malloc'ed arrays; release with ntl_seqfile_free. max_bases = 0 reads everything, otherwise stops after
+ * the record that crosses max_bases (call again with the same handle to continue). */
+typedef struct ntl_seqfile ntl_seqfile;
+int ntl_seqfile_open(const char* path, ntl_seqfile** out);
+int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq, uint64_t** offsets, char** names,
+                     uint64_t** name_off, uint32_t* nseq);
+void ntl_seqfile_close(ntl_seqfile* f);
+void ntl_free(void* p);
+
+/* ---- device-resident / timing interface (bench.py) ----------------------------------------------- */
+/* copy a read batch to the device once; ntl_map_resident then runs the whole hot path on it without touching
+ * the host (results stay on the device; only the counters come back). */
+int ntl_reads_upload(ntl_ctx* ctx, const char* seq, const uint64_t* offsets, uint32_t nreads);
+int ntl_map_resident(ntl_ctx* ctx, uint64_t first_read_ordinal, const ntl_params* prm, ntl_map_out* counts_only);
+/* target kept resident the same way */
+int ntl_target_upload(ntl_ctx* ctx, const char* seq, const uint64_t* offsets, uint32_t ncontig,
+                      const uint32_t* name_rank);
+int ntl_index_build_resident(ntl_ctx* ctx, int k, int w);
+/* device timings (ms, CUDA events on the library's stream) of the last call, indexed by NTL_T_*; and the
+ * number of kernels this library launched since ntl_timing_reset */
+enum { NTL_T_PACK = 0, NTL_T_DENSE, NTL_T_SELECT, NTL_T_GAP, NTL_T_EMIT, NTL_T_LOOKUP, NTL_T_CHAIN, NTL_T_TALLY,
+       NTL_T_INDEX, NTL_T_TOTAL, NTL_T_NUM };
+int ntl_timing_reset(ntl_ctx* ctx);
+int ntl_timing(ntl_ctx* ctx, double* ms_accum /* [NTL_T_NUM] */, uint64_t* launches, uint64_t* dense_launches,
+               uint64_t* dense_bases);
+int ntl_device_sync(ntl_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTLINK_B200_H */

@@ -1,0 +1,119 @@
+"""ctypes binding of libntlink_b200.so (include/ntlink_b200.h). No CPU fallback: a missing library or a missing
+CUDA device raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libntlink_b200.so")
+
+NTL_OK = 0
+NTL_ERR = {-1: "NTL_ERR_CUDA", -2: "NTL_ERR_ARG", -3: "NTL_ERR_WORKSPACE", -4: "NTL_ERR_STATE", -5: "NTL_ERR_ASSERT"}
+STRAND_BIT = 0x80000000
+POS_MASK = 0x7FFFFFFF
+T_NAMES = ["pack", "dense", "select", "gap", "emit", "lookup", "chain", "tally", "index", "total"]
+
+
+class NtlError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{NTL_ERR.get(code, code)}: {msg}")
+        self.code = code
+
+
+class SketchOut(C.Structure):
+    _fields_ = [("n_mx", C.c_uint64), ("nseq", C.c_uint32), ("reserved", C.c_uint32),
+                ("hash", C.POINTER(C.c_uint64)), ("pos_strand", C.POINTER(C.c_uint32)),
+                ("seq_off", C.POINTER(C.c_uint64))]
+
+
+class Params(C.Structure):
+    _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("z", C.c_int32), ("f", C.c_int32), ("x", C.c_double),
+                ("sensitive", C.c_int32), ("repeat_filter", C.c_int32)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("ctg", C.c_uint32), ("ctg_pos_strand", C.c_uint32), ("read_pos_strand", C.c_uint32)]
+
+
+class Run(C.Structure):
+    _fields_ = [("ctg", C.c_uint32), ("start", C.c_uint32), ("count", C.c_uint32)]
+
+
+class Event(C.Structure):
+    _fields_ = [("read", C.c_uint32), ("ord", C.c_uint32), ("src", C.c_uint32), ("tgt", C.c_uint32),
+                ("gap", C.c_int32), ("flags", C.c_uint32)]
+
+
+class MapOut(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("reserved", C.c_uint32), ("n_mx", C.c_uint64), ("n_hits", C.c_uint64),
+                ("n_runs", C.c_uint64), ("n_events", C.c_uint64),
+                ("hit_off", C.POINTER(C.c_uint32)), ("nruns", C.POINTER(C.c_uint32)),
+                ("runs", C.POINTER(Run)), ("hits", C.POINTER(Hit)),
+                ("ev_off", C.POINTER(C.c_uint32)), ("ev_cnt", C.POINTER(C.c_uint32)), ("events", C.POINTER(Event))]
+
+
+class Pair(C.Structure):
+    _fields_ = [("src", C.c_uint32), ("tgt", C.c_uint32), ("flags", C.c_uint32), ("n", C.c_uint32),
+                ("anchor", C.c_uint32), ("reserved", C.c_uint32), ("gap_off", C.c_uint64), ("first_key", C.c_uint64)]
+
+
+class PairsOut(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("n_gaps", C.c_uint64), ("pairs", C.POINTER(Pair)),
+                ("gaps", C.POINTER(C.c_int32))]
+
+
+# every symbol include/ntlink_b200.h declares: name -> (restype, argtypes)
+_VP, _U64P, _U32P = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+SIGNATURES = {
+    "ntl_init": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "ntl_destroy": (None, [_VP]),
+    "ntl_last_error": (C.c_char_p, [_VP]),
+    "ntl_version": (C.c_int, []),
+    "ntl_set_option": (C.c_int, [_VP, C.c_char_p, C.c_double]),
+    "ntl_sketch": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_int, C.c_int, C.POINTER(SketchOut)]),
+    "ntl_index_build": (C.c_int, [_VP, _VP, _VP, _VP, C.c_uint64, _VP, _VP, C.c_uint32]),
+    "ntl_index_build_from_sequences": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_int, C.c_int, _VP, C.POINTER(SketchOut)]),
+    "ntl_index_stats": (C.c_int, [_VP, _U64P, _U64P, _U64P]),
+    "ntl_device_sketch_arrays": (C.c_int, [_VP, _U64P, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    "ntl_index_build_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_uint64, _VP, _VP, C.c_uint32]),
+    "ntl_map_reads": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint64, C.POINTER(Params), C.POINTER(MapOut)]),
+    "ntl_map_sketch": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_uint32, C.c_uint64, C.POINTER(Params), C.POINTER(MapOut)]),
+    "ntl_events_reset": (C.c_int, [_VP]),
+    "ntl_events_append": (C.c_int, [_VP, _VP, C.c_uint64]),
+    "ntl_events_count": (C.c_int, [_VP, _U64P]),
+    "ntl_events_device": (C.c_int, [_VP, _U64P, C.POINTER(_VP)]),
+    "ntl_events_append_device": (C.c_int, [_VP, _VP, C.c_uint64]),
+    "ntl_pairs_finish": (C.c_int, [_VP, C.POINTER(PairsOut)]),
+    "ntl_format_sketch_tsv": (C.c_int64, [C.POINTER(SketchOut), _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.POINTER(_VP)]),
+    "ntl_format_verbose": (C.c_int64, [C.POINTER(MapOut), _VP, _VP, _VP, _VP, C.c_int, C.POINTER(_VP)]),
+    "ntl_format_paf": (C.c_int64, [C.POINTER(MapOut), _VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.POINTER(_VP)]),
+    "ntl_buf_free": (None, [_VP]),
+    "ntl_seqfile_open": (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
+    "ntl_seqfile_read": (C.c_int, [_VP, C.c_uint64, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), _U32P]),
+    "ntl_seqfile_close": (None, [_VP]),
+    "ntl_free": (None, [_VP]),
+    "ntl_reads_upload": (C.c_int, [_VP, _VP, _VP, C.c_uint32]),
+    "ntl_map_resident": (C.c_int, [_VP, C.c_uint64, C.POINTER(Params), C.POINTER(MapOut)]),
+    "ntl_target_upload": (C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP]),
+    "ntl_index_build_resident": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "ntl_timing_reset": (C.c_int, [_VP]),
+    "ntl_timing": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P, _U64P, _U64P]),
+    "ntl_device_sync": (C.c_int, [_VP]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libntlink_b200.so (built in-tree by ntlink_b200/build.py). Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m ntlink_b200.build` (needs nvcc). "
+                              "ntlink_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,341 @@
+"""Thin Python layer over the C ABI (include/ntlink_b200.h): numpy in, numpy out. The surrounding ntLink Python
+stays Python and calls the CUDA path through this module (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import POS_MASK, STRAND_BIT, NtlError
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def _np_from(ptr, n, dtype):
+    "copy n items from a ctypes pointer into a fresh numpy array"
+    if n == 0 or not ptr:
+        return np.empty(0, dtype)
+    addr = C.cast(ptr, C.c_void_p).value
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+def name_ranks(names):
+    "rank of every contig name under Python string comparison (normalize_pair, bin/ntlink_pair.py:213-219)"
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    rank = np.empty(len(names), np.uint32)
+    for r, i in enumerate(order):
+        rank[i] = r
+    return rank
+
+
+class SeqBatch:
+    """Sequences back to back: seq uint8[total], offsets uint64[n+1], names list[str]."""
+
+    def __init__(self, seq, offsets, names):
+        self.seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.names = list(names)
+        assert len(self.offsets) == len(self.names) + 1
+        self._name_blob = None
+
+    @classmethod
+    def from_strings(cls, named_seqs):
+        names, parts, offs, tot = [], [], [0], 0
+        for name, s in named_seqs:
+            b = s.encode() if isinstance(s, str) else bytes(s)
+            names.append(name)
+            parts.append(b)
+            tot += len(b)
+            offs.append(tot)
+        seq = np.frombuffer(b"".join(parts) + b"N" * 64, dtype=np.uint8)[:tot] if tot else np.empty(0, np.uint8)
+        return cls(seq, np.array(offs, np.uint64), names)
+
+    def __len__(self):
+        return len(self.names)
+
+    @property
+    def lengths(self):
+        return np.diff(self.offsets).astype(np.uint64)
+
+    def name_blob(self):
+        if self._name_blob is None:
+            enc = [n.encode() for n in self.names]
+            off = np.zeros(len(enc) + 1, np.uint64)
+            if enc:
+                off[1:] = np.cumsum([len(e) for e in enc])
+            self._name_blob = (np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8), off)
+        return self._name_blob
+
+
+def read_sequences(path, max_bases=0):
+    """FASTA/FASTQ (plain or gzip, multi-line) -> SeqBatch; id = header up to the first whitespace
+    (bin/read_fasta.py). Host-side I/O through the library's reader."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    if lib.ntl_seqfile_open(path.encode(), C.byref(h)) != 0:
+        raise OSError(f"cannot open {path}")
+    try:
+        seq, off, names, noff = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_uint32()
+        rc = lib.ntl_seqfile_read(h, max_bases, C.byref(seq), C.byref(off), C.byref(names), C.byref(noff), C.byref(n))
+        if rc != 0:
+            raise NtlError(rc, "ntl_seqfile_read failed")
+        nseq = n.value
+        offsets = _np_from(off, nseq + 1, np.uint64)
+        name_off = _np_from(noff, nseq + 1, np.uint64)
+        total = int(offsets[-1]) if nseq else 0
+        s = _np_from(seq, total, np.uint8)
+        nb = _np_from(names, int(name_off[-1]) if nseq else 0, np.uint8).tobytes()
+        nm = [nb[int(name_off[i]):int(name_off[i + 1])].decode() for i in range(nseq)]
+        for p in (seq, off, names, noff):
+            lib.ntl_free(p)
+        return SeqBatch(s, offsets, nm)
+    finally:
+        lib.ntl_seqfile_close(h)
+
+
+class Sketch:
+    "indexlr output as arrays: hash u64[n], pos_strand u32[n], seq_off u64[nseq+1]"
+
+    def __init__(self, hash_, pos_strand, seq_off):
+        self.hash, self.pos_strand, self.seq_off = hash_, pos_strand, seq_off
+
+    @property
+    def pos(self):
+        return self.pos_strand & np.uint32(POS_MASK)
+
+    @property
+    def strand(self):
+        return (self.pos_strand >> np.uint32(31)).astype(np.uint8)
+
+    def __len__(self):
+        return len(self.hash)
+
+    def _struct(self):
+        s = _lib.SketchOut()
+        s.n_mx, s.nseq = len(self.hash), len(self.seq_off) - 1
+        s.hash = C.cast(self.hash.ctypes.data, C.POINTER(C.c_uint64))
+        s.pos_strand = C.cast(self.pos_strand.ctypes.data, C.POINTER(C.c_uint32))
+        s.seq_off = C.cast(self.seq_off.ctypes.data, C.POINTER(C.c_uint64))
+        return s
+
+    def to_tsv(self, batch, with_len=False, with_pos=True, with_strand=True, threads=4):
+        "the bytes `indexlr --long [--pos] [--strand] [--len]` writes for these sequences"
+        lib = _lib.load()
+        blob, noff = batch.name_blob()
+        lens = batch.lengths if with_len else None
+        out = C.c_void_p()
+        st = self._struct()
+        n = lib.ntl_format_sketch_tsv(C.byref(st), _ptr(blob), _ptr(noff), _ptr(lens), int(with_pos), int(with_strand),
+                                      threads, C.byref(out))
+        if n < 0:
+            raise NtlError(n, "ntl_format_sketch_tsv")
+        data = C.string_at(out, n)
+        lib.ntl_buf_free(out)
+        return data
+
+
+class MapResult:
+    """Accepted mappings + pair events of a batch of reads (copies of ntl_map_out)."""
+
+    def __init__(self, mo):
+        n = mo.n_reads
+        self.n_reads, self.n_mx, self.n_hits, self.n_runs, self.n_events = n, mo.n_mx, mo.n_hits, mo.n_runs, mo.n_events
+        self.hit_off = _np_from(mo.hit_off, n + 1, np.uint32) if n else np.zeros(1, np.uint32)
+        self.nruns = _np_from(mo.nruns, n, np.uint32)
+        nh = int(self.hit_off[-1]) if n else 0
+        self.runs = _np_from(mo.runs, nh * 3, np.uint32).reshape(-1, 3)
+        self.hits = _np_from(mo.hits, nh * 3, np.uint32).reshape(-1, 3)
+        self.ev_off = _np_from(mo.ev_off, n + 1, np.uint32) if n else np.zeros(1, np.uint32)
+        self.ev_cnt = _np_from(mo.ev_cnt, n, np.uint32)
+        ne = int(self.ev_off[-1]) if n else 0
+        self.events = _np_from(mo.events, ne * 6, np.uint32).reshape(-1, 6)
+
+    def _struct(self):
+        m = _lib.MapOut()
+        m.n_reads, m.n_mx, m.n_hits, m.n_runs, m.n_events = self.n_reads, self.n_mx, self.n_hits, self.n_runs, self.n_events
+        m.hit_off = C.cast(self.hit_off.ctypes.data, C.POINTER(C.c_uint32))
+        m.nruns = C.cast(self.nruns.ctypes.data, C.POINTER(C.c_uint32))
+        m.runs = C.cast(self.runs.ctypes.data, C.POINTER(_lib.Run))
+        m.hits = C.cast(self.hits.ctypes.data, C.POINTER(_lib.Hit))
+        m.ev_off = C.cast(self.ev_off.ctypes.data, C.POINTER(C.c_uint32))
+        m.ev_cnt = C.cast(self.ev_cnt.ctypes.data, C.POINTER(C.c_uint32))
+        m.events = C.cast(self.events.ctypes.data, C.POINTER(_lib.Event))
+        return m
+
+    def verbose_bytes(self, reads, contigs, threads=4):
+        "verbose_mapping.tsv lines (bin/ntlink_pair.py:382-388)"
+        lib = _lib.load()
+        rb, ro = reads.name_blob()
+        cb, co = contigs.name_blob()
+        out = C.c_void_p()
+        st = self._struct()
+        n = lib.ntl_format_verbose(C.byref(st), _ptr(rb), _ptr(ro), _ptr(cb), _ptr(co), threads, C.byref(out))
+        if n < 0:
+            raise NtlError(n, "ntl_format_verbose")
+        data = C.string_at(out, n)
+        lib.ntl_buf_free(out)
+        return data
+
+    def paf_bytes(self, reads, read_len, contigs, k, threads=4):
+        "PAF-like lines (bin/ntlink_paf_output.py:103-135); raises where the reference asserts"
+        lib = _lib.load()
+        rb, ro = reads.name_blob()
+        cb, co = contigs.name_blob()
+        rl = np.ascontiguousarray(read_len, dtype=np.uint32)
+        cl = np.ascontiguousarray(contigs.lengths, dtype=np.uint32)
+        out = C.c_void_p()
+        st = self._struct()
+        n = lib.ntl_format_paf(C.byref(st), _ptr(rb), _ptr(ro), _ptr(rl), _ptr(cb), _ptr(co), _ptr(cl), k, threads,
+                               C.byref(out))
+        if n < 0:
+            raise NtlError(n, "ntl_format_paf: a PAF assertion of the reference failed")
+        data = C.string_at(out, n)
+        lib.ntl_buf_free(out)
+        return data
+
+
+class Context:
+    """One GPU. Not thread-safe."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.ntl_init(device, C.byref(h))
+        if rc != 0:
+            raise NtlError(rc, "ntl_init failed: no usable CUDA device (ntlink_b200 has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.ntl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NtlError(rc, f"{what}: {self.lib.ntl_last_error(self.h).decode()}")
+
+    def set_option(self, name, value):
+        self._check(self.lib.ntl_set_option(self.h, name.encode(), float(value)), "ntl_set_option")
+
+    # ---- sketch
+    def _sketch_from(self, so):
+        n, ns = so.n_mx, so.nseq
+        return Sketch(_np_from(so.hash, n, np.uint64), _np_from(so.pos_strand, n, np.uint32),
+                      _np_from(so.seq_off, ns + 1, np.uint64))
+
+    def sketch(self, batch, k, w):
+        so = _lib.SketchOut()
+        self._check(self.lib.ntl_sketch(self.h, _ptr(batch.seq), _ptr(batch.offsets), len(batch), k, w, C.byref(so)),
+                    "ntl_sketch")
+        return self._sketch_from(so)
+
+    # ---- index
+    def build_index(self, hash_, contig, pos_strand, contig_len, names):
+        hash_ = np.ascontiguousarray(hash_, np.uint64)
+        contig = np.ascontiguousarray(contig, np.uint32)
+        pos_strand = np.ascontiguousarray(pos_strand, np.uint32)
+        cl = np.ascontiguousarray(contig_len, np.uint32)
+        rank = name_ranks(names)
+        self._check(self.lib.ntl_index_build(self.h, _ptr(hash_), _ptr(contig), _ptr(pos_strand), len(hash_), _ptr(cl),
+                                             _ptr(rank), len(names)), "ntl_index_build")
+
+    def build_index_from_sequences(self, batch, k, w, want_sketch=True):
+        rank = name_ranks(batch.names)
+        so = _lib.SketchOut()
+        self._check(self.lib.ntl_index_build_from_sequences(self.h, _ptr(batch.seq), _ptr(batch.offsets), len(batch), k, w,
+                                                            _ptr(rank), C.byref(so) if want_sketch else None),
+                    "ntl_index_build_from_sequences")
+        return self._sketch_from(so) if want_sketch else None
+
+    def index_stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.ntl_index_stats(self.h, C.byref(a), C.byref(b), C.byref(c)), "ntl_index_stats")
+        return {"inserted": a.value, "unique": b.value, "slots": c.value}
+
+    # ---- mapping
+    @staticmethod
+    def params(k, w, z=500, f=10, x=0.0, sensitive=False, repeat_filter=False):
+        return _lib.Params(k, w, z, f, float(x), int(bool(sensitive)), int(bool(repeat_filter)))
+
+    def map_reads(self, batch, prm, first_ordinal=0):
+        mo = _lib.MapOut()
+        self._check(self.lib.ntl_map_reads(self.h, _ptr(batch.seq), _ptr(batch.offsets), len(batch), first_ordinal,
+                                           C.byref(prm), C.byref(mo)), "ntl_map_reads")
+        return MapResult(mo)
+
+    def map_sketch(self, sketch, read_len, prm, first_ordinal=0):
+        mo = _lib.MapOut()
+        rl = np.ascontiguousarray(read_len, np.uint32)
+        h = np.ascontiguousarray(sketch.hash, np.uint64)
+        p = np.ascontiguousarray(sketch.pos_strand, np.uint32)
+        o = np.ascontiguousarray(sketch.seq_off, np.uint64)
+        self._check(self.lib.ntl_map_sketch(self.h, _ptr(h), _ptr(p), _ptr(o), _ptr(rl), len(rl), first_ordinal,
+                                            C.byref(prm), C.byref(mo)), "ntl_map_sketch")
+        return MapResult(mo)
+
+    # ---- pairs
+    def events_reset(self):
+        self._check(self.lib.ntl_events_reset(self.h), "ntl_events_reset")
+
+    def events_append(self, events):
+        ev = np.ascontiguousarray(events, np.uint32).reshape(-1, 6)
+        self._check(self.lib.ntl_events_append(self.h, _ptr(ev), len(ev)), "ntl_events_append")
+
+    def events_count(self):
+        n = C.c_uint64()
+        self._check(self.lib.ntl_events_count(self.h, C.byref(n)), "ntl_events_count")
+        return n.value
+
+    def pairs(self):
+        """[(src, tgt, flags, n, anchor, gaps int32[n])] in first-seen order (the reference's dict order)."""
+        po = _lib.PairsOut()
+        self._check(self.lib.ntl_pairs_finish(self.h, C.byref(po)), "ntl_pairs_finish")
+        n = po.n_pairs
+        raw = _np_from(po.pairs, n * 10, np.uint32).reshape(-1, 10) if n else np.empty((0, 10), np.uint32)
+        gaps = _np_from(po.gaps, po.n_gaps, np.int32)
+        out = []
+        for row in raw:
+            goff = int(row[6]) | (int(row[7]) << 32)
+            out.append((int(row[0]), int(row[1]), int(row[2]), int(row[3]), int(row[4]), gaps[goff:goff + int(row[3])]))
+        return out
+
+    # ---- resident / timing (bench)
+    def reads_upload(self, batch):
+        self._check(self.lib.ntl_reads_upload(self.h, _ptr(batch.seq), _ptr(batch.offsets), len(batch)), "ntl_reads_upload")
+
+    def map_resident(self, prm, first_ordinal=0):
+        mo = _lib.MapOut()
+        self._check(self.lib.ntl_map_resident(self.h, first_ordinal, C.byref(prm), C.byref(mo)), "ntl_map_resident")
+        return {"reads": mo.n_reads, "mx": mo.n_mx, "hits": mo.n_hits, "runs": mo.n_runs, "events": mo.n_events}
+
+    def target_upload(self, batch):
+        rank = name_ranks(batch.names)
+        self._check(self.lib.ntl_target_upload(self.h, _ptr(batch.seq), _ptr(batch.offsets), len(batch), _ptr(rank)),
+                    "ntl_target_upload")
+
+    def index_build_resident(self, k, w):
+        self._check(self.lib.ntl_index_build_resident(self.h, k, w), "ntl_index_build_resident")
+
+    def timing_reset(self):
+        self._check(self.lib.ntl_timing_reset(self.h), "ntl_timing_reset")
+
+    def timing(self):
+        ms = (C.c_double * 16)()
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.ntl_timing(self.h, ms, C.byref(a), C.byref(b), C.byref(c)), "ntl_timing")
+        d = {name: ms[i] for i, name in enumerate(_lib.T_NAMES)}
+        d.update(launches=a.value, dense_launches=b.value, dense_bases=c.value)
+        return d
+
+    def sync(self):
+        self._check(self.lib.ntl_device_sync(self.h), "ntl_device_sync")

@@ -1,0 +1,564 @@
+// capi.cu -- the extern "C" boundary of libntlink_b200.so (declared in include/ntlink_b200.h).
+// Host orchestration only: batching, H2D/D2H staging through pinned memory, error translation. All compute is
+// in sketch.cu / map.cu. There is deliberately no CPU fallback: without a CUDA device ntl_init fails.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ntl {
+int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids);
+int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, uint32_t nreads, uint64_t first_ordinal,
+               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out);
+int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>& gaps);
+int read_len_device(ntl_ctx* c, const uint64_t* d_off, uint32_t nreads, DevBuf& out);
+
+// pinned host vector that can grow while keeping its contents
+struct HostVec {
+    PinnedBuf b;
+    size_t used = 0;   // bytes
+    int reserve(size_t bytes) {
+        if (bytes <= b.cap) return 0;
+        PinnedBuf nb;
+        if (nb.ensure(bytes + bytes / 2) != cudaSuccess) return -1;
+        if (used) memcpy(nb.p, b.p, used);
+        b.release();
+        b = nb;
+        return 0;
+    }
+    template <class T> T* at(size_t byte_off) { return (T*)((char*)b.p + byte_off); }
+};
+
+struct Results {
+    // sketch
+    HostVec sk_hash, sk_posf, sk_off;
+    // map
+    HostVec hit_off, nruns, runs, hits, ev_off, ev_cnt, events;
+    // pairs
+    std::vector<ntl_pair> pairs;
+    std::vector<int32_t> gaps;
+    // resident inputs (bench)
+    DevBuf r_seq, r_off, r_len; uint32_t r_nreads = 0; uint64_t r_bases = 0;
+    DevBuf t_seq, t_off, t_ctg; uint32_t t_ncontig = 0; uint64_t t_bases = 0;
+    std::vector<uint32_t> t_len, t_rank;
+    DevBuf stage_off, ctg_ids, read_len, in_hash, in_posf, in_ctg;
+    PinnedBuf h_off;
+};
+}  // namespace ntl
+
+using namespace ntl;
+
+static Results* res_of(ntl_ctx* c) { return static_cast<Results*>(c->res); }
+
+static int finish_call(ntl_ctx* c) {
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    collect_timing(c);
+    return NTL_OK;
+}
+
+// split [0, nseq) into batches of at most batch_bases bases (a single longer sequence forms its own batch)
+static void plan_batches(const uint64_t* offsets, uint32_t nseq, uint64_t batch_bases, std::vector<uint32_t>& bounds) {
+    bounds.clear();
+    bounds.push_back(0);
+    uint32_t b = 0;
+    while (b < nseq) {
+        uint32_t e = b + 1;
+        while (e < nseq && offsets[e + 1] - offsets[b] <= batch_bases) e++;
+        bounds.push_back(e);
+        b = e;
+    }
+}
+
+// copy sequences [b, e) to the device: ASCII into c->d_seq and rebased offsets into c->d_off
+static int stage_batch(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t b, uint32_t e, uint64_t* nbases_out) {
+    Results* R = res_of(c);
+    const uint64_t base = offsets[b], nb = offsets[e] - base;
+    const uint32_t ns = e - b;
+    if (nb >= (1ull << 32) - 4096) { c->err = "a single sequence/batch exceeds 4 Gbp"; return NTL_ERR_ARG; }
+    NTL_CUDA(c, c->d_seq.ensure(nb + 256));
+    NTL_CUDA(c, c->d_off.ensure(((size_t)ns + 1) * 8));
+    NTL_CUDA(c, R->h_off.ensure(((size_t)ns + 1) * 8));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));      // h_off may still be in flight from the previous batch
+    uint64_t* ho = R->h_off.as<uint64_t>();
+    for (uint32_t i = 0; i <= ns; i++) ho[i] = offsets[b + i] - base;
+    if (nb) NTL_CUDA(c, cudaMemcpyAsync(c->d_seq.p, seq + base, nb, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(c->d_off.p, ho, ((size_t)ns + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    *nbases_out = nb;
+    return NTL_OK;
+}
+
+extern "C" {
+
+int ntl_version(void) { return 100; }
+
+int ntl_init(int device, ntl_ctx** out) {
+    if (!out) return NTL_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NTL_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return NTL_ERR_CUDA;
+    ntl_ctx* c = new ntl_ctx();
+    c->res = new Results();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete res_of(c); delete c; return NTL_ERR_CUDA; }
+    for (int i = 0; i < 2 * T_NUM; i++) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < T_NUM; i++) { c->ev_used[i] = false; c->ms_accum[i] = 0; }
+    *out = c;
+    return NTL_OK;
+}
+
+void ntl_destroy(ntl_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Results* R = res_of(c);
+    SketchWork& W = c->sw;
+    DevBuf* sb[] = {&W.packed, &W.scnt, &W.strip_off, &W.blocksums, &W.slots, &W.cnt, &W.nv, &W.vbase, &W.ovf_off, &W.sel,
+                    &W.selcnt, &W.selbase, &W.gaps, &W.gap_head, &W.extras, &W.has_cand, &W.status, &W.tbl};
+    for (DevBuf* b : sb) b->release();
+    MapWork& M = c->mw;
+    DevBuf* mb[] = {&M.hit_tmp, &M.hit_flag, &M.hit_pref, &M.hits, &M.runs, &M.mark, &M.hit_off, &M.nruns, &M.events,
+                    &M.status, &M.read_len, &M.ev_cnt, &M.blocksums};
+    for (DevBuf* b : mb) b->release();
+    DevBuf* ib[] = {&c->index.table, &c->index.special, &c->index.ctg_len, &c->index.name_rank, &c->index.dupflag,
+                    &c->d_seq, &c->d_off, &c->dsk.hash, &c->dsk.posf, &c->dsk.mx_off, &c->tl_events,
+                    &R->r_seq, &R->r_off, &R->r_len, &R->t_seq, &R->t_off, &R->t_ctg, &R->stage_off, &R->ctg_ids,
+                    &R->read_len, &R->in_hash, &R->in_posf, &R->in_ctg};
+    for (DevBuf* b : ib) b->release();
+    HostVec* hv[] = {&R->sk_hash, &R->sk_posf, &R->sk_off, &R->hit_off, &R->nruns, &R->runs, &R->hits, &R->ev_off,
+                     &R->ev_cnt, &R->events};
+    for (HostVec* v : hv) v->b.release();
+    R->h_off.release();
+    c->h_status.release();
+    for (int i = 0; i < 2 * T_NUM; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete R;
+    delete c;
+}
+
+const char* ntl_last_error(const ntl_ctx* c) { return c ? c->err.c_str() : "no context (ntl_init failed: no CUDA device?)"; }
+
+int ntl_set_option(ntl_ctx* c, const char* name, double value) {
+    if (!c || !name) return NTL_ERR_ARG;
+    if (!strcmp(name, "strip_len")) {
+        uint32_t v = (uint32_t)value;
+        if (v < 8 || v > 65536 || (v & 7)) { c->err = "strip_len must be a multiple of 8 in [8, 65536]"; return NTL_ERR_ARG; }
+        c->strip_len = v;
+    } else if (!strcmp(name, "cand_c")) {
+        if (!(value > 0)) { c->err = "cand_c must be positive"; return NTL_ERR_ARG; }
+        c->cand_c = value;
+    } else if (!strcmp(name, "batch_bases")) {
+        if (value < 1024 || value > 3.9e9) { c->err = "batch_bases out of range"; return NTL_ERR_ARG; }
+        c->batch_bases = (uint64_t)value;
+    } else { c->err = std::string("unknown option ") + name; return NTL_ERR_ARG; }
+    return NTL_OK;
+}
+
+// ------------------------------------------------------------------------------------------- sketch
+static int sketch_to_host(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t nseq, int k, int w,
+                          ntl_sketch_out* out, bool build_index, const uint32_t* name_rank) {
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    std::vector<uint32_t> bounds;
+    plan_batches(offsets, nseq, c->batch_bases, bounds);
+    R->sk_hash.used = R->sk_posf.used = R->sk_off.used = 0;
+    if (R->sk_off.reserve(((size_t)nseq + 1) * 8)) { c->err = "pinned alloc failed"; return NTL_ERR_CUDA; }
+    uint64_t* seq_off = R->sk_off.at<uint64_t>(0);
+    seq_off[0] = 0;
+    uint64_t total = 0;
+    std::vector<uint32_t> tmp_off;
+    // when building the index from a multi-batch target the triples are collected on the device
+    uint64_t idx_n = 0;
+    if (build_index && bounds.size() > 2) {
+        c->err = "target does not fit one device batch: raise the batch_bases option (max 3.9e9)";
+        return NTL_ERR_ARG;
+    }
+    for (size_t bi = 0; bi + 1 < bounds.size(); bi++) {
+        const uint32_t b = bounds[bi], e = bounds[bi + 1];
+        uint64_t nb = 0;
+        tick(c, T_TOTAL);
+        NTL_TRY(stage_batch(c, seq, offsets, b, e, &nb));
+        NTL_TRY(sketch_device(c, c->d_seq.as<uint8_t>(), c->d_off.as<uint64_t>(), e - b, nb, (uint32_t)k, (uint32_t)w, c->dsk));
+        const uint32_t n = c->dsk.n_mx;
+        if (out) {
+            R->sk_hash.used = total * 8; R->sk_posf.used = total * 4;
+            if (R->sk_hash.reserve((total + n + 1) * 8) || R->sk_posf.reserve((total + n + 1) * 4)) { c->err = "pinned alloc failed"; return NTL_ERR_CUDA; }
+            tmp_off.resize((size_t)(e - b) + 1);
+            if (n) {
+                NTL_CUDA(c, cudaMemcpyAsync(R->sk_hash.at<uint64_t>(total * 8), c->dsk.hash.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+                NTL_CUDA(c, cudaMemcpyAsync(R->sk_posf.at<uint32_t>(total * 4), c->dsk.posf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+            }
+            NTL_CUDA(c, cudaMemcpyAsync(tmp_off.data(), c->dsk.mx_off.p, ((size_t)(e - b) + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (build_index) {
+            // contig ids (global) for this batch's minimizers, appended to the device-side triple arrays
+            NTL_TRY(expand_contig_ids(c, c->dsk, R->ctg_ids));
+            // grow in_* preserving contents
+            DevBuf* dst[3] = {&R->in_hash, &R->in_posf, &R->in_ctg};
+            const size_t esz[3] = {8, 4, 4};
+            for (int a = 0; a < 3; a++) {
+                const size_t need = (idx_n + n + 1) * esz[a];
+                if (need > dst[a]->cap) {
+                    DevBuf nbuf;
+                    NTL_CUDA(c, nbuf.ensure(need + need / 2));
+                    if (idx_n) NTL_CUDA(c, cudaMemcpyAsync(nbuf.p, dst[a]->p, idx_n * esz[a], cudaMemcpyDeviceToDevice, c->stream));
+                    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+                    dst[a]->release();
+                    *dst[a] = nbuf;
+                }
+            }
+            if (n) {
+                NTL_CUDA(c, cudaMemcpyAsync(R->in_hash.as<uint64_t>() + idx_n, c->dsk.hash.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+                NTL_CUDA(c, cudaMemcpyAsync(R->in_posf.as<uint32_t>() + idx_n, c->dsk.posf.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+                NTL_CUDA(c, cudaMemcpyAsync(R->in_ctg.as<uint32_t>() + idx_n, R->ctg_ids.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            idx_n += n;
+        }
+        tock(c, T_TOTAL);
+        NTL_TRY(finish_call(c));
+        if (out) {
+            for (uint32_t i = 0; i < e - b; i++) seq_off[b + i + 1] = total + tmp_off[i + 1];
+        }
+        total += n;
+    }
+    if (out) {
+        out->n_mx = total; out->nseq = nseq; out->reserved = 0;
+        out->hash = R->sk_hash.at<uint64_t>(0); out->pos_strand = R->sk_posf.at<uint32_t>(0); out->seq_off = seq_off;
+    }
+    if (build_index) {
+        std::vector<uint32_t> len(nseq);
+        for (uint32_t i = 0; i < nseq; i++) len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+        NTL_TRY(index_build_device(c, R->in_hash.as<uint64_t>(), R->in_ctg.as<uint32_t>(), R->in_posf.as<uint32_t>(), idx_n,
+                                   len.data(), name_rank, nseq));
+        NTL_TRY(finish_call(c));
+    }
+    return NTL_OK;
+}
+
+int ntl_sketch(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t nseq, int k, int w, ntl_sketch_out* out) {
+    if (!c || !out || (!seq && nseq) || !offsets || k <= 0 || w <= 0) { if (c) c->err = "ntl_sketch: bad argument"; return NTL_ERR_ARG; }
+    return sketch_to_host(c, seq, offsets, nseq, k, w, out, false, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------- index
+int ntl_index_build(ntl_ctx* c, const uint64_t* hash, const uint32_t* contig, const uint32_t* pos_strand, uint64_t n,
+                    const uint32_t* contig_len, const uint32_t* name_rank, uint32_t ncontig) {
+    if (!c || (n && (!hash || !contig || !pos_strand)) || !contig_len || !name_rank) { if (c) c->err = "ntl_index_build: bad argument"; return NTL_ERR_ARG; }
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    NTL_CUDA(c, R->in_hash.ensure(n * 8 + 8));
+    NTL_CUDA(c, R->in_posf.ensure(n * 4 + 4));
+    NTL_CUDA(c, R->in_ctg.ensure(n * 4 + 4));
+    if (n) {
+        NTL_CUDA(c, cudaMemcpyAsync(R->in_hash.p, hash, n * 8, cudaMemcpyHostToDevice, c->stream));
+        NTL_CUDA(c, cudaMemcpyAsync(R->in_posf.p, pos_strand, n * 4, cudaMemcpyHostToDevice, c->stream));
+        NTL_CUDA(c, cudaMemcpyAsync(R->in_ctg.p, contig, n * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    NTL_TRY(index_build_device(c, R->in_hash.as<uint64_t>(), R->in_ctg.as<uint32_t>(), R->in_posf.as<uint32_t>(), n, contig_len,
+                               name_rank, ncontig));
+    return finish_call(c);
+}
+
+int ntl_index_build_device(ntl_ctx* c, const void* d_hash, const void* d_contig, const void* d_pos_strand, uint64_t n,
+                           const uint32_t* contig_len, const uint32_t* name_rank, uint32_t ncontig) {
+    if (!c || !contig_len || !name_rank) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    NTL_TRY(index_build_device(c, (const uint64_t*)d_hash, (const uint32_t*)d_contig, (const uint32_t*)d_pos_strand, n,
+                               contig_len, name_rank, ncontig));
+    return finish_call(c);
+}
+
+int ntl_index_build_from_sequences(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t ncontig, int k, int w,
+                                   const uint32_t* name_rank, ntl_sketch_out* sketch_out) {
+    if (!c || (!seq && ncontig) || !offsets || !name_rank || k <= 0 || w <= 0) { if (c) c->err = "ntl_index_build_from_sequences: bad argument"; return NTL_ERR_ARG; }
+    return sketch_to_host(c, seq, offsets, ncontig, k, w, sketch_out, true, name_rank);
+}
+
+int ntl_index_stats(ntl_ctx* c, uint64_t* n_inserted, uint64_t* n_unique, uint64_t* table_slots) {
+    if (!c || !c->index.built) { if (c) c->err = "no index"; return NTL_ERR_STATE; }
+    cudaSetDevice(c->device);
+    unsigned long long u = 0;
+    NTL_CUDA(c, cudaMemcpy(&u, (char*)c->index.special.p + sizeof(IdxSpecial), 8, cudaMemcpyDeviceToHost));
+    IdxSpecial sp;
+    NTL_CUDA(c, cudaMemcpy(&sp, c->index.special.p, sizeof sp, cudaMemcpyDeviceToHost));
+    if (n_inserted) *n_inserted = c->index.n_inserted;
+    if (n_unique) *n_unique = u + (sp.count == 1 ? 1 : 0);
+    if (table_slots) *table_slots = c->index.slots;
+    return NTL_OK;
+}
+
+int ntl_device_sketch_arrays(ntl_ctx* c, uint64_t* n_mx, void** d_hash, void** d_pos_strand, void** d_seq_off) {
+    if (!c) return NTL_ERR_ARG;
+    if (n_mx) *n_mx = c->dsk.n_mx;
+    if (d_hash) *d_hash = c->dsk.hash.p;
+    if (d_pos_strand) *d_pos_strand = c->dsk.posf.p;
+    if (d_seq_off) *d_seq_off = c->dsk.mx_off.p;
+    return NTL_OK;
+}
+
+// ------------------------------------------------------------------------------------------- mapping
+static int append_map_results(ntl_ctx* c, uint32_t rb, uint32_t nreads, const MapStatus& cs, uint64_t log_base,
+                              uint64_t& hits_total, uint64_t& ev_total) {
+    Results* R = res_of(c);
+    MapWork& M = c->mw;
+    const uint32_t nh = cs.n_hits, ne = cs.n_events;
+    if (hits_total + nh >= (1ull << 32) || ev_total + ne >= (1ull << 32)) { c->err = "more than 4G hits in one call: split the call"; return NTL_ERR_ARG; }
+    R->runs.used = hits_total * sizeof(ntl_run); R->hits.used = hits_total * sizeof(ntl_hit);
+    R->events.used = ev_total * sizeof(ntl_event);
+    if (R->runs.reserve((hits_total + nh + 1) * sizeof(ntl_run)) || R->hits.reserve((hits_total + nh + 1) * sizeof(ntl_hit)) ||
+        R->events.reserve((ev_total + ne + 1) * sizeof(ntl_event))) { c->err = "pinned alloc failed"; return NTL_ERR_CUDA; }
+    uint32_t* hit_off = R->hit_off.at<uint32_t>(0) + rb;
+    uint32_t* nruns = R->nruns.at<uint32_t>(0) + rb;
+    uint32_t* ev_off = R->ev_off.at<uint32_t>(0) + rb;
+    uint32_t* ev_cnt = R->ev_cnt.at<uint32_t>(0) + rb;
+    const uint32_t* d_evblock = M.ev_cnt.as<uint32_t>();
+    const uint32_t* d_ev_cnt = d_evblock + 2 * ((size_t)nreads + 2);
+    const uint32_t* d_ev_pref = d_evblock + 3 * ((size_t)nreads + 2);
+    NTL_CUDA(c, cudaMemcpyAsync(hit_off, M.hit_off.p, ((size_t)nreads + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(nruns, M.nruns.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(ev_off, d_ev_pref, ((size_t)nreads + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(ev_cnt, d_ev_cnt, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (nh) {
+        NTL_CUDA(c, cudaMemcpyAsync(R->runs.at<ntl_run>(hits_total * sizeof(ntl_run)), M.runs.p, (size_t)nh * sizeof(ntl_run), cudaMemcpyDeviceToHost, c->stream));
+        NTL_CUDA(c, cudaMemcpyAsync(R->hits.at<ntl_hit>(hits_total * sizeof(ntl_hit)), M.hits.p, (size_t)nh * sizeof(ntl_hit), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (ne)
+        NTL_CUDA(c, cudaMemcpyAsync(R->events.at<ntl_event>(ev_total * sizeof(ntl_event)), c->tl_events.as<Event>() + log_base,
+                                    (size_t)ne * sizeof(ntl_event), cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (hits_total || ev_total) {
+        for (uint32_t i = 0; i <= nreads; i++) { hit_off[i] += (uint32_t)hits_total; ev_off[i] += (uint32_t)ev_total; }
+    }
+    hits_total += nh; ev_total += ne;
+    return NTL_OK;
+}
+
+static int begin_map_results(ntl_ctx* c, uint32_t nreads) {
+    Results* R = res_of(c);
+    HostVec* v[] = {&R->hit_off, &R->nruns, &R->ev_off, &R->ev_cnt};
+    for (HostVec* h : v) { h->used = 0; if (h->reserve(((size_t)nreads + 2) * 4)) { c->err = "pinned alloc failed"; return NTL_ERR_CUDA; } }
+    R->runs.used = R->hits.used = R->events.used = 0;
+    R->hit_off.at<uint32_t>(0)[0] = 0; R->ev_off.at<uint32_t>(0)[0] = 0;
+    return NTL_OK;
+}
+
+static void fill_map_out(ntl_ctx* c, ntl_map_out* out, uint32_t nreads, uint64_t n_mx, uint64_t hits, uint64_t runs, uint64_t events) {
+    Results* R = res_of(c);
+    out->n_reads = nreads; out->reserved = 0; out->n_mx = n_mx; out->n_hits = hits; out->n_runs = runs; out->n_events = events;
+    out->hit_off = R->hit_off.at<uint32_t>(0); out->nruns = R->nruns.at<uint32_t>(0);
+    out->runs = R->runs.at<ntl_run>(0); out->hits = R->hits.at<ntl_hit>(0);
+    out->ev_off = R->ev_off.at<uint32_t>(0); out->ev_cnt = R->ev_cnt.at<uint32_t>(0); out->events = R->events.at<ntl_event>(0);
+}
+
+int ntl_map_reads(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t nreads, uint64_t first_read_ordinal,
+                  const ntl_params* prm, ntl_map_out* out) {
+    if (!c || (!seq && nreads) || !offsets || !prm || !out || prm->k <= 0 || prm->w <= 0) { if (c) c->err = "ntl_map_reads: bad argument"; return NTL_ERR_ARG; }
+    if (!c->index.built) { c->err = "ntl_map_reads: no target index"; return NTL_ERR_STATE; }
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    NTL_TRY(begin_map_results(c, nreads));
+    std::vector<uint32_t> bounds;
+    plan_batches(offsets, nreads, c->batch_bases, bounds);
+    uint64_t hits_total = 0, ev_total = 0, mx_total = 0, runs_total = 0;
+    for (size_t bi = 0; bi + 1 < bounds.size(); bi++) {
+        const uint32_t b = bounds[bi], e = bounds[bi + 1];
+        uint64_t nb = 0;
+        tick(c, T_TOTAL);
+        NTL_TRY(stage_batch(c, seq, offsets, b, e, &nb));
+        NTL_TRY(sketch_device(c, c->d_seq.as<uint8_t>(), c->d_off.as<uint64_t>(), e - b, nb, (uint32_t)prm->k, (uint32_t)prm->w, c->dsk));
+        NTL_TRY(read_len_device(c, c->d_off.as<uint64_t>(), e - b, R->read_len));
+        MapStatus cs; uint64_t log_base = 0;
+        NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), e - b, first_read_ordinal + b, prm, &cs, &log_base));
+        tock(c, T_TOTAL);
+        NTL_TRY(append_map_results(c, b, e - b, cs, log_base, hits_total, ev_total));
+        collect_timing(c);
+        mx_total += c->dsk.n_mx; runs_total += cs.n_runs;
+    }
+    fill_map_out(c, out, nreads, mx_total, hits_total, runs_total, ev_total);
+    return NTL_OK;
+}
+
+int ntl_map_sketch(ntl_ctx* c, const uint64_t* hash, const uint32_t* pos_strand, const uint64_t* mx_off,
+                   const uint32_t* read_len, uint32_t nreads, uint64_t first_read_ordinal, const ntl_params* prm,
+                   ntl_map_out* out) {
+    if (!c || !mx_off || !read_len || !prm || !out || prm->k <= 0) { if (c) c->err = "ntl_map_sketch: bad argument"; return NTL_ERR_ARG; }
+    if (!c->index.built) { c->err = "ntl_map_sketch: no target index"; return NTL_ERR_STATE; }
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    NTL_TRY(begin_map_results(c, nreads));
+    // batches of at most 2^28 minimizers
+    uint64_t hits_total = 0, ev_total = 0, runs_total = 0;
+    uint32_t b = 0;
+    std::vector<uint32_t> off32;
+    if (nreads == 0) { fill_map_out(c, out, 0, 0, 0, 0, 0); return NTL_OK; }
+    while (b < nreads) {
+        uint32_t e = b + 1;
+        while (e < nreads && mx_off[e + 1] - mx_off[b] <= (1ull << 28)) e++;
+        const uint64_t m0 = mx_off[b], n = mx_off[e] - m0;
+        if (n >= (1ull << 31)) { c->err = "a single read has too many minimizers"; return NTL_ERR_ARG; }
+        const uint32_t nr = e - b;
+        off32.resize((size_t)nr + 1);
+        for (uint32_t i = 0; i <= nr; i++) off32[i] = (uint32_t)(mx_off[b + i] - m0);
+        DeviceSketch& sk = c->dsk;
+        NTL_CUDA(c, sk.hash.ensure(n * 8 + 8));
+        NTL_CUDA(c, sk.posf.ensure(n * 4 + 4));
+        NTL_CUDA(c, sk.mx_off.ensure(((size_t)nr + 1) * 4));
+        NTL_CUDA(c, R->read_len.ensure(((size_t)nr + 1) * 4));
+        tick(c, T_TOTAL);
+        if (n) {
+            NTL_CUDA(c, cudaMemcpyAsync(sk.hash.p, hash + m0, n * 8, cudaMemcpyHostToDevice, c->stream));
+            NTL_CUDA(c, cudaMemcpyAsync(sk.posf.p, pos_strand + m0, n * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        NTL_CUDA(c, cudaMemcpyAsync(sk.mx_off.p, off32.data(), ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+        if (nr) NTL_CUDA(c, cudaMemcpyAsync(R->read_len.p, read_len + b, (size_t)nr * 4, cudaMemcpyHostToDevice, c->stream));
+        sk.n_mx = (uint32_t)n; sk.nseq = nr;
+        MapStatus cs; uint64_t log_base = 0;
+        NTL_TRY(map_device(c, sk, R->read_len.as<uint32_t>(), nr, first_read_ordinal + b, prm, &cs, &log_base));
+        tock(c, T_TOTAL);
+        NTL_TRY(append_map_results(c, b, nr, cs, log_base, hits_total, ev_total));
+        collect_timing(c);
+        runs_total += cs.n_runs;
+        b = e;
+    }
+    fill_map_out(c, out, nreads, mx_off[nreads] - mx_off[0], hits_total, runs_total, ev_total);
+    return NTL_OK;
+}
+
+// ------------------------------------------------------------------------------------------- pairs
+int ntl_events_reset(ntl_ctx* c) { if (!c) return NTL_ERR_ARG; c->tl_n_events = 0; return NTL_OK; }
+int ntl_events_count(ntl_ctx* c, uint64_t* n) { if (!c || !n) return NTL_ERR_ARG; *n = c->tl_n_events; return NTL_OK; }
+int ntl_events_device(ntl_ctx* c, uint64_t* n, void** d_events) {
+    if (!c) return NTL_ERR_ARG;
+    if (n) *n = c->tl_n_events;
+    if (d_events) *d_events = c->tl_events.p;
+    return NTL_OK;
+}
+
+static int events_append_impl(ntl_ctx* c, const void* src, uint64_t n, cudaMemcpyKind kind) {
+    cudaSetDevice(c->device);
+    if (!n) return NTL_OK;
+    const size_t keep = c->tl_n_events * sizeof(Event), need = (c->tl_n_events + n + 1) * sizeof(Event);
+    if (need > c->tl_events.cap) {
+        DevBuf nb;
+        NTL_CUDA(c, nb.ensure(need + need / 2));
+        if (keep) NTL_CUDA(c, cudaMemcpyAsync(nb.p, c->tl_events.p, keep, cudaMemcpyDeviceToDevice, c->stream));
+        NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->tl_events.release();
+        c->tl_events = nb;
+    }
+    NTL_CUDA(c, cudaMemcpyAsync(c->tl_events.as<Event>() + c->tl_n_events, src, n * sizeof(Event), kind, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->tl_n_events += n;
+    return NTL_OK;
+}
+int ntl_events_append(ntl_ctx* c, const ntl_event* events, uint64_t n) {
+    if (!c || (n && !events)) return NTL_ERR_ARG;
+    return events_append_impl(c, events, n, cudaMemcpyHostToDevice);
+}
+int ntl_events_append_device(ntl_ctx* c, const void* d_events, uint64_t n) {
+    if (!c || (n && !d_events)) return NTL_ERR_ARG;
+    return events_append_impl(c, d_events, n, cudaMemcpyDeviceToDevice);
+}
+
+int ntl_pairs_finish(ntl_ctx* c, ntl_pairs_out* out) {
+    if (!c || !out) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    NTL_TRY(tally_device(c, R->pairs, R->gaps));
+    collect_timing(c);
+    out->n_pairs = R->pairs.size(); out->n_gaps = R->gaps.size();
+    out->pairs = R->pairs.data(); out->gaps = R->gaps.data();
+    return NTL_OK;
+}
+
+// ------------------------------------------------------------------------------------------- resident (bench)
+int ntl_reads_upload(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t nreads) {
+    if (!c || (!seq && nreads) || !offsets) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    const uint64_t nb = offsets[nreads] - offsets[0];
+    if (nb >= (1ull << 32) - 4096) { c->err = "resident batch exceeds 4 Gbp"; return NTL_ERR_ARG; }
+    std::vector<uint64_t> ho((size_t)nreads + 1);
+    for (uint32_t i = 0; i <= nreads; i++) ho[i] = offsets[i] - offsets[0];
+    NTL_CUDA(c, R->r_seq.ensure(nb + 256));
+    NTL_CUDA(c, R->r_off.ensure(((size_t)nreads + 1) * 8));
+    if (nb) NTL_CUDA(c, cudaMemcpyAsync(R->r_seq.p, seq + offsets[0], nb, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(R->r_off.p, ho.data(), ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    R->r_nreads = nreads; R->r_bases = nb;
+    return NTL_OK;
+}
+
+int ntl_map_resident(ntl_ctx* c, uint64_t first_read_ordinal, const ntl_params* prm, ntl_map_out* counts) {
+    if (!c || !prm) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    if (!R->r_nreads) { c->err = "ntl_map_resident: no resident reads"; return NTL_ERR_STATE; }
+    tick(c, T_TOTAL);
+    NTL_TRY(sketch_device(c, R->r_seq.as<uint8_t>(), R->r_off.as<uint64_t>(), R->r_nreads, R->r_bases, (uint32_t)prm->k,
+                          (uint32_t)prm->w, c->dsk));
+    NTL_TRY(read_len_device(c, R->r_off.as<uint64_t>(), R->r_nreads, R->read_len));
+    MapStatus cs; uint64_t log_base = 0;
+    NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), R->r_nreads, first_read_ordinal, prm, &cs, &log_base));
+    tock(c, T_TOTAL);
+    NTL_TRY(finish_call(c));
+    if (counts) {
+        memset(counts, 0, sizeof *counts);
+        counts->n_reads = R->r_nreads; counts->n_mx = c->dsk.n_mx; counts->n_hits = cs.n_hits; counts->n_runs = cs.n_runs;
+        counts->n_events = cs.n_events;
+    }
+    return NTL_OK;
+}
+
+int ntl_target_upload(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t ncontig, const uint32_t* name_rank) {
+    if (!c || (!seq && ncontig) || !offsets || !name_rank) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    const uint64_t nb = offsets[ncontig] - offsets[0];
+    if (nb >= (1ull << 32) - 4096) { c->err = "resident target exceeds 4 Gbp"; return NTL_ERR_ARG; }
+    std::vector<uint64_t> ho((size_t)ncontig + 1);
+    R->t_len.resize(ncontig); R->t_rank.assign(name_rank, name_rank + ncontig);
+    for (uint32_t i = 0; i <= ncontig; i++) ho[i] = offsets[i] - offsets[0];
+    for (uint32_t i = 0; i < ncontig; i++) R->t_len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+    NTL_CUDA(c, R->t_seq.ensure(nb + 256));
+    NTL_CUDA(c, R->t_off.ensure(((size_t)ncontig + 1) * 8));
+    if (nb) NTL_CUDA(c, cudaMemcpyAsync(R->t_seq.p, seq + offsets[0], nb, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(R->t_off.p, ho.data(), ((size_t)ncontig + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    R->t_ncontig = ncontig; R->t_bases = nb;
+    return NTL_OK;
+}
+
+int ntl_index_build_resident(ntl_ctx* c, int k, int w) {
+    if (!c || k <= 0 || w <= 0) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    if (!R->t_ncontig) { c->err = "ntl_index_build_resident: no resident target"; return NTL_ERR_STATE; }
+    NTL_TRY(sketch_device(c, R->t_seq.as<uint8_t>(), R->t_off.as<uint64_t>(), R->t_ncontig, R->t_bases, (uint32_t)k, (uint32_t)w, c->dsk));
+    NTL_TRY(expand_contig_ids(c, c->dsk, R->t_ctg));
+    NTL_TRY(index_build_device(c, c->dsk.hash.as<uint64_t>(), R->t_ctg.as<uint32_t>(), c->dsk.posf.as<uint32_t>(), c->dsk.n_mx,
+                               R->t_len.data(), R->t_rank.data(), R->t_ncontig));
+    return finish_call(c);
+}
+
+int ntl_timing_reset(ntl_ctx* c) {
+    if (!c) return NTL_ERR_ARG;
+    for (int i = 0; i < T_NUM; i++) c->ms_accum[i] = 0;
+    c->launches = 0; c->dense_launches = 0; c->dense_bases = 0;
+    return NTL_OK;
+}
+int ntl_timing(ntl_ctx* c, double* ms_accum, uint64_t* launches, uint64_t* dense_launches, uint64_t* dense_bases) {
+    if (!c) return NTL_ERR_ARG;
+    if (ms_accum) for (int i = 0; i < T_NUM; i++) ms_accum[i] = c->ms_accum[i];
+    if (launches) *launches = c->launches;
+    if (dense_launches) *dense_launches = c->dense_launches;
+    if (dense_bases) *dense_bases = c->dense_bases;
+    return NTL_OK;
+}
+int ntl_device_sync(ntl_ctx* c) {
+    if (!c) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NTL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// common.cuh -- context, device buffers and error plumbing shared by the translation units of libntlink_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ntlink_b200.h"
+#include "map_logic.cuh"
+#include "nthash.cuh"
+#include "sketch_logic.cuh"
+
+namespace ntl {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    // grows geometrically; contents are NOT preserved
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// device-side counters of one sketch pass (one 64-byte block, zeroed before every pass)
+struct SketchStatus {
+    uint32_t nstrips;       // strips of this batch
+    uint32_t pool_used;     // overflow-pool entries handed out
+    uint32_t ngaps;         // GapRec entries queued
+    uint32_t extras_used;   // gap minimizers reserved
+    uint32_t n_mx;          // total minimizers (after emit-scan)
+    uint32_t err;           // NTL_SKERR_* bits
+    uint32_t n_ovf;         // strips that overflowed their slots
+    uint32_t n_cand;        // total candidates (statistics)
+    uint32_t pad[8];
+};
+enum : uint32_t { SKERR_POOL = 1, SKERR_GAPS = 2, SKERR_EXTRAS = 4, SKERR_OUT = 8 };
+
+struct MapStatus {
+    uint32_t n_hits;        // index hits of the batch
+    uint32_t n_events;      // pair events written
+    uint32_t err;           // MAPERR_* bits
+    uint32_t n_runs;        // accepted (read, contig) runs
+    uint32_t pad[12];
+};
+enum : uint32_t { MAPERR_EVENTS = 1 };
+
+// per-stage device timings (CUDA events on ctx->stream), milliseconds; stage ids are NTL_T_* of the public header
+enum { T_PACK = NTL_T_PACK, T_DENSE = NTL_T_DENSE, T_SELECT = NTL_T_SELECT, T_GAP = NTL_T_GAP, T_EMIT = NTL_T_EMIT,
+       T_LOOKUP = NTL_T_LOOKUP, T_CHAIN = NTL_T_CHAIN, T_TALLY = NTL_T_TALLY, T_INDEX = NTL_T_INDEX,
+       T_TOTAL = NTL_T_TOTAL, T_NUM = NTL_T_NUM };
+
+struct SketchWork {           // device workspace of the sketch pipeline (reused across calls)
+    DevBuf packed, scnt, strip_off, blocksums, slots, cnt, nv, vbase, ovf_off, sel, selcnt, selbase,
+        gaps, gap_head, extras, has_cand, status, tbl;
+    uint32_t tbl_k = 0;       // k the device roll table was built for
+};
+
+struct DeviceSketch {         // result of a sketch pass, resident on the device
+    DevBuf hash;              // uint64 h1 per minimizer
+    DevBuf posf;              // uint32 pos | fwd << 31
+    DevBuf mx_off;            // uint32 [nseq + 1]
+    uint32_t n_mx = 0;
+    uint32_t nseq = 0;
+};
+
+struct TargetIndex {
+    DevBuf table, special, ctg_len, name_rank, dupflag;
+    uint64_t slots = 0;
+    uint32_t ncontig = 0;
+    uint64_t n_inserted = 0;
+    bool built = false;
+};
+
+struct MapWork {
+    DevBuf hit_tmp, hit_flag, hit_pref, hits, runs, mark, hit_off, nruns, events, status, read_len, ev_cnt, blocksums;
+};
+
+}  // namespace ntl
+
+struct ntl_ctx {
+    int device = 0;
+    void* res = nullptr;                   // ntl::Results (capi.cu): host result buffers, resident inputs
+    cudaStream_t stream = nullptr;
+    std::string err;
+    ntl::SketchWork sw;
+    ntl::MapWork mw;
+    ntl::TargetIndex index;
+    ntl::DevBuf d_seq, d_off;              // staging of the current batch (ASCII + offsets)
+    ntl::DeviceSketch dsk;                 // sketch of the current batch
+    ntl::PinnedBuf h_status;
+    // tuning knobs
+    uint32_t strip_len = 256;
+    double cand_c = 10.0;
+    uint64_t batch_bases = 1ull << 30;
+    // timing
+    cudaEvent_t ev[2 * ntl::T_NUM];
+    bool ev_used[ntl::T_NUM];
+    double ms_accum[ntl::T_NUM];           // accumulated since ntl_timing_reset
+    uint64_t launches = 0;                 // kernels launched since ntl_timing_reset
+    uint64_t dense_launches = 0;
+    uint64_t dense_bases = 0;
+    // tally state (pairs accumulated over calls)
+    ntl::DevBuf tl_events;                 // all events appended so far
+    uint64_t tl_n_events = 0;
+};
+
+#define NTL_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            char b__[512];                                                                       \
+            snprintf(b__, sizeof b__, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            (ctx)->err = b__;                                                                    \
+            return NTL_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define NTL_TRY(expr)                    \
+    do {                                 \
+        int r__ = (expr);                \
+        if (r__ != NTL_OK) return r__;   \
+    } while (0)
+
+namespace ntl {
+// implemented in sketch.cu
+int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
+                  uint32_t k, uint32_t w, DeviceSketch& out);
+// implemented in map.cu
+int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg, const uint32_t* d_posf, uint64_t n,
+                       const uint32_t* h_ctg_len, const uint32_t* h_name_rank, uint32_t ncontig);
+// scan utility (scan.cu): exclusive prefix sum of in[0..n) into out[0..n], out[n] = total; n read from the device
+int exclusive_scan_u32(ntl_ctx* c, const uint32_t* in, uint32_t* out, const uint32_t* n_dev, uint32_t n_max,
+                       DevBuf& blocksums);
+inline void tick(ntl_ctx* c, int stage) { cudaEventRecord(c->ev[2 * stage], c->stream); }
+inline void tock(ntl_ctx* c, int stage) { cudaEventRecord(c->ev[2 * stage + 1], c->stream); c->ev_used[stage] = true; }
+// after a stream synchronize: fold the recorded stage times into the accumulators
+inline void collect_timing(ntl_ctx* c) {
+    for (int s = 0; s < T_NUM; s++) {
+        if (!c->ev_used[s]) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev[2 * s], c->ev[2 * s + 1]) == cudaSuccess) c->ms_accum[s] += ms;
+        c->ev_used[s] = false;
+    }
+}
+}  // namespace ntl

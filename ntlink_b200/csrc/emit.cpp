@@ -1,0 +1,356 @@
+// emit.cpp -- host side of the drop-in boundary: byte-identical text emitters and the FASTA/FASTQ reader.
+//
+//   ntl_format_sketch_tsv   the TSV `indexlr --long [--pos] [--strand] [--len]` prints        
+//   ntl_format_verbose      <prefix>.verbose_mapping.tsv lines          bin/ntlink_pair.py:307-313,382-388
+//   ntl_format_paf          <prefix>.paf lines                          bin/ntlink_paf_output.py:9-135
+//   ntl_seqfile_*           readfq-style reader, id = first token       bin/read_fasta.py:6-46
+//
+// Pure host code (decimal formatting of GPU results); multi-threaded over reads because at genome scale
+// these files are gigabytes of text.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ntlink_b200.h"
+
+namespace {
+
+inline void put_u64(std::string& s, uint64_t v) {
+    char t[24];
+    int n = 0;
+    do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    char r[24];
+    for (int i = 0; i < n; i++) r[i] = t[n - 1 - i];
+    s.append(r, (size_t)n);
+}
+
+template <class F>
+void parallel_chunks(uint64_t n, int threads, F&& body /* (chunk_index, begin, end) */, int* nchunks_out) {
+    int T = threads < 1 ? 1 : threads;
+    if ((uint64_t)T > n) T = n ? (int)n : 1;
+    *nchunks_out = T;
+    if (T == 1) { body(0, (uint64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) {
+        const uint64_t b = n * (uint64_t)t / T, e = n * (uint64_t)(t + 1) / T;
+        th.emplace_back([&body, t, b, e]() { body(t, b, e); });
+    }
+    for (auto& x : th) x.join();
+}
+
+int64_t join_out(std::vector<std::string>& parts, char** out_buf) {
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    char* buf = (char*)malloc(total ? total : 1);
+    if (!buf) return NTL_ERR_ARG;
+    size_t o = 0;
+    for (auto& p : parts) { memcpy(buf + o, p.data(), p.size()); o += p.size(); }
+    *out_buf = buf;
+    return (int64_t)total;
+}
+
+struct PHit { uint32_t cpos, rpos; bool cfw, rfw; };
+
+inline bool consistent(const std::vector<PHit>& s, bool inc, size_t a, size_t b, const std::vector<uint32_t>& dups) {
+    auto is_dup = [&](uint32_t p) { return std::binary_search(dups.begin(), dups.end(), p); };
+    if (is_dup(s[a].cpos) || is_dup(s[b].cpos)) return true;
+    return inc ? s[a].rpos <= s[b].rpos : s[a].rpos >= s[b].rpos;
+}
+
+// bin/ntlink_paf_output.py:60-93 + 18-58: split the (ctg_pos, read_pos)-sorted hits into mapped blocks.
+// Returns false when the reference yields no block at all (neither direction is >= 75 % consistent).
+bool mapped_blocks(const std::vector<PHit>& s, std::vector<std::vector<PHit>>& blocks) {
+    const size_t n = s.size(), nt = n - 1;
+    std::vector<char> tinc(nt), tdec(nt);
+    std::vector<uint32_t> seen, dups;
+    bool all_inc = true, all_dec = true;
+    for (size_t i = 0; i < nt; i++) {
+        tinc[i] = s[i].rpos <= s[i + 1].rpos;
+        tdec[i] = s[i].rpos >= s[i + 1].rpos;
+        all_inc = all_inc && tinc[i];
+        all_dec = all_dec && tdec[i];
+        if (std::find(seen.begin(), seen.end(), s[i].cpos) != seen.end()) dups.push_back(s[i].cpos);
+        else seen.push_back(s[i].cpos);
+    }
+    if (std::find(seen.begin(), seen.end(), s[n - 1].cpos) != seen.end()) dups.push_back(s[n - 1].cpos);
+    if (all_inc || all_dec) { blocks.push_back(s); return true; }
+    std::sort(dups.begin(), dups.end());
+    size_t n_inc = 0;
+    for (size_t i = 0; i < nt; i++) n_inc += tinc[i] ? 1 : 0;
+    bool inc;
+    if (4 * n_inc >= 3 * nt) inc = true;                 // n_inc / nt >= 0.75
+    else if (4 * (nt - n_inc) >= 3 * nt) inc = false;    // (nt - n_inc) / nt >= 0.75
+    else return false;
+    const std::vector<char>& tr = inc ? tinc : tdec;
+    std::vector<char> brk(n, 0), flt(n, 0);
+    bool any = false;
+    auto is_dup = [&](uint32_t p) { return std::binary_search(dups.begin(), dups.end(), p); };
+    for (size_t i = 0; i < nt; i++) {
+        if (tr[i]) continue;
+        if (is_dup(s[i].cpos) || is_dup(s[i + 1].cpos)) continue;
+        if (i + 2 >= nt) { brk[i + 1] = 1; any = true; }
+        else if (consistent(s, inc, i, i + 2, dups)) { flt[i + 1] = 1; any = true; }
+        else if (i > 0 && consistent(s, inc, i - 1, i + 1, dups)) { flt[i] = 1; any = true; }
+        else { brk[i + 1] = 1; any = true; }
+    }
+    if (!any) { blocks.push_back(s); return true; }
+    std::vector<PHit> cur;
+    for (size_t i = 0; i < n; i++) {
+        if (flt[i]) continue;
+        if (brk[i]) { blocks.push_back(cur); cur.clear(); cur.push_back(s[i]); }
+        else cur.push_back(s[i]);
+    }
+    blocks.push_back(cur);
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ntl_format_sketch_tsv(const ntl_sketch_out* sk, const char* names, const uint64_t* name_off,
+                              const uint64_t* seq_len, int with_pos, int with_strand, int threads, char** out_buf) {
+    if (!sk || !names || !name_off || !out_buf) return NTL_ERR_ARG;
+    int nch = 1;
+    std::vector<std::string> parts((size_t)(threads < 1 ? 1 : threads));
+    parallel_chunks(sk->nseq, threads, [&](int t, uint64_t b, uint64_t e) {
+        std::string& s = parts[(size_t)t];
+        s.reserve((size_t)((sk->seq_off[e] - sk->seq_off[b]) * 30 + (e - b) * 48));
+        for (uint64_t i = b; i < e; i++) {
+            s.append(names + name_off[i], (size_t)(name_off[i + 1] - name_off[i]));
+            if (seq_len) { s.push_back('\t'); put_u64(s, seq_len[i]); }
+            s.push_back('\t');
+            for (uint64_t m = sk->seq_off[i]; m < sk->seq_off[i + 1]; m++) {
+                if (m != sk->seq_off[i]) s.push_back(' ');
+                put_u64(s, sk->hash[m]);
+                if (with_pos) { s.push_back(':'); put_u64(s, sk->pos_strand[m] & NTL_POS_MASK); }
+                if (with_strand) { s.push_back(':'); s.push_back((sk->pos_strand[m] & NTL_STRAND_BIT) ? '+' : '-'); }
+            }
+            s.push_back('\n');
+        }
+    }, &nch);
+    return join_out(parts, out_buf);
+}
+
+int64_t ntl_format_verbose(const ntl_map_out* m, const char* read_names, const uint64_t* read_name_off,
+                           const char* ctg_names, const uint64_t* ctg_name_off, int threads, char** out_buf) {
+    if (!m || !read_names || !read_name_off || !ctg_names || !ctg_name_off || !out_buf) return NTL_ERR_ARG;
+    int nch = 1;
+    std::vector<std::string> parts((size_t)(threads < 1 ? 1 : threads));
+    parallel_chunks(m->n_reads, threads, [&](int t, uint64_t b, uint64_t e) {
+        std::string& s = parts[(size_t)t];
+        for (uint64_t r = b; r < e; r++) {
+            const uint32_t nr = m->nruns[r];
+            if (!nr) continue;
+            const uint32_t base = m->hit_off[r];
+            for (uint32_t i = 0; i < nr; i++) {
+                const ntl_run run = m->runs[base + i];
+                s.append(read_names + read_name_off[r], (size_t)(read_name_off[r + 1] - read_name_off[r]));
+                s.push_back('\t');
+                s.append(ctg_names + ctg_name_off[run.ctg], (size_t)(ctg_name_off[run.ctg + 1] - ctg_name_off[run.ctg]));
+                s.push_back('\t');
+                put_u64(s, run.count);
+                s.push_back('\t');
+                for (uint32_t h = 0; h < run.count; h++) {
+                    const ntl_hit hit = m->hits[base + run.start + h];
+                    if (h) s.push_back(' ');
+                    put_u64(s, hit.ctg_pos_strand & NTL_POS_MASK);
+                    s.push_back(':');
+                    s.push_back((hit.ctg_pos_strand & NTL_STRAND_BIT) ? '+' : '-');
+                    s.push_back('_');
+                    put_u64(s, hit.read_pos_strand & NTL_POS_MASK);
+                    s.push_back(':');
+                    s.push_back((hit.read_pos_strand & NTL_STRAND_BIT) ? '+' : '-');
+                }
+                s.push_back('\n');
+            }
+        }
+    }, &nch);
+    return join_out(parts, out_buf);
+}
+
+int64_t ntl_format_paf(const ntl_map_out* m, const char* read_names, const uint64_t* read_name_off,
+                       const uint32_t* read_len, const char* ctg_names, const uint64_t* ctg_name_off,
+                       const uint32_t* ctg_len, int k, int threads, char** out_buf) {
+    if (!m || !read_names || !read_name_off || !read_len || !ctg_names || !ctg_name_off || !ctg_len || !out_buf)
+        return NTL_ERR_ARG;
+    int nch = 1;
+    std::vector<std::string> parts((size_t)(threads < 1 ? 1 : threads));
+    std::vector<int> failed((size_t)(threads < 1 ? 1 : threads), 0);
+    parallel_chunks(m->n_reads, threads, [&](int t, uint64_t b, uint64_t e) {
+        std::string& s = parts[(size_t)t];
+        std::vector<PHit> hits, srt;
+        std::vector<std::vector<PHit>> blocks;
+        for (uint64_t r = b; r < e; r++) {
+            const uint32_t nr = m->nruns[r];
+            if (!nr) continue;
+            const uint32_t base = m->hit_off[r];
+            for (uint32_t i = 0; i < nr; i++) {
+                const ntl_run run = m->runs[base + i];
+                hits.clear();
+                for (uint32_t h = 0; h < run.count; h++) {
+                    const ntl_hit hit = m->hits[base + run.start + h];
+                    PHit p;
+                    p.cpos = hit.ctg_pos_strand & NTL_POS_MASK; p.cfw = (hit.ctg_pos_strand & NTL_STRAND_BIT) != 0;
+                    p.rpos = hit.read_pos_strand & NTL_POS_MASK; p.rfw = (hit.read_pos_strand & NTL_STRAND_BIT) != 0;
+                    hits.push_back(p);
+                }
+                srt = hits;
+                std::stable_sort(srt.begin(), srt.end(), [](const PHit& a, const PHit& c) {
+                    return a.cpos != c.cpos ? a.cpos < c.cpos : a.rpos < c.rpos;
+                });
+                auto same = [](const PHit& a, const PHit& c) { return a.cpos == c.cpos && a.rpos == c.rpos; };
+                // paf:95-101: detailed check only if the read order is neither the sorted order nor its reverse
+                bool fwd_eq = true, rev_eq = true;
+                for (size_t q = 0; q < hits.size(); q++) {
+                    if (!same(hits[q], srt[q])) fwd_eq = false;
+                    if (!same(hits[q], srt[hits.size() - 1 - q])) rev_eq = false;
+                }
+                blocks.clear();
+                if (fwd_eq || rev_eq) blocks.push_back(srt);
+                else if (!mapped_blocks(srt, blocks)) continue;
+                for (const auto& blk : blocks) {
+                    size_t same_strand = 0;
+                    for (const auto& p : blk) same_strand += (p.cfw == p.rfw) ? 1 : 0;
+                    const char strand = (2 * same_strand >= blk.size()) ? '+' : '-';
+                    const PHit& f = blk.front(); const PHit& l = blk.back();
+                    const uint64_t ts = std::min(f.cpos, l.cpos), te = (uint64_t)std::max(f.cpos, l.cpos) + (uint64_t)k;
+                    const uint64_t qs = std::min(f.rpos, l.rpos), qe = (uint64_t)std::max(f.rpos, l.rpos) + (uint64_t)k;
+                    if (!(qs < qe) || qe > read_len[r]) { failed[(size_t)t] = 1; return; }   // paf:127-129
+                    s.append(read_names + read_name_off[r], (size_t)(read_name_off[r + 1] - read_name_off[r]));
+                    s.push_back('\t'); put_u64(s, read_len[r]);
+                    s.push_back('\t'); put_u64(s, qs);
+                    s.push_back('\t'); put_u64(s, qe);
+                    s.push_back('\t'); s.push_back(strand);
+                    s.push_back('\t');
+                    s.append(ctg_names + ctg_name_off[run.ctg], (size_t)(ctg_name_off[run.ctg + 1] - ctg_name_off[run.ctg]));
+                    s.push_back('\t'); put_u64(s, ctg_len[run.ctg]);
+                    s.push_back('\t'); put_u64(s, ts);
+                    s.push_back('\t'); put_u64(s, te);
+                    s.push_back('\t'); put_u64(s, blk.size());
+                    s.push_back('\t'); put_u64(s, te - ts);
+                    s.append("\t255\n");
+                }
+            }
+        }
+    }, &nch);
+    for (int f : failed) if (f) return NTL_ERR_ASSERT;
+    return join_out(parts, out_buf);
+}
+
+void ntl_buf_free(char* buf) { free(buf); }
+void ntl_free(void* p) { free(p); }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------- reader
+struct ntl_seqfile {
+    gzFile f = nullptr;
+    std::vector<char> buf;
+    size_t pos = 0, len = 0;
+    bool eof = false;
+    std::string pending;     // header line read ahead
+    bool have_pending = false;
+
+    bool fill() {
+        if (eof) return false;
+        if (buf.empty()) buf.resize(4u << 20);
+        int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (n <= 0) { eof = true; pos = len = 0; return false; }
+        pos = 0; len = (size_t)n;
+        return true;
+    }
+    // next line without its terminator; false at end of file
+    bool getline(std::string& line) {
+        line.clear();
+        bool got = false;
+        for (;;) {
+            if (pos >= len && !fill()) break;
+            got = true;
+            const char* p = buf.data() + pos;
+            const char* nl = (const char*)memchr(p, '\n', len - pos);
+            if (nl) { line.append(p, (size_t)(nl - p)); pos = (size_t)(nl - buf.data()) + 1; break; }
+            line.append(p, len - pos);
+            pos = len;
+        }
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return got;
+    }
+};
+
+extern "C" {
+
+int ntl_seqfile_open(const char* path, ntl_seqfile** out) {
+    if (!path || !out) return NTL_ERR_ARG;
+    ntl_seqfile* f = new ntl_seqfile();
+    f->f = strcmp(path, "-") ? gzopen(path, "rb") : gzdopen(0, "rb");
+    if (!f->f) { delete f; return NTL_ERR_ARG; }
+    gzbuffer(f->f, 1u << 20);
+    *out = f;
+    return NTL_OK;
+}
+
+int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_t** offsets_out, char** names_out,
+                     uint64_t** name_off_out, uint32_t* nseq_out) {
+    if (!f || !seq_out || !offsets_out || !names_out || !name_off_out || !nseq_out) return NTL_ERR_ARG;
+    std::string seq, names, line;
+    std::vector<uint64_t> offs(1, 0), noffs(1, 0);
+    for (;;) {
+        if (max_bases && seq.size() >= max_bases) break;
+        // find the next header (bin/read_fasta.py:10-16)
+        if (!f->have_pending) {
+            bool found = false;
+            while (f->getline(line)) {
+                if (!line.empty() && (line[0] == '>' || line[0] == '@')) { found = true; break; }
+            }
+            if (!found) break;
+            f->pending = line;
+        }
+        f->have_pending = false;
+        const std::string& hdr = f->pending;
+        size_t e = 1;
+        while (e < hdr.size() && hdr[e] != ' ' && hdr[e] != '\t' && hdr[e] != '\v' && hdr[e] != '\f' && hdr[e] != '\r') e++;
+        names.append(hdr, 1, e - 1);
+        noffs.push_back(names.size());
+        const size_t start = seq.size();
+        bool plus = false;
+        while (f->getline(line)) {
+            if (!line.empty() && (line[0] == '>' || line[0] == '@')) { f->pending = line; f->have_pending = true; break; }
+            if (!line.empty() && line[0] == '+') { plus = true; break; }
+            seq.append(line);
+        }
+        if (plus) {                           // FASTQ: as many quality characters as bases (read_fasta.py:36-43)
+            size_t q = 0;
+            const size_t need = seq.size() - start;
+            while (q < need && f->getline(line)) q += line.size();
+        }
+        offs.push_back(seq.size());
+    }
+    const uint32_t nseq = (uint32_t)(offs.size() - 1);
+    char* s = (char*)malloc(seq.size() + 64);
+    uint64_t* o = (uint64_t*)malloc(offs.size() * 8);
+    char* nm = (char*)malloc(names.size() + 1);
+    uint64_t* no = (uint64_t*)malloc(noffs.size() * 8);
+    if (!s || !o || !nm || !no) { free(s); free(o); free(nm); free(no); return NTL_ERR_ARG; }
+    memcpy(s, seq.data(), seq.size());
+    memset(s + seq.size(), 'N', 64);
+    memcpy(o, offs.data(), offs.size() * 8);
+    memcpy(nm, names.data(), names.size());
+    memcpy(no, noffs.data(), noffs.size() * 8);
+    *seq_out = s; *offsets_out = o; *names_out = nm; *name_off_out = no; *nseq_out = nseq;
+    return NTL_OK;
+}
+
+void ntl_seqfile_close(ntl_seqfile* f) {
+    if (!f) return;
+    if (f->f) gzclose(f->f);
+    delete f;
+}
+
+}  // extern "C"

@@ -1,0 +1,440 @@
+// map.cu -- target index, per-read lookup, anchor chaining, pair events and the pair tally on the device.
+// Replaces the mapping stage of bin/ntlink_pair.py (M1-M7 of SURVEY.md 8a); per-thread logic in map_logic.cuh.
+//
+// Kernels:
+//   k_index_insert / k_index_finalize   open-addressing table built with atomicCAS; a hash seen twice is flagged
+//                                       and dropped entirely (bin/ntlink_pair.py:204-209)
+//   k_expand_ctg                        contig id per target minimizer (from the per-contig offsets)
+//   k_lookup                            one probe (one 32-byte sector) per read minimizer
+//   k_compact_hits                      ordered compaction of the hits, per-read hit offsets
+//   k_chain                             one thread per read: z filter, noisy filter, runs, subsumption, merge
+//   k_events                            one thread per read: contig-pair observations in reference order
+//   k_compact_events                    append to the device event log
+//   k_tally_*                           edge table with atomics (n, anchor, first-seen), gap lists in read order
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ntl {
+
+namespace {
+
+inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------- index
+__global__ void k_index_insert(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ ctg,
+                               const uint32_t* __restrict__ posf, uint64_t n, IdxEntry* __restrict__ table,
+                               uint64_t mask, uint8_t* __restrict__ dupflag, IdxSpecial* __restrict__ special) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = hash[i];
+    if (key == NTL_EMPTY_KEY) {
+        if (atomicAdd(&special->count, 1u) == 0) { special->ctg = ctg[i]; special->posf = posf[i]; }
+        return;
+    }
+    uint64_t s = idx_slot(key, mask);
+    for (;;) {
+        const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&table[s].key),
+                                                  (unsigned long long)NTL_EMPTY_KEY, (unsigned long long)key);
+        if (prev == NTL_EMPTY_KEY) {
+            *reinterpret_cast<uint2*>(&table[s].ctg) = make_uint2(ctg[i], posf[i]);
+            return;
+        }
+        if (prev == key) { dupflag[s] = 1; return; }
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void k_index_finalize(IdxEntry* __restrict__ table, uint64_t slots, const uint8_t* __restrict__ dupflag,
+                                 unsigned long long* __restrict__ n_unique) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    if (table[s].key == NTL_EMPTY_KEY) return;
+    if (dupflag[s]) table[s].ctg = DUP_CTG;
+    else atomicAdd(n_unique, 1ull);
+}
+
+__global__ void k_expand_ctg(const uint32_t* __restrict__ mx_off, uint32_t nseq, uint32_t n_mx,
+                             uint32_t* __restrict__ ctg) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mx) return;
+    uint32_t lo = 0, hi = nseq;            // mx_off[lo] <= i < mx_off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (mx_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    ctg[i] = lo;
+}
+
+// ------------------------------------------------------------------------------------------- lookup
+__global__ void __launch_bounds__(256) k_lookup(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ posf,
+                                                uint32_t n, IndexView ix, Hit* __restrict__ tmp,
+                                                uint32_t* __restrict__ flag, uint32_t* __restrict__ n_dev) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_dev = n;
+    if (i >= n) return;
+    uint32_t ctg, cposf;
+    if (index_lookup(ix, hash[i], ctg, cposf)) {
+        Hit h; h.ctg = ctg; h.cposf = cposf; h.rposf = posf[i];
+        tmp[i] = h; flag[i] = 1;
+    } else flag[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_compact_hits(const Hit* __restrict__ tmp, const uint32_t* __restrict__ flag,
+                                                      const uint32_t* __restrict__ pref, uint32_t n,
+                                                      Hit* __restrict__ hits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) hits[pref[i]] = tmp[i];
+}
+
+__global__ void k_hit_offsets(const uint32_t* __restrict__ mx_off, const uint32_t* __restrict__ pref, uint32_t nreads,
+                              uint32_t* __restrict__ hit_off, MapStatus* __restrict__ st, uint32_t* __restrict__ nreads_dev) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) *nreads_dev = nreads;
+    if (r > nreads) return;
+    const uint32_t v = pref[mx_off[r]];
+    hit_off[r] = v;
+    if (r == nreads) st->n_hits = v;
+}
+
+__global__ void k_read_len(const uint64_t* __restrict__ seq_off, uint32_t nreads, uint32_t* __restrict__ read_len) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nreads) read_len[r] = (uint32_t)(seq_off[r + 1] - seq_off[r]);
+}
+
+// ------------------------------------------------------------------------------------------- chain
+__global__ void __launch_bounds__(128) k_chain(Hit* __restrict__ hits, Run* __restrict__ runs, uint8_t* __restrict__ mark,
+                                               const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ read_len,
+                                               uint32_t nreads, const uint32_t* __restrict__ ctg_len, MapParams P,
+                                               uint32_t* __restrict__ nruns, uint32_t* __restrict__ evmax,
+                                               MapStatus* __restrict__ st) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreads) return;
+    const uint32_t o = hit_off[r], nh = hit_off[r + 1] - o;
+    uint32_t nr = 0;
+    if (nh) nr = chain_read(hits + o, nh, runs + o, mark + o, read_len[r], ctg_len, P);
+    nruns[r] = nr;
+    evmax[r] = max_events(nr, P.f);
+    if (nr) atomicAdd(&st->n_runs, nr);
+}
+
+__global__ void __launch_bounds__(128) k_events(const Hit* __restrict__ hits, const Run* __restrict__ runs,
+                                                const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ read_len,
+                                                const uint32_t* __restrict__ nruns, const uint32_t* __restrict__ ev_off,
+                                                uint32_t nreads, uint32_t first_ordinal, const uint32_t* __restrict__ ctg_len,
+                                                const uint32_t* __restrict__ name_rank, MapParams P, uint32_t ev_cap,
+                                                Event* __restrict__ events, uint32_t* __restrict__ ev_cnt,
+                                                MapStatus* __restrict__ st) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreads) return;
+    const uint32_t nr = nruns[r];
+    uint32_t ne = 0;
+    if (nr >= 2) {
+        const uint32_t eo = ev_off[r];
+        if ((uint64_t)eo + max_events(nr, P.f) > ev_cap) atomicOr(&st->err, MAPERR_EVENTS);
+        else {
+            const uint32_t o = hit_off[r];
+            ne = tally_read(hits + o, runs + o, nr, read_len[r], first_ordinal + r, ctg_len, name_rank, P, events + eo);
+        }
+    }
+    ev_cnt[r] = ne;
+}
+
+__global__ void __launch_bounds__(128) k_compact_events(const Event* __restrict__ events, const uint32_t* __restrict__ ev_off,
+                                                        const uint32_t* __restrict__ ev_cnt, const uint32_t* __restrict__ ev_pref,
+                                                        uint32_t nreads, Event* __restrict__ log, MapStatus* __restrict__ st) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) st->n_events = ev_pref[nreads];
+    if (r >= nreads) return;
+    const uint32_t n = ev_cnt[r];
+    for (uint32_t i = 0; i < n; i++) log[ev_pref[r] + i] = events[ev_off[r] + i];
+}
+
+// ------------------------------------------------------------------------------------------- tally
+#define NTL_PAIR_EMPTY 0xFFFFFFFFFFFFFFFFULL
+__device__ __forceinline__ uint64_t pair_key(const Event& e) {
+    return ((uint64_t)e.src << 33) | ((uint64_t)e.tgt << 2) | (e.flags & 3u);
+}
+__device__ __forceinline__ uint64_t order_key(const Event& e) { return ((uint64_t)e.read << 24) | (e.ord & 0xFFFFFFu); }
+
+__global__ void k_tally_insert(const Event* __restrict__ ev, uint64_t n, unsigned long long* __restrict__ keys,
+                               uint64_t mask, uint32_t* __restrict__ pn, uint32_t* __restrict__ panchor,
+                               unsigned long long* __restrict__ pfirst, uint32_t* __restrict__ ev_slot) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Event e = ev[i];
+    const uint64_t key = pair_key(e);
+    uint64_t s = idx_slot(key, mask);
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&keys[s], (unsigned long long)NTL_PAIR_EMPTY, (unsigned long long)key);
+        if (prev == NTL_PAIR_EMPTY || prev == key) break;
+        s = (s + 1) & mask;
+    }
+    atomicAdd(&pn[s], 1u);
+    if (e.flags & 4u) atomicAdd(&panchor[s], 1u);
+    atomicMin(&pfirst[s], (unsigned long long)order_key(e));
+    ev_slot[i] = (uint32_t)s;
+}
+
+__global__ void k_tally_scatter(const Event* __restrict__ ev, uint64_t n, const uint32_t* __restrict__ ev_slot,
+                                const uint32_t* __restrict__ gap_off, uint32_t* __restrict__ cursor,
+                                unsigned long long* __restrict__ gkey, int32_t* __restrict__ gval) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = ev_slot[i];
+    const uint32_t p = gap_off[s] + atomicAdd(&cursor[s], 1u);
+    gkey[p] = order_key(ev[i]);
+    gval[p] = ev[i].gap;
+}
+
+// one thread per pair: insertion sort of its gap list by read order (lists are ~coverage long)
+__global__ void k_tally_sort(const uint32_t* __restrict__ pn, const uint32_t* __restrict__ gap_off, uint32_t slots,
+                             unsigned long long* __restrict__ gkey, int32_t* __restrict__ gval, uint32_t* __restrict__ nonempty) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    const uint32_t n = pn[s];
+    nonempty[s] = n ? 1u : 0u;
+    if (n < 2) return;
+    unsigned long long* k = gkey + gap_off[s];
+    int32_t* v = gval + gap_off[s];
+    for (uint32_t i = 1; i < n; i++) {
+        const unsigned long long kk = k[i]; const int32_t vv = v[i];
+        uint32_t j = i;
+        while (j > 0 && k[j - 1] > kk) { k[j] = k[j - 1]; v[j] = v[j - 1]; j--; }
+        k[j] = kk; v[j] = vv;
+    }
+}
+
+__global__ void k_pairs_compact(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ pn,
+                                const uint32_t* __restrict__ panchor, const unsigned long long* __restrict__ pfirst,
+                                const uint32_t* __restrict__ gap_off, const uint32_t* __restrict__ ppref, uint32_t slots,
+                                ntl_pair* __restrict__ out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots || pn[s] == 0) return;
+    ntl_pair p;
+    const uint64_t key = keys[s];
+    p.src = (uint32_t)(key >> 33); p.tgt = (uint32_t)((key >> 2) & 0x7FFFFFFFu); p.flags = (uint32_t)(key & 3u);
+    p.n = pn[s]; p.anchor = panchor[s]; p.reserved = 0; p.gap_off = gap_off[s]; p.first_key = pfirst[s];
+    out[ppref[s]] = p;
+}
+
+__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+
+}  // namespace
+
+// grow a device buffer keeping its first `keep` bytes
+static int grow_preserve(ntl_ctx* c, DevBuf& b, size_t keep, size_t need) {
+    if (need <= b.cap) return NTL_OK;
+    DevBuf nb;
+    NTL_CUDA(c, nb.ensure(need + need / 2));
+    if (keep && b.p) NTL_CUDA(c, cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    b.release();
+    b = nb;
+    return NTL_OK;
+}
+
+// Build the replicated target index from device-resident minimizer triples.
+int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg, const uint32_t* d_posf, uint64_t n,
+                       const uint32_t* h_ctg_len, const uint32_t* h_name_rank, uint32_t ncontig) {
+    TargetIndex& X = c->index;
+    uint64_t slots = 1024;
+    while (slots < 2 * n) slots <<= 1;
+    X.slots = slots; X.ncontig = ncontig; X.n_inserted = n; X.built = false;
+    NTL_CUDA(c, X.table.ensure(slots * sizeof(IdxEntry)));
+    NTL_CUDA(c, X.dupflag.ensure(slots));
+    NTL_CUDA(c, X.special.ensure(sizeof(IdxSpecial) + 16));
+    NTL_CUDA(c, X.ctg_len.ensure(((size_t)ncontig + 1) * 4));
+    NTL_CUDA(c, X.name_rank.ensure(((size_t)ncontig + 1) * 4));
+    tick(c, T_INDEX);
+    NTL_CUDA(c, cudaMemsetAsync(X.table.p, 0xFF, slots * sizeof(IdxEntry), c->stream));
+    NTL_CUDA(c, cudaMemsetAsync(X.dupflag.p, 0, slots, c->stream));
+    NTL_CUDA(c, cudaMemsetAsync(X.special.p, 0, sizeof(IdxSpecial) + 16, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(X.ctg_len.p, h_ctg_len, (size_t)ncontig * 4, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(X.name_rank.p, h_name_rank, (size_t)ncontig * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n) {
+        k_index_insert<<<div_up(n, 256), 256, 0, c->stream>>>(d_hash, d_ctg, d_posf, n, X.table.as<IdxEntry>(), slots - 1,
+                                                             X.dupflag.as<uint8_t>(), X.special.as<IdxSpecial>());
+        c->launches++;
+    }
+    k_index_finalize<<<div_up(slots, 256), 256, 0, c->stream>>>(X.table.as<IdxEntry>(), slots, X.dupflag.as<uint8_t>(),
+                                                               (unsigned long long*)((char*)X.special.p + sizeof(IdxSpecial)));
+    c->launches++;
+    tock(c, T_INDEX);
+    NTL_CUDA(c, cudaGetLastError());
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));   // h_ctg_len / h_name_rank are caller memory
+    X.built = true;
+    return NTL_OK;
+}
+
+int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids) {
+    NTL_CUDA(c, ctg_ids.ensure((size_t)sk.n_mx * 4 + 4));
+    if (sk.n_mx) {
+        k_expand_ctg<<<div_up(sk.n_mx, 256), 256, 0, c->stream>>>(sk.mx_off.as<uint32_t>(), sk.nseq, sk.n_mx, ctg_ids.as<uint32_t>());
+        c->launches++;
+    }
+    NTL_CUDA(c, cudaGetLastError());
+    return NTL_OK;
+}
+
+// Lookup + chain + events for the reads whose sketch is `sk` (device). d_read_len: device read lengths.
+// Results are left in c->mw (hits, runs, nruns, hit_off, events log segment); the counters are returned.
+int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, uint32_t nreads, uint64_t first_ordinal,
+               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out) {
+    if (!c->index.built) { c->err = "map: no target index (call ntl_index_build first)"; return NTL_ERR_STATE; }
+    MapWork& M = c->mw;
+    const uint32_t n = sk.n_mx;
+    MapParams P;
+    P.k = prm->k; P.z = prm->z; P.f = prm->f; P.x = prm->x; P.x_is_zero = (prm->x == 0.0);
+    P.sensitive = prm->sensitive; P.repeat_filter = prm->repeat_filter;
+    NTL_CUDA(c, M.hit_tmp.ensure((size_t)n * sizeof(Hit) + 16));
+    NTL_CUDA(c, M.hit_flag.ensure((size_t)n * 4 + 16));
+    NTL_CUDA(c, M.hit_pref.ensure((size_t)n * 4 + 16));
+    NTL_CUDA(c, M.hits.ensure((size_t)n * sizeof(Hit) + 16));
+    NTL_CUDA(c, M.runs.ensure((size_t)n * sizeof(Run) + 16));
+    NTL_CUDA(c, M.mark.ensure((size_t)n + 16));
+    NTL_CUDA(c, M.hit_off.ensure(((size_t)nreads + 2) * 4));
+    NTL_CUDA(c, M.nruns.ensure(((size_t)nreads + 2) * 4));
+    NTL_CUDA(c, M.ev_cnt.ensure(((size_t)nreads + 2) * 4 * 4));   // evmax | ev_off | ev_cnt | ev_pref
+    NTL_CUDA(c, M.status.ensure(sizeof(MapStatus) + 64));
+    NTL_CUDA(c, c->h_status.ensure(256));
+    MapStatus* st = M.status.as<MapStatus>();
+    uint32_t* n_dev = (uint32_t*)((char*)M.status.p + sizeof(MapStatus));
+    uint32_t* nreads_dev = n_dev + 1;
+    uint32_t* evmax = M.ev_cnt.as<uint32_t>();
+    uint32_t* ev_off = evmax + (nreads + 2);
+    uint32_t* ev_cnt = ev_off + (nreads + 2);
+    uint32_t* ev_pref = ev_cnt + (nreads + 2);
+    uint32_t ev_cap = std::max<uint32_t>(1 << 16, 4 * nreads);
+    int attempt = 0;
+
+    NTL_CUDA(c, cudaMemsetAsync(st, 0, sizeof(MapStatus) + 64, c->stream));
+    IndexView ix{c->index.table.as<IdxEntry>(), c->index.slots - 1, c->index.special.as<IdxSpecial>()};
+    tick(c, T_LOOKUP);
+    k_lookup<<<div_up(std::max<uint32_t>(n, 1), 256), 256, 0, c->stream>>>(sk.hash.as<uint64_t>(), sk.posf.as<uint32_t>(), n, ix,
+                                                                         M.hit_tmp.as<Hit>(), M.hit_flag.as<uint32_t>(), n_dev);
+    c->launches++;
+    NTL_TRY(exclusive_scan_u32(c, M.hit_flag.as<uint32_t>(), M.hit_pref.as<uint32_t>(), n_dev, n, M.blocksums));
+    if (n) {
+        k_compact_hits<<<div_up(n, 256), 256, 0, c->stream>>>(M.hit_tmp.as<Hit>(), M.hit_flag.as<uint32_t>(),
+                                                            M.hit_pref.as<uint32_t>(), n, M.hits.as<Hit>());
+        c->launches++;
+    }
+    k_hit_offsets<<<div_up((uint64_t)nreads + 1, 256), 256, 0, c->stream>>>(sk.mx_off.as<uint32_t>(), M.hit_pref.as<uint32_t>(), nreads,
+                                                                          M.hit_off.as<uint32_t>(), st, nreads_dev);
+    c->launches++;
+    tock(c, T_LOOKUP);
+
+    tick(c, T_CHAIN);
+    if (nreads) {
+        k_chain<<<div_up(nreads, 128), 128, 0, c->stream>>>(M.hits.as<Hit>(), M.runs.as<Run>(), M.mark.as<uint8_t>(),
+                                                          M.hit_off.as<uint32_t>(), d_read_len, nreads,
+                                                          c->index.ctg_len.as<uint32_t>(), P, M.nruns.as<uint32_t>(), evmax, st);
+        c->launches++;
+    }
+    NTL_TRY(exclusive_scan_u32(c, evmax, ev_off, nreads_dev, nreads, M.blocksums));
+retry_events:
+    NTL_CUDA(c, M.events.ensure((size_t)ev_cap * sizeof(Event)));
+    if (nreads) {
+        k_events<<<div_up(nreads, 128), 128, 0, c->stream>>>(M.hits.as<Hit>(), M.runs.as<Run>(), M.hit_off.as<uint32_t>(), d_read_len,
+                                                           M.nruns.as<uint32_t>(), ev_off, nreads, (uint32_t)first_ordinal,
+                                                           c->index.ctg_len.as<uint32_t>(), c->index.name_rank.as<uint32_t>(), P,
+                                                           ev_cap, M.events.as<Event>(), ev_cnt, st);
+        c->launches++;
+    }
+    NTL_TRY(exclusive_scan_u32(c, ev_cnt, ev_pref, nreads_dev, nreads, M.blocksums));
+    // counters -> host (one synchronisation), then append the events to the device log
+    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.p, st, sizeof(MapStatus), cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.as<char>() + 64, ev_pref + nreads, 4, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.as<char>() + 68, ev_off + nreads, 4, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    MapStatus hs = *c->h_status.as<MapStatus>();
+    const uint32_t n_events = nreads ? *(uint32_t*)(c->h_status.as<char>() + 64) : 0;
+    const uint32_t ev_need = nreads ? *(uint32_t*)(c->h_status.as<char>() + 68) : 0;
+    if (hs.err & MAPERR_EVENTS) {
+        if (++attempt > 2) { c->err = "map: event buffer exhausted"; return NTL_ERR_WORKSPACE; }
+        ev_cap = ev_need + 1024;
+        NTL_CUDA(c, cudaMemsetAsync(&st->err, 0, 4, c->stream));
+        goto retry_events;
+    }
+    NTL_TRY(grow_preserve(c, c->tl_events, c->tl_n_events * sizeof(Event), (c->tl_n_events + n_events + 1) * sizeof(Event)));
+    if (nreads) {
+        k_compact_events<<<div_up(nreads, 128), 128, 0, c->stream>>>(M.events.as<Event>(), ev_off, ev_cnt, ev_pref, nreads,
+                                                                   c->tl_events.as<Event>() + c->tl_n_events, st);
+        c->launches++;
+    }
+    tock(c, T_CHAIN);
+    NTL_CUDA(c, cudaGetLastError());
+    hs.n_events = n_events;
+    *counts_out = hs;
+    *log_base_out = c->tl_n_events;
+    c->tl_n_events += n_events;
+    return NTL_OK;
+}
+
+// Pair table over the whole device event log.
+int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>& gaps) {
+    const uint64_t n = c->tl_n_events;
+    pairs.clear(); gaps.clear();
+    if (n == 0) return NTL_OK;
+    if (n >= (1ull << 31)) { c->err = "tally: too many events"; return NTL_ERR_WORKSPACE; }
+    uint64_t slots = 1024;
+    while (slots < 2 * n) slots <<= 1;
+    DevBuf keys, pn, panchor, pfirst, ev_slot, gap_off, cursor, gkey, gval, nonempty, ppref, out, ndev, bs;
+    int rc = NTL_OK;
+    auto cleanup = [&]() { keys.release(); pn.release(); panchor.release(); pfirst.release(); ev_slot.release(); gap_off.release();
+                           cursor.release(); gkey.release(); gval.release(); nonempty.release(); ppref.release(); out.release();
+                           ndev.release(); bs.release(); };
+#define TL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string("tally: ") + cudaGetErrorString(e__); cleanup(); return NTL_ERR_CUDA; } } while (0)
+    TL_CUDA(keys.ensure(slots * 8)); TL_CUDA(pn.ensure(slots * 4)); TL_CUDA(panchor.ensure(slots * 4));
+    TL_CUDA(pfirst.ensure(slots * 8)); TL_CUDA(ev_slot.ensure(n * 4)); TL_CUDA(gap_off.ensure((slots + 1) * 4));
+    TL_CUDA(cursor.ensure(slots * 4)); TL_CUDA(gkey.ensure(n * 8)); TL_CUDA(gval.ensure(n * 4));
+    TL_CUDA(nonempty.ensure(slots * 4)); TL_CUDA(ppref.ensure((slots + 1) * 4)); TL_CUDA(ndev.ensure(16));
+    tick(c, T_TALLY);
+    TL_CUDA(cudaMemsetAsync(keys.p, 0xFF, slots * 8, c->stream));
+    TL_CUDA(cudaMemsetAsync(pfirst.p, 0xFF, slots * 8, c->stream));
+    TL_CUDA(cudaMemsetAsync(pn.p, 0, slots * 4, c->stream));
+    TL_CUDA(cudaMemsetAsync(panchor.p, 0, slots * 4, c->stream));
+    TL_CUDA(cudaMemsetAsync(cursor.p, 0, slots * 4, c->stream));
+    const Event* ev = c->tl_events.as<Event>();
+    k_set_u32<<<1, 1, 0, c->stream>>>(ndev.as<uint32_t>(), (uint32_t)slots);
+    k_tally_insert<<<div_up(n, 256), 256, 0, c->stream>>>(ev, n, keys.as<unsigned long long>(), slots - 1, pn.as<uint32_t>(),
+                                                         panchor.as<uint32_t>(), pfirst.as<unsigned long long>(), ev_slot.as<uint32_t>());
+    c->launches += 2;
+    rc = exclusive_scan_u32(c, pn.as<uint32_t>(), gap_off.as<uint32_t>(), ndev.as<uint32_t>(), (uint32_t)slots, bs);
+    if (rc != NTL_OK) { cleanup(); return rc; }
+    k_tally_scatter<<<div_up(n, 256), 256, 0, c->stream>>>(ev, n, ev_slot.as<uint32_t>(), gap_off.as<uint32_t>(), cursor.as<uint32_t>(),
+                                                          gkey.as<unsigned long long>(), gval.as<int32_t>());
+    k_tally_sort<<<div_up(slots, 128), 128, 0, c->stream>>>(pn.as<uint32_t>(), gap_off.as<uint32_t>(), (uint32_t)slots,
+                                                           gkey.as<unsigned long long>(), gval.as<int32_t>(), nonempty.as<uint32_t>());
+    c->launches += 2;
+    rc = exclusive_scan_u32(c, nonempty.as<uint32_t>(), ppref.as<uint32_t>(), ndev.as<uint32_t>(), (uint32_t)slots, bs);
+    if (rc != NTL_OK) { cleanup(); return rc; }
+    uint32_t n_pairs = 0;
+    TL_CUDA(cudaMemcpyAsync(&n_pairs, ppref.as<uint32_t>() + slots, 4, cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA(cudaStreamSynchronize(c->stream));
+    TL_CUDA(out.ensure((size_t)n_pairs * sizeof(ntl_pair) + 16));
+    k_pairs_compact<<<div_up(slots, 128), 128, 0, c->stream>>>(keys.as<unsigned long long>(), pn.as<uint32_t>(), panchor.as<uint32_t>(),
+                                                              pfirst.as<unsigned long long>(), gap_off.as<uint32_t>(), ppref.as<uint32_t>(),
+                                                              (uint32_t)slots, (ntl_pair*)out.p);
+    c->launches++;
+    tock(c, T_TALLY);
+    pairs.resize(n_pairs); gaps.resize(n);
+    TL_CUDA(cudaMemcpyAsync(pairs.data(), out.p, (size_t)n_pairs * sizeof(ntl_pair), cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA(cudaMemcpyAsync(gaps.data(), gval.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA(cudaStreamSynchronize(c->stream));
+#undef TL_CUDA
+    cleanup();
+    std::sort(pairs.begin(), pairs.end(), [](const ntl_pair& a, const ntl_pair& b) { return a.first_key < b.first_key; });
+    return NTL_OK;
+}
+
+int read_len_device(ntl_ctx* c, const uint64_t* d_off, uint32_t nreads, DevBuf& out) {
+    NTL_CUDA(c, out.ensure(((size_t)nreads + 1) * 4));
+    if (nreads) { k_read_len<<<div_up(nreads, 256), 256, 0, c->stream>>>(d_off, nreads, out.as<uint32_t>()); c->launches++; }
+    NTL_CUDA(c, cudaGetLastError());
+    return NTL_OK;
+}
+
+}  // namespace ntl

@@ -1,0 +1,457 @@
+// sketch.cu -- the minimizer sketch pipeline on the device (replaces btllib `indexlr --long --pos --strand`,
+// invoked by the reference at ntLink:198-199 and ntLink:221-225). See sketch_logic.cuh for the algorithm.
+//
+// Kernels (all hand-written, sm_100a):
+//   k_pack        ASCII -> 4-bit codes, 128-bit coalesced loads, 64-bit stores      (HBM streaming)
+//   k_strip_count strips per sequence                                               (tiny)
+//   k_dense       one thread per strip of S k-mer positions: rolling ntHash, candidate filter  (THE hot kernel,
+//                 integer-ALU bound; roll table replicated 8x in shared memory for conflict-free LDS.128)
+//   k_overflow    re-runs the rare strips whose candidates did not fit their slots
+//   k_select      per candidate: exact minimizer decision from neighbouring candidates; queues gaps
+//   k_seq_gaps    leading / whole-sequence candidate-free stretches
+//   k_gap         exact sliding-window re-scan of the queued stretches
+//   k_emit        ordered compaction: second hash, pos|strand, per-sequence offsets
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace ntl {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------- pack
+__device__ __forceinline__ uint32_t base_code(uint32_t c) {
+    // A/a=0 C/c=1 G/g=2 T/t=3 else 4. c & 0xDF folds case; then exact compares (predicated selects).
+    c &= 0xDFu;
+    uint32_t r = 4u;
+    r = (c == 0x41u) ? 0u : r;
+    r = (c == 0x43u) ? 1u : r;
+    r = (c == 0x47u) ? 2u : r;
+    r = (c == 0x54u) ? 3u : r;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ seq, uint64_t nbases,
+                                              uint32_t* __restrict__ packed /* 8 bases per word */) {
+    // one thread = 16 bases = one 128-bit load, one 64-bit store
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t b0 = chunk * 16;
+    if (b0 >= nbases) return;
+    uint32_t w[4];
+    if (b0 + 16 <= nbases) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(seq + b0));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        for (int i = 0; i < 4; i++) {
+            uint32_t x = 0;
+            for (int j = 0; j < 4; j++) {
+                const uint64_t b = b0 + 4 * i + j;
+                const uint32_t ch = b < nbases ? seq[b] : (uint32_t)'N';
+                x |= ch << (8 * j);
+            }
+            w[i] = x;
+        }
+    }
+    uint32_t o[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t code = base_code((w[i] >> (8 * j)) & 0xFFu);
+            o[i >> 1] |= code << (4 * ((i & 1) * 4 + j));
+        }
+    *reinterpret_cast<uint2*>(packed + chunk * 2) = make_uint2(o[0], o[1]);
+}
+
+// ------------------------------------------------------------------------------------------- strips
+struct SkParams {
+    uint32_t k, w, S, cap, tau_hi, nseq;
+    uint64_t mult;
+    uint64_t pool_base;     // = nstrips_max * cap
+    uint32_t pool_cap, gaps_cap, extras_cap, out_cap;
+};
+
+__device__ __forceinline__ uint32_t seq_npos(uint64_t L, uint32_t k, uint32_t w) {
+    // btllib: k > L or w > L-k+1 -> nothing
+    if (L < k) return 0;
+    const uint64_t np = L - k + 1;
+    return np < w ? 0u : (uint32_t)np;
+}
+
+__global__ void k_strip_count(const uint64_t* __restrict__ seq_off, uint32_t nseq, uint32_t k, uint32_t w, uint32_t S,
+                              uint32_t* __restrict__ scnt, uint32_t* __restrict__ nseq_dev) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) *nseq_dev = nseq;
+    if (q >= nseq) return;
+    const uint32_t np = seq_npos(seq_off[q + 1] - seq_off[q], k, w);
+    scnt[q] = (np + S - 1) / S;
+}
+
+// largest q with strip_off[q] <= s  (strip_off has nseq+1 entries, strip_off[nseq] = nstrips > s)
+__device__ __forceinline__ uint32_t seq_of_strip(const uint32_t* __restrict__ strip_off, uint32_t nseq, uint32_t s) {
+    uint32_t lo = 0, hi = nseq;           // invariant: strip_off[lo] <= s < strip_off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (strip_off[mid] <= s) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct SlotEmit {
+    Cand* dst;
+    uint32_t cap, count;
+    __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) {
+        if (count < cap) {
+            Cand c; c.h0 = h0; c.posf = pos | (fwd ? FWD_BIT : 0u); c.lord = lord;
+            dst[count] = c;
+        }
+        count++;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_dense(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
+                                               const uint32_t* __restrict__ strip_off, SkParams P,
+                                               const RollEntry* __restrict__ tbl_g, Cand* __restrict__ slots,
+                                               uint32_t* __restrict__ cnt, uint32_t* __restrict__ nv,
+                                               uint8_t* __restrict__ has_cand, SketchStatus* __restrict__ st) {
+    // roll table, 8 interleaved copies: entry e, copy c at [e*8 + c]; a quarter-warp (one LDS.128 phase) reads
+    // 8 different copies = 8 different 16-byte bank groups -> conflict-free whatever the entries are
+    __shared__ RollEntry tbl_s[ROLL_TABLE_ENTRIES * 8];
+    for (uint32_t i = threadIdx.x; i < ROLL_TABLE_ENTRIES * 8; i += blockDim.x) tbl_s[i] = tbl_g[i >> 3];
+    __syncthreads();
+    const uint32_t nstrips = strip_off[P.nseq];
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) st->nstrips = nstrips;
+    if (s >= nstrips) return;
+    const uint32_t q = seq_of_strip(strip_off, P.nseq, s);
+    const uint64_t gseq = seq_off[q];
+    const uint32_t np = seq_npos(seq_off[q + 1] - gseq, P.k, P.w);
+    const uint32_t p0 = (s - strip_off[q]) * P.S;
+    const uint32_t n = min(P.S, np - p0);
+    SlotEmit em{slots + (uint64_t)s * P.cap, P.cap, 0};
+    const uint32_t nvalid = process_strip(packed, gseq, p0, n, P.k, tbl_s + (threadIdx.x & 7), 8, P.tau_hi, em);
+    cnt[s] = em.count;
+    nv[s] = nvalid;
+    if (em.count) has_cand[q] = 1;
+    if (em.count > P.cap) atomicAdd(&st->n_ovf, 1u);
+}
+
+struct PoolEmit {
+    Cand* dst;
+    uint32_t count;
+    __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) {
+        Cand c; c.h0 = h0; c.posf = pos | (fwd ? FWD_BIT : 0u); c.lord = lord;
+        dst[count++] = c;
+    }
+};
+
+// strips whose candidate count exceeded the slot capacity: reserve room in the pool and run them again
+__global__ void __launch_bounds__(128) k_overflow(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
+                                                  const uint32_t* __restrict__ strip_off, SkParams P,
+                                                  const RollEntry* __restrict__ tbl_g, Cand* __restrict__ cands,
+                                                  const uint32_t* __restrict__ cnt, uint32_t* __restrict__ ovf_off,
+                                                  SketchStatus* __restrict__ st) {
+    if (st->n_ovf == 0) return;
+    const uint32_t nstrips = st->nstrips;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstrips || cnt[s] <= P.cap) return;
+    const uint32_t off = atomicAdd(&st->pool_used, cnt[s]);
+    if ((uint64_t)off + cnt[s] > P.pool_cap) { atomicOr(&st->err, SKERR_POOL); ovf_off[s] = 0; return; }
+    ovf_off[s] = off;
+    const uint32_t q = seq_of_strip(strip_off, P.nseq, s);
+    const uint64_t gseq = seq_off[q];
+    const uint32_t np = seq_npos(seq_off[q + 1] - gseq, P.k, P.w);
+    const uint32_t p0 = (s - strip_off[q]) * P.S;
+    const uint32_t n = min(P.S, np - p0);
+    PoolEmit em{cands + P.pool_base + off, 0};
+    process_strip(packed, gseq, p0, n, P.k, tbl_g, 1, P.tau_hi, em);
+}
+
+// ------------------------------------------------------------------------------------------- select
+__device__ __forceinline__ void queue_gap(GapRec* gaps, uint32_t* gap_head, SketchStatus* st, const SkParams& P,
+                                          uint32_t seq, uint32_t start_pos, uint32_t end_pos, uint32_t strip,
+                                          uint32_t j, uint32_t nvalid) {
+    const uint32_t id = atomicAdd(&st->ngaps, 1u);
+    if (id >= P.gaps_cap) { atomicOr(&st->err, SKERR_GAPS); return; }
+    const uint32_t need = nvalid - P.w + 1;
+    const uint32_t off = atomicAdd(&st->extras_used, need);
+    GapRec g;
+    g.seq = seq; g.start_pos = start_pos; g.end_pos = end_pos; g.strip = strip; g.j = j;
+    g.out_off = off; g.out_cnt = 0; g.max_out = need; g.pad = 0;
+    if ((uint64_t)off + need > P.extras_cap) { atomicOr(&st->err, SKERR_EXTRAS); g.max_out = 0; }
+    g.next = atomicExch(&gap_head[strip], id);
+    gaps[id] = g;
+}
+
+__global__ void __launch_bounds__(128) k_select(const uint64_t* __restrict__ seq_off, const uint32_t* __restrict__ strip_off,
+                                                SkParams P, CandView V, uint8_t* __restrict__ sel,
+                                                uint32_t* __restrict__ selcnt, GapRec* __restrict__ gaps,
+                                                uint32_t* __restrict__ gap_head, SketchStatus* __restrict__ st) {
+    const uint32_t nstrips = st->nstrips;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstrips) return;
+    const uint32_t c = V.cnt[s];
+    if (c == 0) { selcnt[s] = 0; return; }
+    const uint32_t q = seq_of_strip(strip_off, P.nseq, s);
+    const uint32_t fs = strip_off[q], es = strip_off[q + 1];
+    const uint32_t np = seq_npos(seq_off[q + 1] - seq_off[q], P.k, P.w);
+    uint32_t nsel = 0;
+    for (uint32_t j = 0; j < c; j++) {
+        const SelectResult r = select_candidate(V, s, j, fs, es, P.w, np);
+        const uint64_t gid = cand_gid(V, s, j);
+        sel[gid] = r.selected ? 1 : 0;
+        nsel += r.selected ? 1u : 0u;
+        if (r.gap_len >= P.w) {
+            const uint32_t pos = V.cands[gid].posf & POS_MASK;
+            queue_gap(gaps, gap_head, st, P, q, pos + 1, r.gap_end, s, j, r.gap_len);
+        }
+    }
+    selcnt[s] = nsel;
+    atomicAdd(&st->n_cand, c);
+}
+
+// candidate-free stretch at the start of a sequence (or the whole sequence)
+__global__ void k_seq_gaps(const uint64_t* __restrict__ seq_off, const uint32_t* __restrict__ strip_off, SkParams P,
+                           CandView V, const uint8_t* __restrict__ has_cand, GapRec* __restrict__ gaps,
+                           uint32_t* __restrict__ gap_head, SketchStatus* __restrict__ st) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.nseq) return;
+    const uint32_t fs = strip_off[q], es = strip_off[q + 1];
+    if (fs == es) return;
+    const uint32_t np = seq_npos(seq_off[q + 1] - seq_off[q], P.k, P.w);
+    const uint32_t idx0 = V.vbase[fs];
+    const uint32_t nvalid = V.vbase[es] - idx0;
+    if (nvalid < P.w) return;
+    if (!has_cand[q]) { queue_gap(gaps, gap_head, st, P, q, 0, np, fs, NONE32, nvalid); return; }
+    uint32_t fc = fs;                               // first candidate of the sequence
+    while (fc < es && V.cnt[fc] == 0) fc++;
+    if (fc >= es) return;   // cannot happen when has_cand is set
+    const Cand c = V.cands[cand_gid(V, fc, 0)];
+    const uint32_t lead = V.vbase[fc] + c.lord - idx0;
+    if (lead >= P.w) queue_gap(gaps, gap_head, st, P, q, 0, c.posf & POS_MASK, fs, NONE32, lead);
+}
+
+struct ExtraEmit {
+    Cand* dst;
+    uint32_t count, cap;
+    __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd) {
+        if (count < cap) { Cand c; c.h0 = h0; c.posf = pos | (fwd ? FWD_BIT : 0u); c.lord = 0; dst[count] = c; }
+        count++;
+    }
+};
+
+__global__ void __launch_bounds__(64) k_gap(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
+                                            SkParams P, const RollEntry* __restrict__ tbl_g, GapRec* __restrict__ gaps,
+                                            Cand* __restrict__ extras, uint32_t* __restrict__ selcnt,
+                                            SketchStatus* __restrict__ st) {
+    const uint32_t ng = min(st->ngaps, P.gaps_cap);
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < ng; id += gridDim.x * blockDim.x) {
+        GapRec g = gaps[id];
+        if (g.max_out == 0) continue;
+        const uint64_t gseq = seq_off[g.seq];
+        const uint32_t L = (uint32_t)(seq_off[g.seq + 1] - gseq);
+        ExtraEmit em{extras + g.out_off, 0, g.max_out};
+        gap_scan(packed, tbl_g, gseq, L, P.k, P.w, g.start_pos, g.end_pos, em);
+        const uint32_t n = min(em.count, g.max_out);
+        gaps[id].out_cnt = n;
+        if (n) atomicAdd(&selcnt[g.strip], n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- emit
+__global__ void __launch_bounds__(128) k_emit(SkParams P, CandView V, const uint8_t* __restrict__ sel,
+                                              const uint32_t* __restrict__ selbase, const GapRec* __restrict__ gaps,
+                                              const uint32_t* __restrict__ gap_head, const Cand* __restrict__ extras,
+                                              uint64_t* __restrict__ out_hash, uint32_t* __restrict__ out_posf,
+                                              SketchStatus* __restrict__ st) {
+    const uint32_t nstrips = st->nstrips;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) st->n_mx = selbase[nstrips];
+    if (s >= nstrips) return;
+    uint32_t o = selbase[s];
+    const uint32_t end = selbase[s + 1];
+    if (o == end) return;
+    if (end > P.out_cap) { atomicOr(&st->err, SKERR_OUT); return; }
+    const uint32_t head = gap_head[s];
+    const uint32_t c = V.cnt[s];
+    if (head != NONE32) {
+        for (uint32_t g = head; g != NONE32; g = gaps[g].next)
+            if (gaps[g].j == NONE32)
+                for (uint32_t i = 0; i < gaps[g].out_cnt; i++) {
+                    const Cand e = extras[gaps[g].out_off + i];
+                    out_hash[o] = second_hash(e.h0, P.mult); out_posf[o] = e.posf; o++;
+                }
+    }
+    for (uint32_t j = 0; j < c; j++) {
+        const uint64_t gid = cand_gid(V, s, j);
+        if (sel[gid]) {
+            const Cand e = V.cands[gid];
+            out_hash[o] = second_hash(e.h0, P.mult); out_posf[o] = e.posf; o++;
+        }
+        if (head != NONE32) {
+            for (uint32_t g = head; g != NONE32; g = gaps[g].next)
+                if (gaps[g].j == j)
+                    for (uint32_t i = 0; i < gaps[g].out_cnt; i++) {
+                        const Cand e = extras[gaps[g].out_off + i];
+                        out_hash[o] = second_hash(e.h0, P.mult); out_posf[o] = e.posf; o++;
+                    }
+        }
+    }
+}
+
+__global__ void k_seq_offsets(const uint32_t* __restrict__ strip_off, const uint32_t* __restrict__ selbase,
+                              uint32_t nseq, uint32_t* __restrict__ mx_off) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q <= nseq) mx_off[q] = selbase[strip_off[q]];
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+}  // namespace
+
+// Sketch `nseq` sequences that are already on the device (ASCII d_seq, offsets d_off). The result stays on the
+// device in `out`. One host synchronisation (to learn the number of minimizers before the final compaction).
+int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
+                  uint32_t k, uint32_t w, DeviceSketch& out) {
+    if (k == 0 || w == 0 || k > 100000 || total_bases >= (1ull << 32)) { c->err = "sketch: bad k/w or batch too large"; return NTL_ERR_ARG; }
+    SketchWork& W = c->sw;
+    out.nseq = nseq; out.n_mx = 0;
+    NTL_CUDA(c, out.mx_off.ensure(((size_t)nseq + 1) * 4));
+    if (nseq == 0 || total_bases == 0) {
+        NTL_CUDA(c, cudaMemsetAsync(out.mx_off.p, 0, ((size_t)nseq + 1) * 4, c->stream));
+        return NTL_OK;
+    }
+    const uint32_t S = c->strip_len;
+    double mu = (double)S * c->cand_c / (double)w;
+    if (mu > S) mu = S;
+    uint32_t cap = (uint32_t)(mu + 6.0 * sqrt(mu) + 8.0);
+    if (cap > S) cap = S;
+    cap = (cap + 1) & ~1u;
+    const uint32_t nstrips_max = (uint32_t)(total_bases / S + nseq + 1);
+
+    int attempt = 0;
+    uint32_t pool_cap = (uint32_t)std::max<uint64_t>(1 << 16, (uint64_t)nstrips_max * cap / 16);
+    uint32_t gaps_cap = (uint32_t)std::max<uint64_t>(1 << 14, total_bases / (4ull * w) + nseq);
+    uint32_t extras_cap = (uint32_t)std::max<uint64_t>(1 << 16, total_bases / (2ull * w) + nseq);
+    uint32_t out_cap = 0;
+
+retry:
+    SkParams P;
+    P.k = k; P.w = w; P.S = S; P.cap = cap; P.tau_hi = candidate_threshold(w, c->cand_c); P.nseq = nseq;
+    P.mult = second_hash_multiplier(k);
+    P.pool_base = (uint64_t)nstrips_max * cap;
+    P.pool_cap = pool_cap; P.gaps_cap = gaps_cap; P.extras_cap = extras_cap; P.out_cap = 0;
+
+    NTL_CUDA(c, W.packed.ensure(total_bases / 2 + 128));
+    NTL_CUDA(c, W.scnt.ensure(((size_t)nseq + 2) * 4));
+    NTL_CUDA(c, W.strip_off.ensure(((size_t)nseq + 2) * 4));
+    NTL_CUDA(c, W.slots.ensure(((size_t)P.pool_base + pool_cap) * sizeof(Cand)));
+    NTL_CUDA(c, W.sel.ensure((size_t)P.pool_base + pool_cap));
+    NTL_CUDA(c, W.cnt.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.nv.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.vbase.ensure(((size_t)nstrips_max + 2) * 4));
+    NTL_CUDA(c, W.ovf_off.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.selcnt.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.selbase.ensure(((size_t)nstrips_max + 2) * 4));
+    NTL_CUDA(c, W.gap_head.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.gaps.ensure((size_t)gaps_cap * sizeof(GapRec)));
+    NTL_CUDA(c, W.extras.ensure((size_t)extras_cap * sizeof(Cand)));
+    NTL_CUDA(c, W.has_cand.ensure((size_t)nseq + 1));
+    NTL_CUDA(c, W.status.ensure(sizeof(SketchStatus) + 64));
+    NTL_CUDA(c, W.tbl.ensure(sizeof(RollEntry) * ROLL_TABLE_ENTRIES));
+    NTL_CUDA(c, c->h_status.ensure(256));
+
+    SketchStatus* st = W.status.as<SketchStatus>();
+    uint32_t* nseq_dev = (uint32_t*)((char*)W.status.p + sizeof(SketchStatus));   // scan length for the strip table
+    if (W.tbl_k != k) {
+        RollEntry tbl[ROLL_TABLE_ENTRIES];
+        build_roll_table(k, tbl);
+        NTL_CUDA(c, cudaMemcpyAsync(W.tbl.p, tbl, sizeof tbl, cudaMemcpyHostToDevice, c->stream));
+        NTL_CUDA(c, cudaStreamSynchronize(c->stream));   // tbl is a stack array
+        W.tbl_k = k;
+    }
+    NTL_CUDA(c, cudaMemsetAsync(st, 0, sizeof(SketchStatus) + 64, c->stream));
+    NTL_CUDA(c, cudaMemsetAsync(W.has_cand.p, 0, (size_t)nseq + 1, c->stream));
+    NTL_CUDA(c, cudaMemsetAsync(W.packed.as<char>() + total_bases / 2, 0x44, 128, c->stream));
+
+    tick(c, T_PACK);
+    k_pack<<<div_up(div_up(total_bases, 16), 256), 256, 0, c->stream>>>(d_seq, total_bases, W.packed.as<uint32_t>());
+    k_strip_count<<<div_up(nseq, 256), 256, 0, c->stream>>>(d_off, nseq, k, w, S, W.scnt.as<uint32_t>(), nseq_dev);
+    c->launches += 2;
+    NTL_TRY(exclusive_scan_u32(c, W.scnt.as<uint32_t>(), W.strip_off.as<uint32_t>(), nseq_dev, nseq, W.blocksums));
+    k_fill_u32<<<296, 256, 0, c->stream>>>(W.gap_head.as<uint32_t>(), NONE32, (uint64_t)nstrips_max + 1);
+    c->launches += 1;
+    tock(c, T_PACK);
+
+    tick(c, T_DENSE);
+    k_dense<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(W.packed.as<uint32_t>(), d_off, W.strip_off.as<uint32_t>(), P,
+                                                            W.tbl.as<RollEntry>(), W.slots.as<Cand>(), W.cnt.as<uint32_t>(),
+                                                            W.nv.as<uint32_t>(), W.has_cand.as<uint8_t>(), st);
+    tock(c, T_DENSE);
+    c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases;
+
+    tick(c, T_SELECT);
+    k_overflow<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(W.packed.as<uint32_t>(), d_off, W.strip_off.as<uint32_t>(), P,
+                                                               W.tbl.as<RollEntry>(), W.slots.as<Cand>(), W.cnt.as<uint32_t>(),
+                                                               W.ovf_off.as<uint32_t>(), st);
+    c->launches += 1;
+    NTL_TRY(exclusive_scan_u32(c, W.nv.as<uint32_t>(), W.vbase.as<uint32_t>(), &st->nstrips, nstrips_max, W.blocksums));
+    CandView V;
+    V.cands = W.slots.as<Cand>(); V.cnt = W.cnt.as<uint32_t>(); V.ovf_off = W.ovf_off.as<uint32_t>();
+    V.vbase = W.vbase.as<uint32_t>(); V.cap = cap; V.pool_base = P.pool_base;
+    k_select<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
+                                                             W.selcnt.as<uint32_t>(), W.gaps.as<GapRec>(),
+                                                             W.gap_head.as<uint32_t>(), st);
+    k_seq_gaps<<<div_up(nseq, 128), 128, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.has_cand.as<uint8_t>(),
+                                                        W.gaps.as<GapRec>(), W.gap_head.as<uint32_t>(), st);
+    c->launches += 2;
+    tock(c, T_SELECT);
+
+    tick(c, T_GAP);
+    k_gap<<<div_up(std::min<uint32_t>(gaps_cap, 1 << 16), 64), 64, 0, c->stream>>>(W.packed.as<uint32_t>(), d_off, P,
+                                                                                 W.tbl.as<RollEntry>(), W.gaps.as<GapRec>(),
+                                                                                 W.extras.as<Cand>(), W.selcnt.as<uint32_t>(), st);
+    c->launches += 1;
+    tock(c, T_GAP);
+
+    tick(c, T_EMIT);
+    NTL_TRY(exclusive_scan_u32(c, W.selcnt.as<uint32_t>(), W.selbase.as<uint32_t>(), &st->nstrips, nstrips_max, W.blocksums));
+    // total = selbase[nstrips]; fetch the counters to size the output
+    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.p, st, sizeof(SketchStatus), cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.as<char>() + 64, W.strip_off.as<uint32_t>() + nseq, 4, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    {
+        SketchStatus hs = *c->h_status.as<SketchStatus>();
+        const uint32_t nstrips = *(uint32_t*)(c->h_status.as<char>() + 64);
+        if (hs.err) {
+            if (++attempt > 6) { c->err = "sketch: device workspace exhausted"; return NTL_ERR_WORKSPACE; }
+            if (hs.err & SKERR_POOL) pool_cap = (uint32_t)std::min<uint64_t>(0xFFFF0000ull, std::max<uint64_t>((uint64_t)hs.pool_used + 1024, (uint64_t)pool_cap * 4));
+            if (hs.err & SKERR_GAPS) gaps_cap = (uint32_t)std::min<uint64_t>(0xFFFF0000ull, std::max<uint64_t>((uint64_t)hs.ngaps + 1024, (uint64_t)gaps_cap * 4));
+            if (hs.err & SKERR_EXTRAS) extras_cap = (uint32_t)std::min<uint64_t>(0xFFFF0000ull, std::max<uint64_t>((uint64_t)hs.extras_used + 1024, (uint64_t)extras_cap * 4));
+            goto retry;
+        }
+        uint32_t total = 0;
+        NTL_CUDA(c, cudaMemcpy(&total, W.selbase.as<uint32_t>() + nstrips, 4, cudaMemcpyDeviceToHost));
+        out_cap = total;
+        out.n_mx = total;
+    }
+    NTL_CUDA(c, out.hash.ensure((size_t)out_cap * 8 + 8));
+    NTL_CUDA(c, out.posf.ensure((size_t)out_cap * 4 + 4));
+    P.out_cap = out_cap;
+    k_emit<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(P, V, W.sel.as<uint8_t>(), W.selbase.as<uint32_t>(), W.gaps.as<GapRec>(),
+                                                           W.gap_head.as<uint32_t>(), W.extras.as<Cand>(), out.hash.as<uint64_t>(),
+                                                           out.posf.as<uint32_t>(), st);
+    k_seq_offsets<<<div_up((uint64_t)nseq + 1, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), W.selbase.as<uint32_t>(), nseq,
+                                                                        out.mx_off.as<uint32_t>());
+    c->launches += 2;
+    tock(c, T_EMIT);
+    NTL_CUDA(c, cudaGetLastError());
+    return NTL_OK;
+}
+
+}  // namespace ntl

@@ -119,3 +119,80 @@ def dot_parts(data):
 def is_ordered_subsequence(small_lines, big_lines):
     it = iter(big_lines)
     return all(any(x == y for y in it) for x in small_lines)
+
+
+# ---------------------------------------------------------------------------------------------------
+# host emulation of the kernel logic (tests/emu) -- CPU tests only
+EMU_DIR = os.path.join(HERE, "emu")
+EMU_LIB = os.path.join(EMU_DIR, "_build", "libntl_emu.so")
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+        lib = ctypes.CDLL(EMU_LIB)
+        lib.emu_sketch.restype = ctypes.c_int64
+        lib.emu_sketch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                   ctypes.c_uint32, ctypes.c_double, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+        lib.emu_map.restype = ctypes.c_int64
+        lib.emu_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        _emu = lib
+    return _emu
+
+
+def emu_sketch(seq, offsets, k, w, S=256, c=10.0, cap_override=0):
+    "returns (hash, pos_strand, mx_off, stats dict)"
+    lib = emu_lib()
+    seq = np.ascontiguousarray(seq, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    nseq = len(offsets) - 1
+    cap = len(seq) + 16
+    h = np.empty(cap, np.uint64)
+    p = np.empty(cap, np.uint32)
+    off = np.empty(nseq + 1, np.uint64)
+    st = np.zeros(4, np.uint64)
+    n = lib.emu_sketch(seq.ctypes.data, offsets.ctypes.data, nseq, k, w, S, c, cap_override, h.ctypes.data,
+                       p.ctypes.data, cap, off.ctypes.data, st.ctypes.data)
+    assert n >= 0
+    return h[:n], p[:n], off, {"cand": int(st[0]), "gaps": int(st[1]), "ovf": int(st[2])}
+
+
+def load_fasta_batch(path):
+    "tiny pure-Python FASTA/FASTQ reader for tests: returns (names, seq uint8, offsets uint64)"
+    import gzip as _gz
+    opener = _gz.open if path.endswith(".gz") else open
+    names, parts = [], []
+    with opener(path, "rt") as fin:
+        lines = fin.read().split("\n")
+    i = 0
+    while i < len(lines):
+        ln = lines[i]
+        if ln[:1] in (">", "@"):
+            names.append(ln[1:].split()[0])
+            i += 1
+            s = []
+            while i < len(lines) and lines[i][:1] not in (">", "@", "+"):
+                s.append(lines[i].strip())
+                i += 1
+            seq = "".join(s)
+            parts.append(seq)
+            if i < len(lines) and lines[i][:1] == "+":
+                i += 1
+                q = 0
+                while q < len(seq) and i < len(lines):
+                    q += len(lines[i])
+                    i += 1
+        else:
+            i += 1
+    offs = np.zeros(len(parts) + 1, np.uint64)
+    if parts:
+        offs[1:] = np.cumsum([len(p) for p in parts])
+    seq = np.frombuffer("".join(parts).encode(), dtype=np.uint8)
+    return names, seq, offs
