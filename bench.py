@@ -1,0 +1,390 @@
+#!/usr/bin/env python3
+"""
+bench.py -- long-read Gbp/s sketched+mapped on B200 (BASELINE.json metric), one JSON line on stdout.
+
+Workload (config.workload): BASELINE.json configs[1] -- synthetic 5 Mbp genome cut into 1-200 kbp contigs,
+30x simulated ONT reads (~10 % error), k=32 w=100, 1 GPU. One "step" = the whole job on that input:
+target sketch + index build + read sketch + lookup + chaining + pair events + pair tally.
+
+  value   inputs resident in HBM, device-side CUDA-event time on the library's stream, max over ranks
+  e2e     the same job through the public API with pinned HOST buffers: H2D of target+reads and D2H of all
+          mapping results inside the timed region
+  roofline  the dominant kernel (k_dense): algorithmic bytes of the sketch (1.0 B/base + 13 B/minimizer,
+          SURVEY.md 8d) / its mean launch time (CUDA events inside the library, same run) vs the measured HBM peak
+  cpu_baseline  the CPU oracle (C sketcher on all host threads + the Python mapper, i.e. the shape of the
+          reference pipeline `indexlr -t N | ntlink_pair.py`) on a bounded sample of the same reads
+
+N > 1 (torchrun): reads are sharded (weak scaling: every rank maps its own 30x read set against the same target);
+the target sketch is split over the ranks by contig and all-gathered with NCCL so every GPU builds the full
+replicated index; pair events are gathered to rank 0 with NCCL and tallied there.
+
+`--impl reference` times the CPU oracle port instead (the reference itself is Python + btllib and cannot run on
+the GPU box: /root/reference is absent there and btllib is not installed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+GENOME_BP = 5_000_000
+COVERAGE = 30
+K, W, Z = 32, 100, 1000
+SEED = 20240502
+
+
+def make_inputs(rank, world):
+    from ntlink_b200 import synth
+    gen = synth.genome(GENOME_BP, SEED)
+    contigs = synth.assembly(gen, SEED + 7)
+    reads = synth.reads(gen, COVERAGE, SEED + 1 + 1000 * rank, first_id=rank * 10_000_000)
+    return contigs, reads
+
+
+def pinned_copy(batch):
+    "same SeqBatch with its arrays in pinned host memory (torch is used for buffer management only)"
+    import torch
+    from ntlink_b200 import SeqBatch
+    seq = torch.empty(len(batch.seq) + 64, dtype=torch.uint8, pin_memory=True)
+    off = torch.empty(len(batch.offsets), dtype=torch.int64, pin_memory=True)
+    s = seq.numpy()
+    s[:len(batch.seq)] = batch.seq
+    s[len(batch.seq):] = ord("N")
+    o = off.numpy().view(np.uint64)
+    o[:] = batch.offsets
+    out = SeqBatch.__new__(SeqBatch)
+    out.seq, out.offsets, out.names, out._name_blob = s[:len(batch.seq)], o, batch.names, None
+    out._keep = (seq, off)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    "samples nvidia-smi clocks / throttle reasons while the timed region runs"
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.stop_flag, self.samples = gpu, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fin:
+            return float(json.load(fin)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_pipeline(contigs, reads, n_reads, threads):
+    """oracle port of the reference pipeline on the first n_reads reads: C sketcher (all threads) for target and
+    reads, TSV text in between, Python mapper (single thread, like bin/ntlink_pair.py). Returns (seconds, bases)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import util
+    import pair_oracle as po
+    n_reads = min(n_reads, len(reads))
+    sub_off = reads.offsets[:n_reads + 1]
+    sub_seq = reads.seq[:int(sub_off[-1])]
+    t0 = time.perf_counter()
+    th, tp, ts, to = util.oracle_sketch_batch(contigs.seq, contigs.offsets, K, W, threads=threads)
+    rh, rp, rs, ro = util.oracle_sketch_batch(sub_seq, sub_off, K, W, threads=threads)
+
+    def tsv(names, h, p, s, off, lens=None):
+        out = []
+        for i, n in enumerate(names):
+            a, b = int(off[i]), int(off[i + 1])
+            toks = " ".join(f"{x}:{y}:{'+' if z else '-'}" for x, y, z in zip(h[a:b].tolist(), p[a:b].tolist(), s[a:b].tolist()))
+            out.append(n + (f"\t{lens[i]}" if lens is not None else "") + "\t" + toks + "\n")
+        return out
+
+    t_lines = tsv(contigs.names, th, tp, ts, to)
+    r_lines = tsv(reads.names[:n_reads], rh, rp, rs, ro, np.diff(sub_off))
+    index = po.read_target_index(t_lines)
+    lengths = {n: int(l) for n, l in zip(contigs.names, contigs.lengths)}
+    prm = po.default_params(K, z=Z)
+    pairs = po.filter_pairs(po.map_reads(r_lines, index, lengths, prm), lengths, 1)
+    dt = time.perf_counter() - t0
+    return dt, int(sub_off[-1]), len(pairs)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    contigs, reads = make_inputs(0, 1)
+    threads = os.cpu_count() or 1
+    n_reads = args.cpu_reads
+    for _ in range(args.warmup):
+        cpu_pipeline(contigs, reads, max(50, n_reads // 10), threads)
+    t, bases = 0.0, 0
+    for _ in range(args.steps):
+        dt, nb, _ = cpu_pipeline(contigs, reads, n_reads, threads)
+        t += dt
+        bases += nb
+    val = bases / t / 1e9
+    line = {"impl": "reference", "metric": "long_read_gbp_per_s_sketched_mapped", "value": val, "unit": "Gbp/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic 5 Mbp genome, 1-200 kbp contigs, 30x ONT-like reads, k=32 w=100",
+                       "k": K, "w": W, "z": Z},
+            "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": threads, "kind": "port",
+                             "sample": f"first {n_reads} reads ({bases // args.steps} bp) against the full 5 Mbp target; "
+                                       "C oracle sketcher on all threads + single-threaded Python mapper (the reference's "
+                                       "ntlink_pair.py has no -t)"},
+            "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def build_index_distributed(ctx, contigs, rank, world, dist, torch):
+    """target sketch split over the ranks by contig, all-gathered over NCCL, index built on every GPU"""
+    import ctypes as C
+    from ntlink_b200 import SeqBatch, name_ranks
+    n = len(contigs)
+    cum = contigs.offsets.astype(np.int64)
+    bounds = [int(np.searchsorted(cum, cum[-1] * r // world)) for r in range(world)] + [n]
+    bounds[0] = 0
+    a, b = bounds[rank], bounds[rank + 1]
+    part = SeqBatch(contigs.seq[int(cum[a]):int(cum[b])], contigs.offsets[a:b + 1] - contigs.offsets[a], contigs.names[a:b])
+    sk = ctx.sketch(part, K, W)            # leaves the triples on the device as well; host copy used for contig ids
+    m = len(sk.hash)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cnt = torch.tensor([m], device=dev, dtype=torch.int64)
+    cnts = [torch.zeros(1, device=dev, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    cnts = [int(c.item()) for c in cnts]
+    mmax = max(max(cnts), 1)
+    ctg = (np.repeat(np.arange(a, b, dtype=np.uint32), np.diff(sk.seq_off).astype(np.int64)))
+    send = torch.zeros(mmax * 2, device=dev, dtype=torch.int64)       # [hash | (ctg << 32 | pos_strand)]
+    nmx, dh, dp, do = C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ctx._check(ctx.lib.ntl_device_sketch_arrays(ctx.h, C.byref(nmx), C.byref(dh), C.byref(dp), C.byref(do)), "arrays")
+    if m:
+        ctx._check(ctx.lib.ntl_copy_device(ctx.h, send.data_ptr(), dh, m * 8), "copy")
+        meta = torch.from_numpy((ctg.astype(np.int64) << 32) | sk.pos_strand.astype(np.int64)).to(dev)
+        send[mmax:mmax + m] = meta
+    recv = [torch.zeros(mmax * 2, device=dev, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(recv, send)
+    hashes = torch.cat([recv[r][:cnts[r]] for r in range(world)])
+    metas = torch.cat([recv[r][mmax:mmax + cnts[r]] for r in range(world)])
+    ctgs = (metas >> 32).to(torch.int32).contiguous()
+    posf = (metas & 0xFFFFFFFF).to(torch.int32).contiguous()
+    torch.cuda.synchronize()
+    cl = contigs.lengths.astype(np.uint32)
+    rk = name_ranks(contigs.names)
+    ctx._check(ctx.lib.ntl_index_build_device(ctx.h, hashes.data_ptr(), ctgs.data_ptr(), posf.data_ptr(), int(hashes.numel()),
+                                              cl.ctypes.data, rk.ctypes.data, n), "ntl_index_build_device")
+
+
+def gather_events(ctx, rank, world, dist, torch):
+    "pair events of every rank -> rank 0's device event log (NCCL all_gather of padded buffers)"
+    import ctypes as C
+    n, dptr = C.c_uint64(), C.c_void_p()
+    ctx._check(ctx.lib.ntl_events_device(ctx.h, C.byref(n), C.byref(dptr)), "events_device")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cnt = torch.tensor([n.value], device=dev, dtype=torch.int64)
+    cnts = [torch.zeros(1, device=dev, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    cnts = [int(c.item()) for c in cnts]
+    mmax = max(max(cnts), 1)
+    send = torch.zeros(mmax * 6, device=dev, dtype=torch.int32)
+    if n.value:
+        ctx._check(ctx.lib.ntl_copy_device(ctx.h, send.data_ptr(), dptr, n.value * 24), "copy")
+    recv = [torch.zeros(mmax * 6, device=dev, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(recv, send)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ctx.events_reset()
+        for r in range(world):
+            if cnts[r]:
+                ctx._check(ctx.lib.ntl_events_append_device(ctx.h, recv[r].data_ptr(), cnts[r]), "append")
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    from ntlink_b200 import Context
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    contigs, reads = make_inputs(rank, world)
+    ctx = Context(local_rank)
+    prm = ctx.params(K, W, Z)
+    read_bases = int(reads.offsets[-1])
+
+    # ---------------- resident arm (value)
+    ctx.target_upload(contigs)
+    ctx.reads_upload(reads)
+    stats = {}
+
+    def step_resident():
+        ctx.events_reset()
+        if world == 1:
+            ctx.index_build_resident(K, W)
+        else:
+            build_index_distributed(ctx, contigs, rank, world, dist, torch)
+        st = ctx.map_resident(prm, first_ordinal=0)
+        if world > 1:
+            gather_events(ctx, rank, world, dist, torch)
+        if rank == 0:
+            stats["pairs"] = len(ctx.pairs())
+        stats.update(st)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.timing_reset()
+    t0 = time.perf_counter()
+    ctx.mark(0)
+    for _ in range(args.steps):
+        step_resident()
+    ctx.mark(1)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ctx.mark_elapsed_ms()
+    tm = ctx.timing()
+    # the timed region is bracketed by syncs; use the larger of (device events, host wall) so that host gaps count
+    t_res = max(dev_ms / 1e3, wall)
+
+    # ---------------- end-to-end arm (e2e): pinned host buffers in, host results out
+    pc, pr = pinned_copy(contigs), pinned_copy(reads)
+    d2h = {}
+
+    def step_e2e():
+        ctx.events_reset()
+        if world == 1:
+            ctx.build_index_from_sequences(pc, K, W, want_sketch=False)
+        else:
+            build_index_distributed(ctx, pc, rank, world, dist, torch)
+        import ctypes as C
+        from ntlink_b200 import _lib
+        mo = _lib.MapOut()
+        ctx._check(ctx.lib.ntl_map_reads(ctx.h, pr.seq.ctypes.data, pr.offsets.ctypes.data, len(pr), 0, C.byref(prm), C.byref(mo)),
+                   "ntl_map_reads")
+        d2h["bytes"] = int(mo.n_hits) * 24 + int(mo.n_events) * 24 + (len(pr) + 1) * 16
+        if world > 1:
+            gather_events(ctx, rank, world, dist, torch)
+        if rank == 0:
+            d2h["pairs"] = len(ctx.pairs())
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.summary()
+
+    # ---------------- max over ranks
+    if dist is not None:
+        t = torch.tensor([t_res, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        total_bases = read_bases * world          # weak scaling: same-size shard per rank (rank 0's size x N)
+        value = total_bases * args.steps / t_res / 1e9
+        e2e = total_bases * args.steps / t_e2e / 1e9
+        peak, peak_kind = measured_peak()
+        n_mx = stats["mx"]
+        dense_ms = tm["dense"] / max(1, tm["dense_launches"])
+        # algorithmic bytes of the sketch per dense launch (1.0 B/base ASCII + 13 B/minimizer);
+        # each step has two dense launches (target, reads): average bytes per launch over the timed region
+        bases_per_launch = tm["dense_bases"] / max(1, tm["dense_launches"])
+        mx_per_base = n_mx / read_bases
+        alg_bytes = bases_per_launch * (1.0 + 13.0 * mx_per_base)
+        achieved = alg_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
+        line = {"metric": "long_read_gbp_per_s_sketched_mapped", "value": value, "unit": "Gbp/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": "configs[1]: synthetic 5 Mbp genome, 1-200 kbp contigs, 30x ONT-like reads "
+                                       "(4% sub, 3% ins, 3% del), k=32 w=100 z=1000",
+                           "read_bases_per_gpu": read_bases, "reads_per_gpu": len(reads), "contigs": len(contigs),
+                           "k": K, "w": W, "z": Z, "l2": "inputs larger than L2 (150 MB ASCII reads per step)",
+                           "step": "target sketch + index build + read sketch + lookup + chain + events + tally"},
+                "e2e": {"value": e2e, "unit": "Gbp/s",
+                        "h2d_bytes_per_step": int(len(pc.seq) + len(pr.seq) + 8 * (len(pc) + len(pr) + 2)),
+                        "d2h_bytes_per_step": int(d2h.get("bytes", 0)), "ms_per_step": 1e3 * t_e2e / args.steps},
+                "gpu_launches": int(tm["launches"]),
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "k_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                             "ms_per_launch": dense_ms, "launches": int(tm["dense_launches"]),
+                             "algorithmic_bytes_per_launch": alg_bytes,
+                             "note": "integer-ALU bound kernel (rolling ntHash); HBM fraction reported as the metric asks"},
+                "stage_ms_per_step": {k: tm[k] / args.steps for k in ("pack", "dense", "select", "gap", "emit", "lookup",
+                                                                      "chain", "tally", "index")},
+                "counts": {"read_minimizers": int(n_mx), "hits": int(stats["hits"]), "runs": int(stats["runs"]),
+                           "events": int(stats["events"]), "pairs": int(stats.get("pairs", 0))}}
+        if world == 1 and not args.no_cpu:
+            dt, nb, _ = cpu_pipeline(contigs, reads, args.cpu_reads, os.cpu_count() or 1)
+            line["cpu_baseline"] = {"value": nb / dt / 1e9, "unit": "Gbp/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"first {min(args.cpu_reads, len(reads))} reads ({nb} bp) against the full target, "
+                                              f"{dt:.1f} s; C oracle sketcher on all threads + single-threaded Python mapper"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ntlink_b200", choices=["ntlink_b200", "reference"])
+    ap.add_argument("--cpu-reads", type=int, default=1500, help="reads in the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

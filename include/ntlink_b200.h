@@ -208,6 +208,13 @@ int ntl_timing_reset(ntl_ctx* ctx);
 int ntl_timing(ntl_ctx* ctx, double* ms_accum /* [NTL_T_NUM] */, uint64_t* launches, uint64_t* dense_launches,
                uint64_t* dense_bases);
 int ntl_device_sync(ntl_ctx* ctx);
+/* CUDA-event stopwatch on the library's stream: ntl_mark(ctx, 0) ... work ... ntl_mark(ctx, 1); after a sync
+ * ntl_mark_elapsed gives the device time between the two marks in milliseconds */
+int ntl_mark(ntl_ctx* ctx, int which);
+int ntl_mark_elapsed(ntl_ctx* ctx, double* ms);
+/* device-to-device copy on the library's stream (synchronous on return); lets the caller move the library's device
+ * arrays into buffers it owns (e.g. torch tensors handed to NCCL) */
+int ntl_copy_device(ntl_ctx* ctx, void* d_dst, const void* d_src, uint64_t bytes);
 
 #ifdef __cplusplus
 }

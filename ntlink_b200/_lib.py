@@ -98,6 +98,9 @@ SIGNATURES = {
     "ntl_timing_reset": (C.c_int, [_VP]),
     "ntl_timing": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P, _U64P, _U64P]),
     "ntl_device_sync": (C.c_int, [_VP]),
+    "ntl_mark": (C.c_int, [_VP, C.c_int]),
+    "ntl_mark_elapsed": (C.c_int, [_VP, C.POINTER(C.c_double)]),
+    "ntl_copy_device": (C.c_int, [_VP, _VP, _VP, C.c_uint64]),
 }
 
 _lib = None

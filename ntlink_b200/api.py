@@ -337,5 +337,13 @@ class Context:
         d.update(launches=a.value, dense_launches=b.value, dense_bases=c.value)
         return d
 
+    def mark(self, which):
+        self._check(self.lib.ntl_mark(self.h, which), "ntl_mark")
+
+    def mark_elapsed_ms(self):
+        ms = C.c_double()
+        self._check(self.lib.ntl_mark_elapsed(self.h, C.byref(ms)), "ntl_mark_elapsed")
+        return ms.value
+
     def sync(self):
         self._check(self.lib.ntl_device_sync(self.h), "ntl_device_sync")

@@ -101,6 +101,7 @@ int ntl_init(int device, ntl_ctx** out) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete res_of(c); delete c; return NTL_ERR_CUDA; }
     for (int i = 0; i < 2 * T_NUM; i++) cudaEventCreate(&c->ev[i]);
+    cudaEventCreate(&c->mark[0]); cudaEventCreate(&c->mark[1]);
     for (int i = 0; i < T_NUM; i++) { c->ev_used[i] = false; c->ms_accum[i] = 0; }
     *out = c;
     return NTL_OK;
@@ -130,6 +131,7 @@ void ntl_destroy(ntl_ctx* c) {
     R->h_off.release();
     c->h_status.release();
     for (int i = 0; i < 2 * T_NUM; i++) cudaEventDestroy(c->ev[i]);
+    cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]);
     cudaStreamDestroy(c->stream);
     delete R;
     delete c;
@@ -552,6 +554,28 @@ int ntl_timing(ntl_ctx* c, double* ms_accum, uint64_t* launches, uint64_t* dense
     if (launches) *launches = c->launches;
     if (dense_launches) *dense_launches = c->dense_launches;
     if (dense_bases) *dense_bases = c->dense_bases;
+    return NTL_OK;
+}
+int ntl_mark(ntl_ctx* c, int which) {
+    if (!c || which < 0 || which > 1) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    NTL_CUDA(c, cudaEventRecord(c->mark[which], c->stream));
+    return NTL_OK;
+}
+int ntl_mark_elapsed(ntl_ctx* c, double* ms) {
+    if (!c || !ms) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    NTL_CUDA(c, cudaEventSynchronize(c->mark[1]));
+    float f = 0;
+    NTL_CUDA(c, cudaEventElapsedTime(&f, c->mark[0], c->mark[1]));
+    *ms = f;
+    return NTL_OK;
+}
+int ntl_copy_device(ntl_ctx* c, void* d_dst, const void* d_src, uint64_t bytes) {
+    if (!c || (bytes && (!d_dst || !d_src))) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (bytes) NTL_CUDA(c, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
     return NTL_OK;
 }
 int ntl_device_sync(ntl_ctx* c) {

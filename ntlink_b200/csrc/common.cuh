@@ -119,6 +119,7 @@ struct ntl_ctx {
     uint64_t batch_bases = 1ull << 30;
     // timing
     cudaEvent_t ev[2 * ntl::T_NUM];
+    cudaEvent_t mark[2];
     bool ev_used[ntl::T_NUM];
     double ms_accum[ntl::T_NUM];           // accumulated since ntl_timing_reset
     uint64_t launches = 0;                 // kernels launched since ntl_timing_reset

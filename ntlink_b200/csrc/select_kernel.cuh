@@ -1,0 +1,165 @@
+// select_kernel.cuh -- k_select: the exact minimizer decision for every candidate (included by sketch.cu).
+//
+// SIMT-friendly shape: a block stages the candidates of SEL_STRIPS consecutive strips plus SEL_CTX strips of
+// context on each side in shared memory as two compact arrays (value, valid-k-mer index); then every thread takes
+// one candidate and scans its neighbours left (first strictly smaller) and right (first smaller-or-equal) in shared
+// memory with two short, simple loops. The rule applied is exactly select_candidate (sketch_logic.cuh); whatever
+// the staged range cannot answer (context cut short by N runs, strips that overflowed their slots, more than
+// SEL_CAP candidates) falls back to select_candidate on global memory, candidate by candidate.
+#pragma once
+
+namespace ntl {
+namespace {
+
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_STRIPS = 32;     // strips decided per block
+constexpr int SEL_CTX = 3;         // context strips staged on each side
+constexpr int SEL_NL = SEL_STRIPS + 2 * SEL_CTX;
+constexpr int SEL_CAP = 2560;      // candidates staged per block (30 KB)
+
+__global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restrict__ seq_off,
+                                                         const uint32_t* __restrict__ strip_off, SkParams P, CandView V,
+                                                         uint8_t* __restrict__ sel, uint32_t* __restrict__ selcnt,
+                                                         GapRec* __restrict__ gaps, uint32_t* __restrict__ gap_head,
+                                                         SketchStatus* __restrict__ st) {
+    __shared__ uint64_t sh_h[SEL_CAP];
+    __shared__ uint32_t sh_i[SEL_CAP];
+    __shared__ uint32_t sh_off[SEL_NL + 1];       // compact offset of every staged strip
+    __shared__ uint32_t sh_cnt[SEL_NL];
+    __shared__ uint32_t sh_q[SEL_NL], sh_fs[SEL_NL], sh_es[SEL_NL], sh_idx0[SEL_NL], sh_n[SEL_NL], sh_np[SEL_NL];
+    __shared__ uint32_t sh_sel[SEL_STRIPS];
+    __shared__ uint32_t sh_bad;                   // the staged range cannot be used -> whole block falls back
+
+    const uint32_t nstrips = st->nstrips;
+    const uint32_t b0 = blockIdx.x * SEL_STRIPS;
+    if (b0 >= nstrips) return;
+    const uint32_t b1 = min(b0 + SEL_STRIPS, nstrips);
+    const uint32_t l0 = b0 > SEL_CTX ? b0 - SEL_CTX : 0;
+    const uint32_t l1 = min(b1 + SEL_CTX, nstrips);
+    const uint32_t nl = l1 - l0;
+    const uint32_t tid = threadIdx.x;
+
+    if (tid == 0) sh_bad = 0;
+    if (tid < SEL_STRIPS) sh_sel[tid] = 0;
+    __syncthreads();
+    // per staged strip: candidate count and sequence bounds; offsets by a tiny serial scan (nl <= 38)
+    if (tid < nl) {
+        const uint32_t s = l0 + tid;
+        uint32_t c = V.cnt[s];
+        if (c > V.cap) { sh_bad = 1; c = 0; }
+        sh_cnt[tid] = c;
+        const uint32_t q = seq_of_strip(strip_off, P.nseq, s);
+        const uint32_t fs = strip_off[q], es = strip_off[q + 1];
+        sh_q[tid] = q; sh_fs[tid] = fs; sh_es[tid] = es;
+        sh_idx0[tid] = V.vbase[fs]; sh_n[tid] = V.vbase[es] - V.vbase[fs];
+        sh_np[tid] = seq_npos(seq_off[q + 1] - seq_off[q], P.k, P.w);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (uint32_t t = 0; t < nl; t++) { sh_off[t] = acc; acc += sh_cnt[t]; }
+        sh_off[nl] = acc;
+    }
+    __syncthreads();
+    const uint32_t total = sh_off[nl];
+    const bool staged = (sh_bad == 0) && (total <= SEL_CAP);
+    __syncthreads();
+
+    if (staged) {
+        for (uint32_t e = tid; e < total; e += SEL_THREADS) {
+            uint32_t lo = 0, hi = nl;             // strip t with sh_off[t] <= e < sh_off[t+1]
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_off[mid] <= e) lo = mid; else hi = mid; }
+            const uint32_t s = l0 + lo;
+            const Cand cd = V.cands[(uint64_t)s * V.cap + (e - sh_off[lo])];
+            sh_h[e] = cd.h0;
+            sh_i[e] = V.vbase[s] + cd.lord;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t w = P.w;
+    const int64_t W1 = (int64_t)w - 1;
+    if (staged) {
+        const uint32_t e_begin = sh_off[b0 - l0], e_end = sh_off[b1 - l0];
+        const int64_t first_idx = V.vbase[l0], end_idx = V.vbase[l1];   // valid k-mers covered by the staged strips
+        for (uint32_t e = e_begin + tid; e < e_end; e += SEL_THREADS) {
+            uint32_t lo = b0 - l0, hi = b1 - l0;
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_off[mid] <= e) lo = mid; else hi = mid; }
+            const uint32_t t = lo, s = l0 + t, j = e - sh_off[t];
+            const uint32_t fs = sh_fs[t], es = sh_es[t];
+            const int64_t idx0 = sh_idx0[t], n = sh_n[t];
+            const uint64_t val = sh_h[e];
+            const int64_t idx = sh_i[e], rel = idx - idx0;
+            const uint32_t e_lo = sh_off[(fs > l0 ? fs : l0) - l0];      // staged candidates of the same sequence
+            const uint32_t e_hi = sh_off[(es < l1 ? es : l1) - l0];
+            bool need_fallback = false;
+            // left: first strictly smaller value
+            int64_t A = -1;
+            for (uint32_t p = e; p > e_lo;) {
+                p--;
+                const int64_t d = idx - (int64_t)sh_i[p];
+                if (d >= (int64_t)w) { A = W1; break; }
+                if (sh_h[p] < val) { A = d - 1; break; }
+            }
+            if (A < 0) {
+                if (fs >= l0) A = rel;                                   // the sequence starts inside the staged range
+                else if (idx - first_idx >= W1) A = W1;                  // everything earlier is out of reach
+                else need_fallback = true;
+            }
+            // right: first smaller-or-equal value; the immediate neighbour bounds the candidate-free stretch
+            int64_t B = -1;
+            uint32_t gap_len = 0, gap_end = 0;
+            bool gap_known = true;
+            if (e + 1 < e_hi) gap_len = (uint32_t)((int64_t)sh_i[e + 1] - idx - 1);
+            else if (es <= l1) { gap_len = (uint32_t)(idx0 + n - 1 - idx); gap_end = sh_np[t]; }
+            else gap_known = false;
+            for (uint32_t p = e + 1; p < e_hi; p++) {
+                const int64_t d = (int64_t)sh_i[p] - idx;
+                if (d >= (int64_t)w) { B = W1; break; }
+                if (sh_h[p] <= val) { B = d - 1; break; }
+            }
+            if (B < 0) {
+                if (es <= l1) B = idx0 + n - 1 - idx;                    // the sequence ends inside the staged range
+                else if (end_idx - idx > W1) B = W1;
+                else need_fallback = true;
+            }
+            const uint64_t gid = (uint64_t)s * V.cap + j;
+            bool selected;
+            if (need_fallback || !gap_known) {
+                const SelectResult r = select_candidate(V, s, j, fs, es, w, sh_np[t]);
+                selected = r.selected; gap_len = r.gap_len; gap_end = r.gap_end;
+            } else {
+                int64_t lo_w = rel - W1; if (lo_w < 0) lo_w = 0; if (rel - A > lo_w) lo_w = rel - A;
+                int64_t hi_w = rel; if (n - (int64_t)w < hi_w) hi_w = n - (int64_t)w; if (rel + B - W1 < hi_w) hi_w = rel + B - W1;
+                selected = lo_w <= hi_w;
+                if (gap_len >= w && e + 1 < e_hi) {                      // position of the neighbour that ends the stretch
+                    uint32_t lo2 = t, hi2 = nl;
+                    while (hi2 - lo2 > 1) { const uint32_t mid = (lo2 + hi2) >> 1; if (sh_off[mid] <= e + 1) lo2 = mid; else hi2 = mid; }
+                    gap_end = V.cands[(uint64_t)(l0 + lo2) * V.cap + (e + 1 - sh_off[lo2])].posf & POS_MASK;
+                }
+            }
+            sel[gid] = selected ? 1 : 0;
+            if (selected) atomicAdd(&sh_sel[t - (b0 - l0)], 1u);
+            if (gap_len >= w) queue_gap(gaps, gap_head, st, P, sh_q[t], (V.cands[gid].posf & POS_MASK) + 1, gap_end, s, j, gap_len);
+        }
+    } else {
+        // fallback for the whole block: per-candidate neighbour scan on global memory
+        for (uint32_t t = b0 - l0; t < b1 - l0; t++) {
+            const uint32_t s = l0 + t;
+            const uint32_t c = V.cnt[s];
+            for (uint32_t j = tid; j < c; j += SEL_THREADS) {
+                const SelectResult r = select_candidate(V, s, j, sh_fs[t], sh_es[t], w, sh_np[t]);
+                const uint64_t gid = cand_gid(V, s, j);
+                sel[gid] = r.selected ? 1 : 0;
+                if (r.selected) atomicAdd(&sh_sel[t - (b0 - l0)], 1u);
+                if (r.gap_len >= w)
+                    queue_gap(gaps, gap_head, st, P, sh_q[t], (V.cands[gid].posf & POS_MASK) + 1, r.gap_end, s, j, r.gap_len);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < b1 - b0) selcnt[b0 + tid] = sh_sel[tid];
+}
+
+}  // namespace
+}  // namespace ntl

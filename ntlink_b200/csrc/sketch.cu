@@ -99,26 +99,133 @@ __device__ __forceinline__ uint32_t seq_of_strip(const uint32_t* __restrict__ st
 }
 
 struct SlotEmit {
-    Cand* dst;
-    uint32_t cap, count;
+    uint4* p;          // next slot (a Cand is exactly one uint4: h0.lo, h0.hi, posf, lord)
+    int32_t room;      // free slots left; keeps counting below zero so that cap - room = total candidates
     __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) {
-        if (count < cap) {
-            Cand c; c.h0 = h0; c.posf = pos | (fwd ? FWD_BIT : 0u); c.lord = lord;
-            dst[count] = c;
-        }
-        count++;
+        if (room > 0) *p = make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), pos | (fwd ? FWD_BIT : 0u), lord);
+        p++;
+        room--;
     }
 };
+
+// ---- the hot loop, device-only formulation --------------------------------------------------------------------
+// Same arithmetic as process_strip (sketch_logic.cuh) but shaped for the integer pipes of an SM:
+//  * hash state in four 32-bit registers; the split 33/31-bit rotations are 3-input LOP3s and funnel shifts
+//    (7 ALU ops per hash per base);
+//  * roll table in shared memory with a 256-byte entry stride and 16 interleaved copies: the LDS.128 address of an
+//    entry is produced by ONE byte-permute (PRMT) from a per-block word of precomputed (in<<3|out) bytes and the
+//    lane's copy offset, and a quarter-warp always touches 8 different 16-byte bank groups (conflict-free);
+//  * lead-in blocks never test for candidates, interior blocks carry no bounds or validity checks; everything
+//    irregular (sequence tail, first output block, blocks containing N) goes through the generic block.
+struct H32 { uint32_t flo, fhi, rlo, rhi; };
+
+__device__ __forceinline__ void roll32(H32& h, const uint4 t) {
+    const uint32_t a = h.flo << 1;
+    const uint32_t b = __funnelshift_l(h.flo, h.fhi, 1);
+    const uint32_t c = h.fhi >> 30;
+    const uint32_t lo = a ^ (h.fhi & 1u) ^ t.x;            // bit32 -> bit0
+    const uint32_t hi = b ^ ((b ^ c) & 2u) ^ t.y;          // bit63 -> bit33
+    const uint32_t xlo = h.rlo ^ t.z, xhi = h.rhi ^ t.w;
+    const uint32_t rl = __funnelshift_r(xlo, xhi, 1);
+    const uint32_t s = xhi >> 1;
+    const uint32_t u = (s & ~1u) | (xlo & 1u);             // bit0 -> bit32
+    const uint32_t rh = u | ((xhi << 30) & 0x80000000u);   // bit33 -> bit63
+    h.flo = lo; h.fhi = hi; h.rlo = rl; h.rhi = rh;
+}
+
+enum : uint32_t { TBL_STRIDE = 256, TBL_COPIES = 16 };     // bytes per entry, copies per entry
+
+__device__ __forceinline__ uint4 tbl_fetch(const unsigned char* tbl_s, uint32_t comb, uint32_t lanebase, uint32_t sel) {
+    const uint32_t off = __byte_perm(comb, lanebase, sel); // (entry << 8) | (copy << 4)
+    return *reinterpret_cast<const uint4*>(tbl_s + off);
+}
+
+// generic block (8 steps) with bounds and validity checks; identical to the slow branch of process_strip
+template <class Emit>
+__device__ __forceinline__ void generic_block(H32& h, uint32_t wi, uint32_t wo, int32_t t, int32_t lead, int32_t T, int32_t k,
+                                              int32_t& last_bad, uint32_t& nv, uint32_t p0, uint32_t tau_hi,
+                                              const unsigned char* tbl_s, uint32_t lanebase, Emit& emit) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int32_t s = t + j;
+        const uint32_t cin = (wi >> (4 * j)) & 7u;
+        const uint32_t e = (cin << 3) | ((wo >> (4 * j)) & 7u);
+        roll32(h, *reinterpret_cast<const uint4*>(tbl_s + e * TBL_STRIDE + lanebase));
+        if (cin >= CODE_INVALID) last_bad = s;
+        if (s >= lead && s < T && s - last_bad >= k) {
+            const uint64_t fh = ((uint64_t)h.fhi << 32) | h.flo, rh = ((uint64_t)h.rhi << 32) | h.rlo;
+            const uint64_t h0 = fh + rh;
+            if ((uint32_t)(h0 >> 32) < tau_hi) emit(h0, p0 + (uint32_t)(s - lead), fh <= rh, nv);
+            nv++;
+        }
+    }
+}
+
+template <class Emit>
+__device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict__ packed, uint64_t gseq, uint32_t p0, uint32_t n,
+                                                      uint32_t k, const unsigned char* tbl_s, uint32_t lanebase,
+                                                      uint32_t tau_hi, Emit& emit) {
+    const uint64_t g0 = gseq + p0;
+    const int32_t T = (int32_t)(k - 1 + n);
+    const int32_t lead = (int32_t)k - 1;
+    H32 h = {0, 0, 0, 0};
+    int32_t last_bad = -(1 << 30);
+    uint32_t nv = 0;
+    // sequential word streams: cur/next aligned words of the entering bases, funnel-shifted to the strip's phase
+    const uint32_t* pin = packed + (g0 >> 3);
+    const uint32_t sh_in = (uint32_t)(g0 & 7) * 4;
+    uint32_t in_lo = pin[0];
+    for (int32_t t = 0; t < T; t += 8) {
+        const uint32_t in_hi = pin[(t >> 3) + 1];
+        const uint32_t wi = __funnelshift_r(in_lo, in_hi, sh_in);
+        in_lo = in_hi;
+        uint32_t wo;
+        const int32_t o = t - (int32_t)k;
+        if (o >= 0) wo = fetch8(packed, g0 + (uint32_t)o);
+        else if (o <= -8) wo = 0x44444444u;
+        else {
+            const uint32_t sh = 4u * (uint32_t)(-o);
+            wo = (fetch8(packed, g0) << sh) | (0x44444444u & ((1u << sh) - 1u));
+        }
+        const bool clean = ((wi & 0x44444444u) == 0u);
+        if (clean && t + 8 <= lead) {
+            // lead-in: no k-mer completes in this block -> roll only
+            const uint32_t ce = (wi & 0x0F0F0F0Fu) * 8u + (wo & 0x0F0F0F0Fu);
+            const uint32_t co = ((wi >> 4) & 0x0F0F0F0Fu) * 8u + ((wo >> 4) & 0x0F0F0F0Fu);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
+        } else if (clean && t >= lead && t + 8 <= T && t - last_bad >= (int32_t)k) {
+            // interior: 8 valid, in-range k-mers
+            const uint32_t ce = (wi & 0x0F0F0F0Fu) * 8u + (wo & 0x0F0F0F0Fu);
+            const uint32_t co = ((wi >> 4) & 0x0F0F0F0Fu) * 8u + ((wo >> 4) & 0x0F0F0F0Fu);
+            const uint32_t pos0 = p0 + (uint32_t)(t - lead);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
+                const uint64_t fh = ((uint64_t)h.fhi << 32) | h.flo, rh = ((uint64_t)h.rhi << 32) | h.rlo;
+                const uint64_t h0 = fh + rh;
+                if ((uint32_t)(h0 >> 32) < tau_hi) emit(h0, pos0 + j, fh <= rh, nv + j);
+            }
+            nv += 8;
+        } else {
+            generic_block(h, wi, wo, t, lead, T, (int32_t)k, last_bad, nv, p0, tau_hi, tbl_s, lanebase, emit);
+        }
+    }
+    return nv;
+}
 
 __global__ void __launch_bounds__(128) k_dense(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
                                                const uint32_t* __restrict__ strip_off, SkParams P,
                                                const RollEntry* __restrict__ tbl_g, Cand* __restrict__ slots,
                                                uint32_t* __restrict__ cnt, uint32_t* __restrict__ nv,
                                                uint8_t* __restrict__ has_cand, SketchStatus* __restrict__ st) {
-    // roll table, 8 interleaved copies: entry e, copy c at [e*8 + c]; a quarter-warp (one LDS.128 phase) reads
-    // 8 different copies = 8 different 16-byte bank groups -> conflict-free whatever the entries are
-    __shared__ RollEntry tbl_s[ROLL_TABLE_ENTRIES * 8];
-    for (uint32_t i = threadIdx.x; i < ROLL_TABLE_ENTRIES * 8; i += blockDim.x) tbl_s[i] = tbl_g[i >> 3];
+    // entry e, copy c at byte offset e*256 + c*16
+    __shared__ __align__(256) unsigned char tbl_s[ROLL_TABLE_ENTRIES * TBL_STRIDE];
+    for (uint32_t i = threadIdx.x; i < ROLL_TABLE_ENTRIES * TBL_COPIES; i += blockDim.x) {
+        const RollEntry e = tbl_g[i / TBL_COPIES];
+        reinterpret_cast<uint4*>(tbl_s)[i] = make_uint4((uint32_t)e.f, (uint32_t)(e.f >> 32), (uint32_t)e.r, (uint32_t)(e.r >> 32));
+    }
     __syncthreads();
     const uint32_t nstrips = strip_off[P.nseq];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,12 +236,13 @@ __global__ void __launch_bounds__(128) k_dense(const uint32_t* __restrict__ pack
     const uint32_t np = seq_npos(seq_off[q + 1] - gseq, P.k, P.w);
     const uint32_t p0 = (s - strip_off[q]) * P.S;
     const uint32_t n = min(P.S, np - p0);
-    SlotEmit em{slots + (uint64_t)s * P.cap, P.cap, 0};
-    const uint32_t nvalid = process_strip(packed, gseq, p0, n, P.k, tbl_s + (threadIdx.x & 7), 8, P.tau_hi, em);
-    cnt[s] = em.count;
+    SlotEmit em{reinterpret_cast<uint4*>(slots + (uint64_t)s * P.cap), (int32_t)P.cap};
+    const uint32_t nvalid = process_strip_dev(packed, gseq, p0, n, P.k, tbl_s, (threadIdx.x & 15u) << 4, P.tau_hi, em);
+    const uint32_t count = (uint32_t)((int32_t)P.cap - em.room);
+    cnt[s] = count;
     nv[s] = nvalid;
-    if (em.count) has_cand[q] = 1;
-    if (em.count > P.cap) atomicAdd(&st->n_ovf, 1u);
+    if (count) has_cand[q] = 1;
+    if (count > P.cap) atomicAdd(&st->n_ovf, 1u);
 }
 
 struct PoolEmit {
@@ -184,32 +292,11 @@ __device__ __forceinline__ void queue_gap(GapRec* gaps, uint32_t* gap_head, Sket
     gaps[id] = g;
 }
 
-__global__ void __launch_bounds__(128) k_select(const uint64_t* __restrict__ seq_off, const uint32_t* __restrict__ strip_off,
-                                                SkParams P, CandView V, uint8_t* __restrict__ sel,
-                                                uint32_t* __restrict__ selcnt, GapRec* __restrict__ gaps,
-                                                uint32_t* __restrict__ gap_head, SketchStatus* __restrict__ st) {
-    const uint32_t nstrips = st->nstrips;
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nstrips) return;
-    const uint32_t c = V.cnt[s];
-    if (c == 0) { selcnt[s] = 0; return; }
-    const uint32_t q = seq_of_strip(strip_off, P.nseq, s);
-    const uint32_t fs = strip_off[q], es = strip_off[q + 1];
-    const uint32_t np = seq_npos(seq_off[q + 1] - seq_off[q], P.k, P.w);
-    uint32_t nsel = 0;
-    for (uint32_t j = 0; j < c; j++) {
-        const SelectResult r = select_candidate(V, s, j, fs, es, P.w, np);
-        const uint64_t gid = cand_gid(V, s, j);
-        sel[gid] = r.selected ? 1 : 0;
-        nsel += r.selected ? 1u : 0u;
-        if (r.gap_len >= P.w) {
-            const uint32_t pos = V.cands[gid].posf & POS_MASK;
-            queue_gap(gaps, gap_head, st, P, q, pos + 1, r.gap_end, s, j, r.gap_len);
-        }
-    }
-    selcnt[s] = nsel;
-    atomicAdd(&st->n_cand, c);
-}
+}  // namespace
+}  // namespace ntl
+#include "select_kernel.cuh"   // k_select (block-cooperative, shared-memory neighbour scans)
+namespace ntl {
+namespace {
 
 // candidate-free stretch at the start of a sequence (or the whole sequence)
 __global__ void k_seq_gaps(const uint64_t* __restrict__ seq_off, const uint32_t* __restrict__ strip_off, SkParams P,
@@ -245,6 +332,9 @@ __global__ void __launch_bounds__(64) k_gap(const uint32_t* __restrict__ packed,
                                             SkParams P, const RollEntry* __restrict__ tbl_g, GapRec* __restrict__ gaps,
                                             Cand* __restrict__ extras, uint32_t* __restrict__ selcnt,
                                             SketchStatus* __restrict__ st) {
+    __shared__ RollEntry tbl_s[ROLL_TABLE_ENTRIES];
+    for (uint32_t i = threadIdx.x; i < ROLL_TABLE_ENTRIES; i += blockDim.x) tbl_s[i] = tbl_g[i];
+    __syncthreads();
     const uint32_t ng = min(st->ngaps, P.gaps_cap);
     for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < ng; id += gridDim.x * blockDim.x) {
         GapRec g = gaps[id];
@@ -252,7 +342,7 @@ __global__ void __launch_bounds__(64) k_gap(const uint32_t* __restrict__ packed,
         const uint64_t gseq = seq_off[g.seq];
         const uint32_t L = (uint32_t)(seq_off[g.seq + 1] - gseq);
         ExtraEmit em{extras + g.out_off, 0, g.max_out};
-        gap_scan(packed, tbl_g, gseq, L, P.k, P.w, g.start_pos, g.end_pos, em);
+        gap_scan(packed, tbl_s, gseq, L, P.k, P.w, g.start_pos, g.end_pos, em);
         const uint32_t n = min(em.count, g.max_out);
         gaps[id].out_cnt = n;
         if (n) atomicAdd(&selcnt[g.strip], n);
@@ -404,7 +494,7 @@ retry:
     CandView V;
     V.cands = W.slots.as<Cand>(); V.cnt = W.cnt.as<uint32_t>(); V.ovf_off = W.ovf_off.as<uint32_t>();
     V.vbase = W.vbase.as<uint32_t>(); V.cap = cap; V.pool_base = P.pool_base;
-    k_select<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
+    k_select<<<div_up(nstrips_max, SEL_STRIPS), SEL_THREADS, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
                                                              W.selcnt.as<uint32_t>(), W.gaps.as<GapRec>(),
                                                              W.gap_head.as<uint32_t>(), st);
     k_seq_gaps<<<div_up(nseq, 128), 128, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.has_cand.as<uint8_t>(),

@@ -33,7 +33,7 @@
 namespace ntl {
 
 // A candidate k-mer. 16 bytes, written with one 128-bit store.
-struct Cand {
+struct alignas(16) Cand {
     uint64_t h0;     // canonical hash (orders the window)
     uint32_t posf;   // k-mer start position | (forward-strand flag << 31)
     uint32_t lord;   // number of valid k-mers of the same strip before this one
@@ -132,8 +132,19 @@ struct KmerWalker {
     uint32_t L, k;
     uint32_t pos;
     uint64_t fh, rh;
+    // two cached 8-base windows of the packed sequence (entering / leaving base streams are sequential)
+    uint32_t win, wout, in_base, out_base;
 
+    NTL_HD void reset_cache() { in_base = NONE32; out_base = NONE32; win = 0; wout = 0; }
     NTL_HD uint32_t code(uint32_t i) const { return fetch1(packed, gseq + i); }
+    NTL_HD uint32_t code_in(uint32_t i) {
+        if (in_base == NONE32 || i - in_base >= 8u) { in_base = i; win = fetch8(packed, gseq + i); }
+        return (win >> (4u * (i - in_base))) & 7u;
+    }
+    NTL_HD uint32_t code_out(uint32_t i) {
+        if (out_base == NONE32 || i - out_base >= 8u) { out_base = i; wout = fetch8(packed, gseq + i); }
+        return (wout >> (4u * (i - out_base))) & 7u;
+    }
 
     // first valid k-mer starting at or after p; false if there is none
     NTL_HD bool seek(uint32_t p) {
@@ -145,7 +156,7 @@ struct KmerWalker {
             if (bad >= 0) { p = (uint32_t)bad + 1; continue; }
             fh = 0; rh = 0;
             for (uint32_t j = 0; j < k; j++) {
-                const RollEntry re = tbl[(code(p + j) << 3) | CODE_INVALID];
+                const RollEntry re = tbl[(code_in(p + j) << 3) | CODE_INVALID];
                 fh = srol1(fh) ^ re.f;
                 rh = sror1(rh ^ re.r);
             }
@@ -156,9 +167,9 @@ struct KmerWalker {
     // next valid k-mer after the current one
     NTL_HD bool next() {
         if ((uint64_t)pos + 1 + k > L) return false;
-        const uint32_t cin = code(pos + k);
+        const uint32_t cin = code_in(pos + k);
         if (cin >= CODE_INVALID) return seek(pos + k + 1);
-        const RollEntry re = tbl[(cin << 3) | code(pos)];
+        const RollEntry re = tbl[(cin << 3) | code_out(pos)];
         fh = srol1(fh) ^ re.f;
         rh = sror1(rh ^ re.r);
         pos++;
@@ -175,7 +186,10 @@ struct KmerWalker {
 template <class Out>
 NTL_HD uint32_t gap_scan(const uint32_t* packed, const RollEntry* tbl, uint64_t gseq, uint32_t L, uint32_t k,
                          uint32_t w, uint32_t start_pos, uint32_t end_pos, Out& out) {
-    KmerWalker head{packed, tbl, gseq, L, k, 0, 0, 0}, tail = head;
+    KmerWalker head;
+    head.packed = packed; head.tbl = tbl; head.gseq = gseq; head.L = L; head.k = k; head.pos = 0; head.fh = 0; head.rh = 0;
+    head.reset_cache();
+    KmerWalker tail = head;
     if (!head.seek(start_pos) || head.pos >= end_pos) return 0;
     tail = head;                                  // tail = left end of the current window
     uint64_t t = 0;                               // index (within the range) of head's k-mer
@@ -308,6 +322,140 @@ NTL_HD SelectResult select_candidate(const CandView& v, uint32_t s, uint32_t j, 
     int64_t hi = rel; if (n - (int64_t)w < hi) hi = n - (int64_t)w; if (rel + B - W1 < hi) hi = rel + B - W1;
     res.selected = lo <= hi;
     return res;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One pass over a whole strip: the same decisions as select_candidate for every candidate of strip s, but in
+// O(#candidates) with a monotone stack (all-nearest-smaller-values): walk the candidates from (w-1) valid k-mers
+// before the strip to (w-1) after it; when a candidate x arrives every stacked candidate with value >= x.h0 is
+// popped -- x is its first smaller-or-equal neighbour on the right, and the entry below it on the stack is its
+// first strictly smaller neighbour on the left. Candidates outside the strip only serve as context.
+//   sel        flags indexed by candidate id (cand_gid)
+//   gap(j, gap_len, gap_end)   called for every own candidate j followed by >= w candidate-free valid k-mers
+// Returns the number of selected candidates, or NONE32 when the stack would overflow (caller falls back to
+// select_candidate; only degenerate hash sequences nest deeper than SEL_STACK).
+// ---------------------------------------------------------------------------------------------------
+enum : uint32_t { SEL_STACK = 16 };
+
+// stack storage: entry d of this thread lives at index d * stride (shared memory, one column per thread, on the
+// device; a plain local array with stride 1 on the host)
+struct SelStack { uint64_t* h; uint32_t* i; uint32_t* j; uint32_t stride; };
+
+template <class GapFn>
+NTL_HD uint32_t select_strip(const CandView& v, uint32_t s, uint32_t fs, uint32_t es, uint32_t w, uint32_t npos,
+                             uint8_t* sel, GapFn& gap, const SelStack& S) {
+    const uint32_t c = v.cnt[s];
+    if (c == 0) return 0;
+    const int64_t idx0 = v.vbase[fs];
+    const int64_t n = (int64_t)v.vbase[es] - idx0;
+    const int64_t W1 = (int64_t)w - 1;
+    const uint64_t own_base = cand_gid(v, s, 0);
+    const int64_t i_first = (int64_t)v.vbase[s] + v.cands[own_base].lord;
+    const int64_t i_last = (int64_t)v.vbase[s] + v.cands[own_base + c - 1].lord;
+
+    // ---- candidate-free stretches of >= w valid k-mers after an own candidate (independent of the stack walk, so
+    //      a stack overflow below never loses or duplicates a gap)
+    {
+        int64_t prev = i_first;
+        for (uint32_t j = 1; j < c; j++) {
+            const Cand y = v.cands[own_base + j];
+            const int64_t yi = (int64_t)v.vbase[s] + y.lord;
+            if (yi - prev - 1 >= (int64_t)w) gap(j - 1, (uint32_t)(yi - prev - 1), y.posf & POS_MASK);
+            prev = yi;
+        }
+        uint32_t ns = s;
+        bool found = false;
+        while (ns + 1 < es) { ns++; if (v.cnt[ns]) { found = true; break; } }
+        if (found) {
+            const Cand y = v.cands[cand_gid(v, ns, 0)];
+            const int64_t g = ((int64_t)v.vbase[ns] + y.lord) - i_last - 1;
+            if (g >= (int64_t)w) gap(c - 1, (uint32_t)g, y.posf & POS_MASK);
+        } else {
+            const int64_t g = idx0 + n - 1 - i_last;
+            if (g >= (int64_t)w) gap(c - 1, (uint32_t)g, npos);
+        }
+    }
+
+    // ---- where the left context starts: first candidate within w-1 valid k-mers of the first own candidate
+    uint32_t cs = s, cj = 0;
+    bool left_is_seq_start = false;
+    for (;;) {
+        if (cj == 0) {
+            bool found = false, far = false;
+            uint32_t ss = cs;
+            while (ss > fs) {
+                if (i_first - (int64_t)v.vbase[ss] + 1 >= (int64_t)w) { far = true; break; }
+                ss--;
+                if (v.cnt[ss]) { found = true; break; }
+            }
+            if (far) break;
+            if (!found) { left_is_seq_start = true; break; }
+            const Cand p = v.cands[cand_gid(v, ss, v.cnt[ss] - 1)];
+            if (i_first - ((int64_t)v.vbase[ss] + p.lord) >= (int64_t)w) break;
+            cs = ss; cj = v.cnt[ss] - 1;
+        } else {
+            const Cand p = v.cands[cand_gid(v, cs, cj - 1)];
+            if (i_first - ((int64_t)v.vbase[cs] + p.lord) >= (int64_t)w) break;
+            cj--;
+        }
+    }
+
+    uint64_t* const st_h = S.h;        // value
+    uint32_t* const st_i = S.i;        // valid-k-mer index (fits 32 bits: a device batch is < 2^32 bases)
+    uint32_t* const st_j = S.j;        // own candidate number or NONE32 for context
+    const uint32_t sd = S.stride;
+    uint32_t depth = 0, nsel = 0;
+
+    // decision for own candidate j once both neighbours are known (B_known: a right neighbour <= value was found)
+    auto decide = [&](uint32_t j, int64_t idx, bool has_psv, int64_t psv_idx, bool has_nse, int64_t nse_idx,
+                      bool right_is_seq_end) {
+        const int64_t rel = idx - idx0;
+        const int64_t A = has_psv ? idx - psv_idx - 1 : (left_is_seq_start ? rel : W1);
+        const int64_t B = has_nse ? nse_idx - idx - 1 : (right_is_seq_end ? idx0 + n - 1 - idx : W1);
+        int64_t lo = rel - W1; if (lo < 0) lo = 0; if (rel - A > lo) lo = rel - A;
+        int64_t hi = rel; if (n - (int64_t)w < hi) hi = n - (int64_t)w; if (rel + B - W1 < hi) hi = rel + B - W1;
+        const bool selected = lo <= hi;
+        sel[own_base + j] = selected ? 1 : 0;
+        nsel += selected ? 1u : 0u;
+    };
+
+    // ---- forward walk
+    bool right_is_seq_end = false;
+    for (;;) {
+        const Cand x = v.cands[cand_gid(v, cs, cj)];
+        const int64_t xi = (int64_t)v.vbase[cs] + x.lord;
+        const bool own = (cs == s);
+        if (!own && cs > s && xi - i_last > W1) break;          // beyond every own candidate's reach
+        while (depth && st_h[(depth - 1) * sd] >= x.h0) {
+            depth--;
+            if (st_j[depth * sd] != NONE32)
+                decide(st_j[depth * sd], (int64_t)st_i[depth * sd], depth > 0, depth > 0 ? (int64_t)st_i[(depth - 1) * sd] : 0,
+                       true, xi, false);
+        }
+        if (depth == SEL_STACK) return NONE32;
+        st_h[depth * sd] = x.h0; st_i[depth * sd] = (uint32_t)xi; st_j[depth * sd] = own ? cj : NONE32; depth++;
+        // next candidate of the sequence
+        uint32_t ns = cs, nj = cj + 1;
+        bool found = nj < v.cnt[ns];
+        if (!found) {
+            for (;;) {
+                if (ns + 1 >= es) { right_is_seq_end = true; break; }           // no candidate left in the sequence
+                ns++;
+                if (v.cnt[ns]) { nj = 0; found = true; break; }
+                if (cs > s && (int64_t)v.vbase[ns + 1] - i_last > W1) break;    // the rest is out of reach
+            }
+        }
+        if (!found) break;
+        cs = ns; cj = nj;
+    }
+    // whatever is still stacked has no smaller-or-equal neighbour within reach on the right
+    while (depth) {
+        depth--;
+        if (st_j[depth * sd] != NONE32)
+            decide(st_j[depth * sd], (int64_t)st_i[depth * sd], depth > 0, depth > 0 ? (int64_t)st_i[(depth - 1) * sd] : 0,
+                   false, 0, right_is_seq_end);
+    }
+    return nsel;
 }
 
 // candidate threshold on the high word of h0: about c/w of the hash space (everything when w <= c)

@@ -43,7 +43,7 @@ struct VecEmit {
     void operator()(uint64_t h0, uint32_t pos, bool fwd) { Cand c; c.h0 = h0; c.posf = pos | (fwd ? FWD_BIT : 0u); c.lord = 0; v->push_back(c); }
 };
 
-struct Sketch { std::vector<uint64_t> hash; std::vector<uint32_t> posf; std::vector<uint64_t> off; uint64_t ncand = 0, ngaps = 0, novf = 0; };
+struct Sketch { std::vector<uint64_t> hash; std::vector<uint32_t> posf; std::vector<uint64_t> off; uint64_t ncand = 0, ngaps = 0, novf = 0, nstackovf = 0; };
 
 void emu_sketch_impl(const unsigned char* seq, const uint64_t* off, uint32_t nseq, uint32_t k, uint32_t w, uint32_t S,
                      double cc, uint32_t cap_override, Sketch& out) {
@@ -106,14 +106,34 @@ void emu_sketch_impl(const unsigned char* seq, const uint64_t* off, uint32_t nse
     for (uint32_t q = 0; q < nseq; q++) {
         const uint32_t fs = strip_off[q], es = strip_off[q + 1];
         const uint32_t np = seq_npos(off[q + 1] - off[q], k, w);
-        for (uint32_t s = fs; s < es; s++)
+        for (uint32_t s = fs; s < es; s++) {
+            if (!cnt[s]) continue;
+            // k_select: one monotone-stack pass per strip; cross-checked here against the per-candidate scan
+            struct GapCollect {
+                std::vector<uint32_t> j, len, end;
+                void operator()(uint32_t jj, uint32_t l, uint32_t e) { j.push_back(jj); len.push_back(l); end.push_back(e); }
+            } gc;
+            uint64_t stk_h[SEL_STACK]; uint32_t stk_i[SEL_STACK], stk_j[SEL_STACK];
+            const SelStack stk{stk_h, stk_i, stk_j, 1};
+            const uint32_t nsel = select_strip(V, s, fs, es, w, np, sel.data(), gc, stk);
+            uint32_t nsel_ref = 0, ngap_ref = 0;
             for (uint32_t j = 0; j < cnt[s]; j++) {
                 SelectResult r = select_candidate(V, s, j, fs, es, w, np);
                 const uint64_t gid = cand_gid(V, s, j);
+                if (nsel != NONE32 && sel[gid] != (r.selected ? 1 : 0)) abort();
                 sel[gid] = r.selected;
+                nsel_ref += r.selected;
                 out.ncand++;
-                if (r.gap_len >= w) queue_gap(q, (cands[gid].posf & POS_MASK) + 1, r.gap_end, s, j, r.gap_len);
+                if (r.gap_len >= w) {
+                    if (ngap_ref >= gc.j.size() || gc.j[ngap_ref] != j || gc.len[ngap_ref] != r.gap_len || gc.end[ngap_ref] != r.gap_end) abort();
+                    ngap_ref++;
+                    queue_gap(q, (cands[gid].posf & POS_MASK) + 1, r.gap_end, s, j, r.gap_len);
+                }
             }
+            if (ngap_ref != gc.j.size()) abort();
+            if (nsel != NONE32 && nsel != nsel_ref) abort();
+            if (nsel == NONE32) out.nstackovf++;
+        }
         if (fs == es) continue;
         const uint32_t nvalid = vbase[es] - vbase[fs];
         if (nvalid < w) continue;
@@ -163,7 +183,7 @@ int64_t emu_sketch(const unsigned char* seq, const uint64_t* off, uint32_t nseq,
                    uint64_t* stats) {
     Sketch sk;
     emu_sketch_impl(seq, off, nseq, k, w, S, cc, cap_override, sk);
-    if (stats) { stats[0] = sk.ncand; stats[1] = sk.ngaps; stats[2] = sk.novf; }
+    if (stats) { stats[0] = sk.ncand; stats[1] = sk.ngaps; stats[2] = sk.novf; stats[3] = sk.nstackovf; }
     for (uint32_t q = 0; q <= nseq; q++) mx_off[q] = sk.off[q];
     if (sk.hash.size() > cap) return -1;
     if (!sk.hash.empty()) {

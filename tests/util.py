@@ -161,7 +161,7 @@ def emu_sketch(seq, offsets, k, w, S=256, c=10.0, cap_override=0):
     n = lib.emu_sketch(seq.ctypes.data, offsets.ctypes.data, nseq, k, w, S, c, cap_override, h.ctypes.data,
                        p.ctypes.data, cap, off.ctypes.data, st.ctypes.data)
     assert n >= 0
-    return h[:n], p[:n], off, {"cand": int(st[0]), "gaps": int(st[1]), "ovf": int(st[2])}
+    return h[:n], p[:n], off, {"cand": int(st[0]), "gaps": int(st[1]), "ovf": int(st[2]), "stackovf": int(st[3])}
 
 
 def load_fasta_batch(path):
