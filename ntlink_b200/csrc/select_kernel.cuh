@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
     __shared__ uint32_t sh_i[SEL_CAP];
     __shared__ uint32_t sh_off[SEL_NL + 1];       // compact offset of every staged strip
     __shared__ uint32_t sh_cnt[SEL_NL];
+    __shared__ uint8_t sh_t[SEL_CAP];             // staged strip number of every staged candidate
     __shared__ uint32_t sh_q[SEL_NL], sh_fs[SEL_NL], sh_es[SEL_NL], sh_idx0[SEL_NL], sh_n[SEL_NL], sh_np[SEL_NL];
     __shared__ uint32_t sh_sel[SEL_STRIPS];
     __shared__ uint32_t sh_bad;                   // the staged range cannot be used -> whole block falls back
@@ -66,13 +67,15 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
     __syncthreads();
 
     if (staged) {
-        for (uint32_t e = tid; e < total; e += SEL_THREADS) {
-            uint32_t lo = 0, hi = nl;             // strip t with sh_off[t] <= e < sh_off[t+1]
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_off[mid] <= e) lo = mid; else hi = mid; }
-            const uint32_t s = l0 + lo;
-            const Cand cd = V.cands[(uint64_t)s * V.cap + (e - sh_off[lo])];
-            sh_h[e] = cd.h0;
-            sh_i[e] = V.vbase[s] + cd.lord;
+        // one warp per staged strip: lanes copy the strip's candidates (coalesced 16-byte loads, no searching)
+        for (uint32_t t = tid >> 5; t < nl; t += SEL_THREADS / 32) {
+            const uint32_t s = l0 + t, c = sh_cnt[t], o = sh_off[t], vb = V.vbase[s];
+            for (uint32_t j = tid & 31; j < c; j += 32) {
+                const Cand cd = V.cands[(uint64_t)s * V.cap + j];
+                sh_h[o + j] = cd.h0;
+                sh_i[o + j] = vb + cd.lord;
+                sh_t[o + j] = (uint8_t)t;
+            }
         }
     }
     __syncthreads();
@@ -83,13 +86,14 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
         const uint32_t e_begin = sh_off[b0 - l0], e_end = sh_off[b1 - l0];
         const int64_t first_idx = V.vbase[l0], end_idx = V.vbase[l1];   // valid k-mers covered by the staged strips
         for (uint32_t e = e_begin + tid; e < e_end; e += SEL_THREADS) {
-            uint32_t lo = b0 - l0, hi = b1 - l0;
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh_off[mid] <= e) lo = mid; else hi = mid; }
-            const uint32_t t = lo, s = l0 + t, j = e - sh_off[t];
+            const uint32_t t = sh_t[e], s = l0 + t, j = e - sh_off[t];
             const uint32_t fs = sh_fs[t], es = sh_es[t];
-            const int64_t idx0 = sh_idx0[t], n = sh_n[t];
+            const int32_t w32 = (int32_t)w, W1s = w32 - 1;
+            const uint32_t idx0u = sh_idx0[t];
+            const int64_t idx0 = idx0u, n = sh_n[t];
             const uint64_t val = sh_h[e];
-            const int64_t idx = sh_i[e], rel = idx - idx0;
+            const uint32_t idxu = sh_i[e];
+            const int64_t idx = idxu, rel = idx - idx0;
             const uint32_t e_lo = sh_off[(fs > l0 ? fs : l0) - l0];      // staged candidates of the same sequence
             const uint32_t e_hi = sh_off[(es < l1 ? es : l1) - l0];
             bool need_fallback = false;
@@ -97,8 +101,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
             int64_t A = -1;
             for (uint32_t p = e; p > e_lo;) {
                 p--;
-                const int64_t d = idx - (int64_t)sh_i[p];
-                if (d >= (int64_t)w) { A = W1; break; }
+                const int32_t d = (int32_t)(idxu - sh_i[p]);
+                if (d >= w32) { A = W1s; break; }
                 if (sh_h[p] < val) { A = d - 1; break; }
             }
             if (A < 0) {
@@ -110,12 +114,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
             int64_t B = -1;
             uint32_t gap_len = 0, gap_end = 0;
             bool gap_known = true;
-            if (e + 1 < e_hi) gap_len = (uint32_t)((int64_t)sh_i[e + 1] - idx - 1);
+            if (e + 1 < e_hi) gap_len = sh_i[e + 1] - idxu - 1;
             else if (es <= l1) { gap_len = (uint32_t)(idx0 + n - 1 - idx); gap_end = sh_np[t]; }
             else gap_known = false;
             for (uint32_t p = e + 1; p < e_hi; p++) {
-                const int64_t d = (int64_t)sh_i[p] - idx;
-                if (d >= (int64_t)w) { B = W1; break; }
+                const int32_t d = (int32_t)(sh_i[p] - idxu);
+                if (d >= w32) { B = W1s; break; }
                 if (sh_h[p] <= val) { B = d - 1; break; }
             }
             if (B < 0) {
@@ -133,9 +137,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
                 int64_t hi_w = rel; if (n - (int64_t)w < hi_w) hi_w = n - (int64_t)w; if (rel + B - W1 < hi_w) hi_w = rel + B - W1;
                 selected = lo_w <= hi_w;
                 if (gap_len >= w && e + 1 < e_hi) {                      // position of the neighbour that ends the stretch
-                    uint32_t lo2 = t, hi2 = nl;
-                    while (hi2 - lo2 > 1) { const uint32_t mid = (lo2 + hi2) >> 1; if (sh_off[mid] <= e + 1) lo2 = mid; else hi2 = mid; }
-                    gap_end = V.cands[(uint64_t)(l0 + lo2) * V.cap + (e + 1 - sh_off[lo2])].posf & POS_MASK;
+                    const uint32_t t2 = sh_t[e + 1];
+                    gap_end = V.cands[(uint64_t)(l0 + t2) * V.cap + (e + 1 - sh_off[t2])].posf & POS_MASK;
                 }
             }
             sel[gid] = selected ? 1 : 0;

@@ -319,35 +319,11 @@ __global__ void k_seq_gaps(const uint64_t* __restrict__ seq_off, const uint32_t*
     if (lead >= P.w) queue_gap(gaps, gap_head, st, P, q, 0, c.posf & POS_MASK, fs, NONE32, lead);
 }
 
-struct ExtraEmit {
-    Cand* dst;
-    uint32_t count, cap;
-    __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd) {
-        if (count < cap) { Cand c; c.h0 = h0; c.posf = pos | (fwd ? FWD_BIT : 0u); c.lord = 0; dst[count] = c; }
-        count++;
-    }
-};
-
-__global__ void __launch_bounds__(64) k_gap(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
-                                            SkParams P, const RollEntry* __restrict__ tbl_g, GapRec* __restrict__ gaps,
-                                            Cand* __restrict__ extras, uint32_t* __restrict__ selcnt,
-                                            SketchStatus* __restrict__ st) {
-    __shared__ RollEntry tbl_s[ROLL_TABLE_ENTRIES];
-    for (uint32_t i = threadIdx.x; i < ROLL_TABLE_ENTRIES; i += blockDim.x) tbl_s[i] = tbl_g[i];
-    __syncthreads();
-    const uint32_t ng = min(st->ngaps, P.gaps_cap);
-    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < ng; id += gridDim.x * blockDim.x) {
-        GapRec g = gaps[id];
-        if (g.max_out == 0) continue;
-        const uint64_t gseq = seq_off[g.seq];
-        const uint32_t L = (uint32_t)(seq_off[g.seq + 1] - gseq);
-        ExtraEmit em{extras + g.out_off, 0, g.max_out};
-        gap_scan(packed, tbl_s, gseq, L, P.k, P.w, g.start_pos, g.end_pos, em);
-        const uint32_t n = min(em.count, g.max_out);
-        gaps[id].out_cnt = n;
-        if (n) atomicAdd(&selcnt[g.strip], n);
-    }
-}
+}  // namespace
+}  // namespace ntl
+#include "gap_kernel.cuh"      // k_gap (one warp per candidate-free stretch)
+namespace ntl {
+namespace {
 
 // ------------------------------------------------------------------------------------------- emit
 __global__ void __launch_bounds__(128) k_emit(SkParams P, CandView V, const uint8_t* __restrict__ sel,
@@ -503,9 +479,8 @@ retry:
     tock(c, T_SELECT);
 
     tick(c, T_GAP);
-    k_gap<<<div_up(std::min<uint32_t>(gaps_cap, 1 << 16), 64), 64, 0, c->stream>>>(W.packed.as<uint32_t>(), d_off, P,
-                                                                                 W.tbl.as<RollEntry>(), W.gaps.as<GapRec>(),
-                                                                                 W.extras.as<Cand>(), W.selcnt.as<uint32_t>(), st);
+    k_gap<<<std::min<uint32_t>(div_up(gaps_cap, GAP_WARPS), 148 * 8), GAP_WARPS * 32, 0, c->stream>>>(
+        W.packed.as<uint32_t>(), d_off, P, W.tbl.as<RollEntry>(), W.gaps.as<GapRec>(), W.extras.as<Cand>(), W.selcnt.as<uint32_t>(), st);
     c->launches += 1;
     tock(c, T_GAP);
 

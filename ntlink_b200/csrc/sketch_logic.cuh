@@ -64,7 +64,8 @@ NTL_HD uint32_t fetch1(const uint32_t* __restrict__ packed, uint64_t g) {
 // The hash state starts from zero and is rolled over k-1 lead-in bases with a virtual "zero" base leaving
 // (code 4), which yields exactly the ntHash initial value (see nthash.cuh).
 // ---------------------------------------------------------------------------------------------------
-template <class Emit>
+// With ALL = true every valid k-mer is emitted regardless of the threshold (used by the gap re-scan).
+template <bool ALL = false, class Emit>
 NTL_HD uint32_t process_strip(const uint32_t* __restrict__ packed, uint64_t gseq, uint32_t p0, uint32_t n,
                               uint32_t k, const RollEntry* tbl, uint32_t tstride, uint32_t tau_hi, Emit& emit) {
     const uint64_t g0 = gseq + p0;              // first base consumed
@@ -93,7 +94,7 @@ NTL_HD uint32_t process_strip(const uint32_t* __restrict__ packed, uint64_t gseq
                 fh = srol1(fh) ^ re.f;
                 rh = sror1(rh ^ re.r);
                 const uint64_t h0 = fh + rh;
-                if ((uint32_t)(h0 >> 32) < tau_hi) {
+                if (ALL || (uint32_t)(h0 >> 32) < tau_hi) {
                     const int32_t s = t + j;
                     if (s >= lead && s < T)
                         emit(h0, p0 + (uint32_t)(s - lead), fh <= rh, nv + (uint32_t)(s - first_out));
@@ -113,7 +114,7 @@ NTL_HD uint32_t process_strip(const uint32_t* __restrict__ packed, uint64_t gseq
                 if (cin >= CODE_INVALID) last_bad = s;
                 if (s >= lead && s < T && s - last_bad >= (int32_t)k) {
                     const uint64_t h0 = fh + rh;
-                    if ((uint32_t)(h0 >> 32) < tau_hi) emit(h0, p0 + (uint32_t)(s - lead), fh <= rh, nv);
+                    if (ALL || (uint32_t)(h0 >> 32) < tau_hi) emit(h0, p0 + (uint32_t)(s - lead), fh <= rh, nv);
                     nv++;
                 }
             }
