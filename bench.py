@@ -247,6 +247,9 @@ def run_gpu(args, rank, world, local_rank):
 
     contigs, reads = make_inputs(rank, world)
     ctx = Context(local_rank)
+    for opt, env in (("cand_c", "NTL_CAND_C"), ("strip_len", "NTL_STRIP_LEN")):   # tuning sweeps only
+        if os.environ.get(env):
+            ctx.set_option(opt, float(os.environ[env]))
     prm = ctx.params(K, W, Z)
     read_bases = int(reads.offsets[-1])
 

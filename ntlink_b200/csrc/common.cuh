@@ -96,6 +96,10 @@ struct TargetIndex {
     bool built = false;
 };
 
+struct TallyWork {
+    DevBuf keys, pn, panchor, pfirst, ev_slot, gap_off, cursor, gkey, gval, nonempty, ppref, out, ndev, bs;
+};
+
 struct MapWork {
     DevBuf hit_tmp, hit_flag, hit_pref, hits, runs, mark, hit_off, nruns, events, status, read_len, ev_cnt, blocksums;
 };
@@ -109,13 +113,14 @@ struct ntl_ctx {
     std::string err;
     ntl::SketchWork sw;
     ntl::MapWork mw;
+    ntl::TallyWork tw;
     ntl::TargetIndex index;
     ntl::DevBuf d_seq, d_off;              // staging of the current batch (ASCII + offsets)
     ntl::DeviceSketch dsk;                 // sketch of the current batch
     ntl::PinnedBuf h_status;
     // tuning knobs
     uint32_t strip_len = 256;
-    double cand_c = 10.0;
+    double cand_c = 7.0;
     uint64_t batch_bases = 1ull << 30;
     // timing
     cudaEvent_t ev[2 * ntl::T_NUM];

@@ -381,11 +381,13 @@ int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>&
     if (n >= (1ull << 31)) { c->err = "tally: too many events"; return NTL_ERR_WORKSPACE; }
     uint64_t slots = 1024;
     while (slots < 2 * n) slots <<= 1;
-    DevBuf keys, pn, panchor, pfirst, ev_slot, gap_off, cursor, gkey, gval, nonempty, ppref, out, ndev, bs;
+    // persistent work buffers (cudaMalloc/cudaFree per call would dominate a small tally)
+    TallyWork& T = c->tw;
+    DevBuf &keys = T.keys, &pn = T.pn, &panchor = T.panchor, &pfirst = T.pfirst, &ev_slot = T.ev_slot, &gap_off = T.gap_off,
+           &cursor = T.cursor, &gkey = T.gkey, &gval = T.gval, &nonempty = T.nonempty, &ppref = T.ppref, &out = T.out,
+           &ndev = T.ndev, &bs = T.bs;
     int rc = NTL_OK;
-    auto cleanup = [&]() { keys.release(); pn.release(); panchor.release(); pfirst.release(); ev_slot.release(); gap_off.release();
-                           cursor.release(); gkey.release(); gval.release(); nonempty.release(); ppref.release(); out.release();
-                           ndev.release(); bs.release(); };
+    auto cleanup = [&]() {};
 #define TL_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string("tally: ") + cudaGetErrorString(e__); cleanup(); return NTL_ERR_CUDA; } } while (0)
     TL_CUDA(keys.ensure(slots * 8)); TL_CUDA(pn.ensure(slots * 4)); TL_CUDA(panchor.ensure(slots * 4));
     TL_CUDA(pfirst.ensure(slots * 8)); TL_CUDA(ev_slot.ensure(n * 4)); TL_CUDA(gap_off.ensure((slots + 1) * 4));

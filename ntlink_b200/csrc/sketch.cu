@@ -161,6 +161,20 @@ __device__ __forceinline__ void generic_block(H32& h, uint32_t wi, uint32_t wo, 
     }
 }
 
+// five consecutive 32-bit words starting at word r (0..3) of the 8-word window {A, B}
+__device__ __forceinline__ void pick5(const uint4 A, const uint4 B, uint32_t r, uint32_t (&x)[5]) {
+    switch (r) {
+        case 0: x[0] = A.x; x[1] = A.y; x[2] = A.z; x[3] = A.w; x[4] = B.x; break;
+        case 1: x[0] = A.y; x[1] = A.z; x[2] = A.w; x[3] = B.x; x[4] = B.y; break;
+        case 2: x[0] = A.z; x[1] = A.w; x[2] = B.x; x[3] = B.y; x[4] = B.z; break;
+        default: x[0] = A.w; x[1] = B.x; x[2] = B.y; x[3] = B.z; x[4] = B.w; break;
+    }
+}
+
+// The packed sequence is read with 128-bit loads, one per 32 bases and stream (entering / leaving bases): lanes of a
+// warp work on strips that are 128 bytes apart, so every load instruction costs 32 L1 wavefronts whatever its
+// width -- 16-byte loads cut the wavefront count (the limiter of this kernel before) by 4x compared to words.
+// `packed` must be preceded by one readable 16-byte chunk (the leaving stream starts k bases before the strip).
 template <class Emit>
 __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict__ packed, uint64_t gseq, uint32_t p0, uint32_t n,
                                                       uint32_t k, const unsigned char* tbl_s, uint32_t lanebase,
@@ -171,45 +185,69 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
     H32 h = {0, 0, 0, 0};
     int32_t last_bad = -(1 << 30);
     uint32_t nv = 0;
-    // sequential word streams: cur/next aligned words of the entering bases, funnel-shifted to the strip's phase
-    const uint32_t* pin = packed + (g0 >> 3);
-    const uint32_t sh_in = (uint32_t)(g0 & 7) * 4;
-    uint32_t in_lo = pin[0];
-    for (int32_t t = 0; t < T; t += 8) {
-        const uint32_t in_hi = pin[(t >> 3) + 1];
-        const uint32_t wi = __funnelshift_r(in_lo, in_hi, sh_in);
-        in_lo = in_hi;
-        uint32_t wo;
-        const int32_t o = t - (int32_t)k;
-        if (o >= 0) wo = fetch8(packed, g0 + (uint32_t)o);
-        else if (o <= -8) wo = 0x44444444u;
-        else {
-            const uint32_t sh = 4u * (uint32_t)(-o);
-            wo = (fetch8(packed, g0) << sh) | (0x44444444u & ((1u << sh) - 1u));
+    const uint4* __restrict__ chunks = reinterpret_cast<const uint4*>(packed);
+    // entering bases: base index g0 + t
+    const int64_t ci_in = (int64_t)(g0 >> 5);
+    const uint32_t r_in = (uint32_t)(g0 >> 3) & 3u, sh_in = (uint32_t)(g0 & 7) * 4;
+    // leaving bases: base index g0 + t - k (virtual "zero" bases while t < k)
+    const int64_t go = (int64_t)g0 - (int64_t)k;
+    const int64_t ci_out = go >> 5;                                   // arithmetic shift: floor
+    const uint32_t r_out = (uint32_t)(go >> 3) & 3u, sh_out = (uint32_t)(go & 7) * 4;
+    uint4 Ain = chunks[ci_in];
+    uint4 Aout = make_uint4(0, 0, 0, 0);
+    bool out_live = false;
+    for (int32_t t0 = 0; t0 < T; t0 += 32) {
+        const int32_t sb = t0 >> 5;
+        uint32_t xi[5], xo[5];
+        const uint4 Bin = chunks[ci_in + sb + 1];
+        pick5(Ain, Bin, r_in, xi);
+        Ain = Bin;
+        const bool need_out = t0 + 32 > (int32_t)k;                   // some real leaving base in this super-block
+        if (need_out) {
+            if (!out_live) { Aout = chunks[ci_out + sb]; out_live = true; }
+            const uint4 Bout = chunks[ci_out + sb + 1];
+            pick5(Aout, Bout, r_out, xo);
+            Aout = Bout;
         }
-        const bool clean = ((wi & 0x44444444u) == 0u);
-        if (clean && t + 8 <= lead) {
-            // lead-in: no k-mer completes in this block -> roll only
-            const uint32_t ce = (wi & 0x0F0F0F0Fu) * 8u + (wo & 0x0F0F0F0Fu);
-            const uint32_t co = ((wi >> 4) & 0x0F0F0F0Fu) * 8u + ((wo >> 4) & 0x0F0F0F0Fu);
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
-        } else if (clean && t >= lead && t + 8 <= T && t - last_bad >= (int32_t)k) {
-            // interior: 8 valid, in-range k-mers
-            const uint32_t ce = (wi & 0x0F0F0F0Fu) * 8u + (wo & 0x0F0F0F0Fu);
-            const uint32_t co = ((wi >> 4) & 0x0F0F0F0Fu) * 8u + ((wo >> 4) & 0x0F0F0F0Fu);
-            const uint32_t pos0 = p0 + (uint32_t)(t - lead);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
-                const uint64_t fh = ((uint64_t)h.fhi << 32) | h.flo, rh = ((uint64_t)h.rhi << 32) | h.rlo;
-                const uint64_t h0 = fh + rh;
-                if ((uint32_t)(h0 >> 32) < tau_hi) emit(h0, pos0 + j, fh <= rh, nv + j);
+        for (int b = 0; b < 4; b++) {
+            const int32_t t = t0 + 8 * b;
+            if (t >= T) break;
+            const uint32_t wi = __funnelshift_r(xi[b], xi[b + 1], sh_in);
+            uint32_t wo;
+            const int32_t o = t - (int32_t)k;
+            if (o <= -8) wo = 0x44444444u;
+            else {
+                wo = __funnelshift_r(xo[b], xo[b + 1], sh_out);
+                if (o < 0) {                                          // the first -o steps still push out virtual bases
+                    const uint32_t m = (1u << (4u * (uint32_t)(-o))) - 1u;
+                    wo = (wo & ~m) | (0x44444444u & m);
+                }
             }
-            nv += 8;
-        } else {
-            generic_block(h, wi, wo, t, lead, T, (int32_t)k, last_bad, nv, p0, tau_hi, tbl_s, lanebase, emit);
+            const bool clean = ((wi & 0x44444444u) == 0u);
+            if (clean && t + 8 <= lead) {
+                // lead-in: no k-mer completes in this block -> roll only
+                const uint32_t ce = (wi & 0x0F0F0F0Fu) * 8u + (wo & 0x0F0F0F0Fu);
+                const uint32_t co = ((wi >> 4) & 0x0F0F0F0Fu) * 8u + ((wo >> 4) & 0x0F0F0F0Fu);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
+            } else if (clean && t >= lead && t + 8 <= T && t - last_bad >= (int32_t)k) {
+                // interior: 8 valid, in-range k-mers
+                const uint32_t ce = (wi & 0x0F0F0F0Fu) * 8u + (wo & 0x0F0F0F0Fu);
+                const uint32_t co = ((wi >> 4) & 0x0F0F0F0Fu) * 8u + ((wo >> 4) & 0x0F0F0F0Fu);
+                const uint32_t pos0 = p0 + (uint32_t)(t - lead);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
+                    const uint64_t fh = ((uint64_t)h.fhi << 32) | h.flo, rh = ((uint64_t)h.rhi << 32) | h.rlo;
+                    const uint64_t h0 = fh + rh;
+                    if ((uint32_t)(h0 >> 32) < tau_hi) emit(h0, pos0 + j, fh <= rh, nv + j);
+                }
+                nv += 8;
+            } else {
+                generic_block(h, wi, wo, t, lead, T, (int32_t)k, last_bad, nv, p0, tau_hi, tbl_s, lanebase, emit);
+            }
         }
     }
     return nv;
@@ -413,7 +451,7 @@ retry:
     P.pool_base = (uint64_t)nstrips_max * cap;
     P.pool_cap = pool_cap; P.gaps_cap = gaps_cap; P.extras_cap = extras_cap; P.out_cap = 0;
 
-    NTL_CUDA(c, W.packed.ensure(total_bases / 2 + 128));
+    NTL_CUDA(c, W.packed.ensure(total_bases / 2 + 512));
     NTL_CUDA(c, W.scnt.ensure(((size_t)nseq + 2) * 4));
     NTL_CUDA(c, W.strip_off.ensure(((size_t)nseq + 2) * 4));
     NTL_CUDA(c, W.slots.ensure(((size_t)P.pool_base + pool_cap) * sizeof(Cand)));
@@ -443,10 +481,13 @@ retry:
     }
     NTL_CUDA(c, cudaMemsetAsync(st, 0, sizeof(SketchStatus) + 64, c->stream));
     NTL_CUDA(c, cudaMemsetAsync(W.has_cand.p, 0, (size_t)nseq + 1, c->stream));
-    NTL_CUDA(c, cudaMemsetAsync(W.packed.as<char>() + total_bases / 2, 0x44, 128, c->stream));
+    // layout: [64 B front pad | packed bases | >= 192 B tail pad]; d_packed points at the first real chunk
+    uint32_t* const d_packed = reinterpret_cast<uint32_t*>(W.packed.as<char>() + 64);
+    NTL_CUDA(c, cudaMemsetAsync(W.packed.p, 0x44, 64, c->stream));
+    NTL_CUDA(c, cudaMemsetAsync(W.packed.as<char>() + 64 + total_bases / 2, 0x44, 192, c->stream));
 
     tick(c, T_PACK);
-    k_pack<<<div_up(div_up(total_bases, 16), 256), 256, 0, c->stream>>>(d_seq, total_bases, W.packed.as<uint32_t>());
+    k_pack<<<div_up(div_up(total_bases, 16), 256), 256, 0, c->stream>>>(d_seq, total_bases, d_packed);
     k_strip_count<<<div_up(nseq, 256), 256, 0, c->stream>>>(d_off, nseq, k, w, S, W.scnt.as<uint32_t>(), nseq_dev);
     c->launches += 2;
     NTL_TRY(exclusive_scan_u32(c, W.scnt.as<uint32_t>(), W.strip_off.as<uint32_t>(), nseq_dev, nseq, W.blocksums));
@@ -455,14 +496,14 @@ retry:
     tock(c, T_PACK);
 
     tick(c, T_DENSE);
-    k_dense<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(W.packed.as<uint32_t>(), d_off, W.strip_off.as<uint32_t>(), P,
+    k_dense<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), P,
                                                             W.tbl.as<RollEntry>(), W.slots.as<Cand>(), W.cnt.as<uint32_t>(),
                                                             W.nv.as<uint32_t>(), W.has_cand.as<uint8_t>(), st);
     tock(c, T_DENSE);
     c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases;
 
     tick(c, T_SELECT);
-    k_overflow<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(W.packed.as<uint32_t>(), d_off, W.strip_off.as<uint32_t>(), P,
+    k_overflow<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), P,
                                                                W.tbl.as<RollEntry>(), W.slots.as<Cand>(), W.cnt.as<uint32_t>(),
                                                                W.ovf_off.as<uint32_t>(), st);
     c->launches += 1;
@@ -480,7 +521,7 @@ retry:
 
     tick(c, T_GAP);
     k_gap<<<std::min<uint32_t>(div_up(gaps_cap, GAP_WARPS), 148 * 8), GAP_WARPS * 32, 0, c->stream>>>(
-        W.packed.as<uint32_t>(), d_off, P, W.tbl.as<RollEntry>(), W.gaps.as<GapRec>(), W.extras.as<Cand>(), W.selcnt.as<uint32_t>(), st);
+        d_packed, d_off, P, W.tbl.as<RollEntry>(), W.gaps.as<GapRec>(), W.extras.as<Cand>(), W.selcnt.as<uint32_t>(), st);
     c->launches += 1;
     tock(c, T_GAP);
 
