@@ -247,7 +247,8 @@ def run_gpu(args, rank, world, local_rank):
 
     contigs, reads = make_inputs(rank, world)
     ctx = Context(local_rank)
-    for opt, env in (("cand_c", "NTL_CAND_C"), ("strip_len", "NTL_STRIP_LEN")):   # tuning sweeps only
+    for opt, env in (("cand_c", "NTL_CAND_C"), ("strip_len", "NTL_STRIP_LEN"),
+                     ("pipeline_min_bases", "NTL_PIPE_MIN")):                      # tuning sweeps only
         if os.environ.get(env):
             ctx.set_option(opt, float(os.environ[env]))
     prm = ctx.params(K, W, Z)

@@ -2,6 +2,8 @@
 // Host orchestration only: batching, H2D/D2H staging through pinned memory, error translation. All compute is
 // in sketch.cu / map.cu. There is deliberately no CPU fallback: without a CUDA device ntl_init fails.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -42,6 +44,11 @@ struct Results {
     std::vector<uint32_t> t_len, t_rank;
     DevBuf stage_off, ctg_ids, read_len, in_hash, in_posf, in_ctg;
     PinnedBuf h_off;
+    // pipelined read path: copy stream + double-buffered staging
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+    DevBuf st_seq[2], st_off[2];
+    PinnedBuf st_hoff[2];
 };
 }  // namespace ntl
 
@@ -86,6 +93,25 @@ static int stage_batch(ntl_ctx* c, const char* seq, const uint64_t* offsets, uin
     return NTL_OK;
 }
 
+// asynchronous variant for the pipelined read path: copies on the copy stream into staging slot `slot`
+static int stage_batch_async(ntl_ctx* c, int slot, const char* seq, const uint64_t* offsets, uint32_t b, uint32_t e,
+                             uint64_t* nbases_out) {
+    Results* R = res_of(c);
+    const uint64_t base = offsets[b], nb = offsets[e] - base;
+    const uint32_t ns = e - b;
+    if (nb >= (1ull << 32) - 4096) { c->err = "a single sequence/batch exceeds 4 Gbp"; return NTL_ERR_ARG; }
+    NTL_CUDA(c, R->st_seq[slot].ensure(nb + 256));
+    NTL_CUDA(c, R->st_off[slot].ensure(((size_t)ns + 1) * 8));
+    NTL_CUDA(c, R->st_hoff[slot].ensure(((size_t)ns + 1) * 8));
+    uint64_t* ho = R->st_hoff[slot].as<uint64_t>();
+    for (uint32_t i = 0; i <= ns; i++) ho[i] = offsets[b + i] - base;
+    if (nb) NTL_CUDA(c, cudaMemcpyAsync(R->st_seq[slot].p, seq + base, nb, cudaMemcpyHostToDevice, R->copy_stream));
+    NTL_CUDA(c, cudaMemcpyAsync(R->st_off[slot].p, ho, ((size_t)ns + 1) * 8, cudaMemcpyHostToDevice, R->copy_stream));
+    NTL_CUDA(c, cudaEventRecord(R->h2d_done[slot], R->copy_stream));
+    *nbases_out = nb;
+    return NTL_OK;
+}
+
 extern "C" {
 
 int ntl_version(void) { return 100; }
@@ -102,6 +128,9 @@ int ntl_init(int device, ntl_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete res_of(c); delete c; return NTL_ERR_CUDA; }
     for (int i = 0; i < 2 * T_NUM; i++) cudaEventCreate(&c->ev[i]);
     cudaEventCreate(&c->mark[0]); cudaEventCreate(&c->mark[1]);
+    cudaStreamCreateWithFlags(&res_of(c)->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&res_of(c)->h2d_done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&res_of(c)->h2d_done[1], cudaEventDisableTiming);
     for (int i = 0; i < T_NUM; i++) { c->ev_used[i] = false; c->ms_accum[i] = 0; }
     *out = c;
     return NTL_OK;
@@ -133,6 +162,9 @@ void ntl_destroy(ntl_ctx* c) {
                      &R->ev_cnt, &R->events};
     for (HostVec* v : hv) v->b.release();
     R->h_off.release();
+    for (int i = 0; i < 2; i++) { R->st_seq[i].release(); R->st_off[i].release(); R->st_hoff[i].release(); cudaEventDestroy(R->h2d_done[i]); }
+    cudaStreamSynchronize(R->copy_stream);
+    cudaStreamDestroy(R->copy_stream);
     c->h_status.release();
     for (int i = 0; i < 2 * T_NUM; i++) cudaEventDestroy(c->ev[i]);
     cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]);
@@ -152,6 +184,9 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
     } else if (!strcmp(name, "cand_c")) {
         if (!(value > 0)) { c->err = "cand_c must be positive"; return NTL_ERR_ARG; }
         c->cand_c = value;
+    } else if (!strcmp(name, "pipeline_min_bases")) {
+        if (value < 1024 || value > 3.9e9) { c->err = "pipeline_min_bases out of range"; return NTL_ERR_ARG; }
+        c->pipeline_min_bases = (uint64_t)value;
     } else if (!strcmp(name, "batch_bases")) {
         if (value < 1024 || value > 3.9e9) { c->err = "batch_bases out of range"; return NTL_ERR_ARG; }
         c->batch_bases = (uint64_t)value;
@@ -362,21 +397,42 @@ int ntl_map_reads(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t
     Results* R = res_of(c);
     cudaSetDevice(c->device);
     NTL_TRY(begin_map_results(c, nreads));
+    // Pipelined: the host->device copy of batch i+1 (copy stream, double-buffered staging) overlaps the kernels of
+    // batch i (compute stream). Batches of about a quarter of the call so that the overlap pays off.
     std::vector<uint32_t> bounds;
-    plan_batches(offsets, nreads, c->batch_bases, bounds);
+    const uint64_t total_bases = offsets[nreads] - offsets[0];
+    // balanced batches of about pipeline_min_bases each (measured: with less than ~75 Mbp per batch the fixed
+    // per-batch cost outweighs the copy/compute overlap)
+    const uint64_t nb_target = std::max<uint64_t>(1, (total_bases + c->pipeline_min_bases / 2) / c->pipeline_min_bases);
+    uint64_t per_batch = (total_bases + nb_target - 1) / nb_target + (1u << 20);
+    if (per_batch > c->batch_bases) per_batch = c->batch_bases;
+    plan_batches(offsets, nreads, per_batch, bounds);
+    const size_t nbat = bounds.size() - 1;
     uint64_t hits_total = 0, ev_total = 0, mx_total = 0, runs_total = 0;
-    for (size_t bi = 0; bi + 1 < bounds.size(); bi++) {
+    uint64_t nb_slot[2] = {0, 0};
+    if (nbat) NTL_TRY(stage_batch_async(c, 0, seq, offsets, bounds[0], bounds[1], &nb_slot[0]));
+    const bool trace = getenv("NTL_TRACE") != nullptr;
+    auto now_us = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now_us();
+    auto lap = [&](const char* what, size_t bi) { if (trace) { double t = now_us(); fprintf(stderr, "[ntl] batch %zu %-8s %8.1f us\n", bi, what, t - t_prev); t_prev = t; } };
+    for (size_t bi = 0; bi < nbat; bi++) {
         const uint32_t b = bounds[bi], e = bounds[bi + 1];
-        uint64_t nb = 0;
+        const int slot = (int)(bi & 1);
+        if (bi + 1 < nbat) NTL_TRY(stage_batch_async(c, slot ^ 1, seq, offsets, bounds[bi + 1], bounds[bi + 2], &nb_slot[slot ^ 1]));
+        lap("stage", bi);
+        NTL_CUDA(c, cudaStreamWaitEvent(c->stream, R->h2d_done[slot], 0));
         tick(c, T_TOTAL);
-        NTL_TRY(stage_batch(c, seq, offsets, b, e, &nb));
-        NTL_TRY(sketch_device(c, c->d_seq.as<uint8_t>(), c->d_off.as<uint64_t>(), e - b, nb, (uint32_t)prm->k, (uint32_t)prm->w, c->dsk));
-        NTL_TRY(read_len_device(c, c->d_off.as<uint64_t>(), e - b, R->read_len));
+        NTL_TRY(sketch_device(c, R->st_seq[slot].as<uint8_t>(), R->st_off[slot].as<uint64_t>(), e - b, nb_slot[slot], (uint32_t)prm->k,
+                              (uint32_t)prm->w, c->dsk));
+        lap("sketch", bi);
+        NTL_TRY(read_len_device(c, R->st_off[slot].as<uint64_t>(), e - b, R->read_len));
         MapStatus cs; uint64_t log_base = 0;
         NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), e - b, first_read_ordinal + b, prm, &cs, &log_base));
         tock(c, T_TOTAL);
+        lap("map", bi);
         NTL_TRY(append_map_results(c, b, e - b, cs, log_base, hits_total, ev_total));
         collect_timing(c);
+        lap("results", bi);
         mx_total += c->dsk.n_mx; runs_total += cs.n_runs;
     }
     fill_map_out(c, out, nreads, mx_total, hits_total, runs_total, ev_total);

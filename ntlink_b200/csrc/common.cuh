@@ -122,6 +122,7 @@ struct ntl_ctx {
     uint32_t strip_len = 256;
     double cand_c = 7.0;
     uint64_t batch_bases = 1ull << 30;
+    uint64_t pipeline_min_bases = 80ull << 20;   // smallest batch worth pipelining (copy/compute overlap)
     // timing
     cudaEvent_t ev[2 * ntl::T_NUM];
     cudaEvent_t mark[2];

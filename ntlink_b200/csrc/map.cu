@@ -221,6 +221,15 @@ __global__ void k_pairs_compact(const unsigned long long* __restrict__ keys, con
 
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
 
+// counters -> pinned (UVA-mapped) host memory without using a copy engine
+__global__ void k_publish_map(const MapStatus* __restrict__ st, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                              uint32_t* __restrict__ host) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(st);
+    if (threadIdx.x < sizeof(MapStatus) / 4) host[threadIdx.x] = src[threadIdx.x];
+    if (threadIdx.x == 0) { host[16] = *a; host[17] = *b; }
+    __threadfence_system();
+}
+
 }  // namespace
 
 // grow a device buffer keeping its first `keep` bytes
@@ -345,9 +354,8 @@ retry_events:
     }
     NTL_TRY(exclusive_scan_u32(c, ev_cnt, ev_pref, nreads_dev, nreads, M.blocksums));
     // counters -> host (one synchronisation), then append the events to the device log
-    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.p, st, sizeof(MapStatus), cudaMemcpyDeviceToHost, c->stream));
-    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.as<char>() + 64, ev_pref + nreads, 4, cudaMemcpyDeviceToHost, c->stream));
-    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.as<char>() + 68, ev_off + nreads, 4, cudaMemcpyDeviceToHost, c->stream));
+    k_publish_map<<<1, 32, 0, c->stream>>>(st, ev_pref + nreads, ev_off + nreads, c->h_status.as<uint32_t>());
+    c->launches++;
     NTL_CUDA(c, cudaStreamSynchronize(c->stream));
     MapStatus hs = *c->h_status.as<MapStatus>();
     const uint32_t n_events = nreads ? *(uint32_t*)(c->h_status.as<char>() + 64) : 0;

@@ -410,6 +410,15 @@ __global__ void k_seq_offsets(const uint32_t* __restrict__ strip_off, const uint
     if (q <= nseq) mx_off[q] = selbase[strip_off[q]];
 }
 
+// status block + number of strips + number of minimizers -> host-mapped memory
+__global__ void k_publish_sketch(const SketchStatus* __restrict__ st, const uint32_t* __restrict__ nstrips_p,
+                                 const uint32_t* __restrict__ selbase, uint32_t* __restrict__ host) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(st);
+    if (threadIdx.x < sizeof(SketchStatus) / 4) host[threadIdx.x] = src[threadIdx.x];
+    if (threadIdx.x == 0) { const uint32_t ns = *nstrips_p; host[16] = ns; host[17] = selbase[ns]; }
+    __threadfence_system();
+}
+
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -528,8 +537,10 @@ retry:
     tick(c, T_EMIT);
     NTL_TRY(exclusive_scan_u32(c, W.selcnt.as<uint32_t>(), W.selbase.as<uint32_t>(), &st->nstrips, nstrips_max, W.blocksums));
     // total = selbase[nstrips]; fetch the counters to size the output
-    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.p, st, sizeof(SketchStatus), cudaMemcpyDeviceToHost, c->stream));
-    NTL_CUDA(c, cudaMemcpyAsync(c->h_status.as<char>() + 64, W.strip_off.as<uint32_t>() + nseq, 4, cudaMemcpyDeviceToHost, c->stream));
+    // the counters reach the host through a tiny kernel that writes pinned (UVA-mapped) host memory: no copy engine
+    // is involved, so this never queues behind a large host->device copy of the next batch
+    k_publish_sketch<<<1, 32, 0, c->stream>>>(st, W.strip_off.as<uint32_t>() + nseq, W.selbase.as<uint32_t>(), c->h_status.as<uint32_t>());
+    c->launches += 1;
     NTL_CUDA(c, cudaStreamSynchronize(c->stream));
     {
         SketchStatus hs = *c->h_status.as<SketchStatus>();
@@ -541,8 +552,8 @@ retry:
             if (hs.err & SKERR_EXTRAS) extras_cap = (uint32_t)std::min<uint64_t>(0xFFFF0000ull, std::max<uint64_t>((uint64_t)hs.extras_used + 1024, (uint64_t)extras_cap * 4));
             goto retry;
         }
-        uint32_t total = 0;
-        NTL_CUDA(c, cudaMemcpy(&total, W.selbase.as<uint32_t>() + nstrips, 4, cudaMemcpyDeviceToHost));
+        (void)nstrips;
+        const uint32_t total = *(uint32_t*)(c->h_status.as<char>() + 68);
         out_cap = total;
         out.n_mx = total;
     }
