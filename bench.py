@@ -172,63 +172,45 @@ def build_index_distributed(ctx, contigs, rank, world, dist, torch):
     """target sketch split over the ranks by contig, all-gathered over NCCL, index built on every GPU"""
     import ctypes as C
     from ntlink_b200 import SeqBatch, name_ranks
+    from ntlink_b200 import dist as nd
     n = len(contigs)
     cum = contigs.offsets.astype(np.int64)
-    bounds = [int(np.searchsorted(cum, cum[-1] * r // world)) for r in range(world)] + [n]
-    bounds[0] = 0
-    a, b = bounds[rank], bounds[rank + 1]
+    a, b = nd.contig_shard(contigs.offsets, rank, world)
     part = SeqBatch(contigs.seq[int(cum[a]):int(cum[b])], contigs.offsets[a:b + 1] - contigs.offsets[a], contigs.names[a:b])
-    sk = ctx.sketch(part, K, W)            # leaves the triples on the device as well; host copy used for contig ids
+    sk = ctx.sketch(part, K, W)            # the triples also stay on the device; the host copy gives the contig ids
     m = len(sk.hash)
     dev = torch.device("cuda", torch.cuda.current_device())
-    cnt = torch.tensor([m], device=dev, dtype=torch.int64)
-    cnts = [torch.zeros(1, device=dev, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(cnts, cnt)
-    cnts = [int(c.item()) for c in cnts]
-    mmax = max(max(cnts), 1)
-    ctg = (np.repeat(np.arange(a, b, dtype=np.uint32), np.diff(sk.seq_off).astype(np.int64)))
-    send = torch.zeros(mmax * 2, device=dev, dtype=torch.int64)       # [hash | (ctg << 32 | pos_strand)]
+    h = torch.empty(m, device=dev, dtype=torch.int64)
     nmx, dh, dp, do = C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_void_p()
     ctx._check(ctx.lib.ntl_device_sketch_arrays(ctx.h, C.byref(nmx), C.byref(dh), C.byref(dp), C.byref(do)), "arrays")
     if m:
-        ctx._check(ctx.lib.ntl_copy_device(ctx.h, send.data_ptr(), dh, m * 8), "copy")
-        meta = torch.from_numpy((ctg.astype(np.int64) << 32) | sk.pos_strand.astype(np.int64)).to(dev)
-        send[mmax:mmax + m] = meta
-    recv = [torch.zeros(mmax * 2, device=dev, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(recv, send)
-    hashes = torch.cat([recv[r][:cnts[r]] for r in range(world)])
-    metas = torch.cat([recv[r][mmax:mmax + cnts[r]] for r in range(world)])
-    ctgs = (metas >> 32).to(torch.int32).contiguous()
-    posf = (metas & 0xFFFFFFFF).to(torch.int32).contiguous()
+        ctx._check(ctx.lib.ntl_copy_device(ctx.h, h.data_ptr(), dh, m * 8), "copy")
+    ctg = torch.from_numpy(np.repeat(np.arange(a, b, dtype=np.int32), np.diff(sk.seq_off).astype(np.int64))).to(dev)
+    posf = torch.from_numpy(sk.pos_strand.view(np.int32)).to(dev)
+    hashes, ctgs, posfs = nd.gather_triples(h, ctg, posf, dist)
     torch.cuda.synchronize()
     cl = contigs.lengths.astype(np.uint32)
     rk = name_ranks(contigs.names)
-    ctx._check(ctx.lib.ntl_index_build_device(ctx.h, hashes.data_ptr(), ctgs.data_ptr(), posf.data_ptr(), int(hashes.numel()),
+    ctx._check(ctx.lib.ntl_index_build_device(ctx.h, hashes.data_ptr(), ctgs.data_ptr(), posfs.data_ptr(), int(hashes.numel()),
                                               cl.ctypes.data, rk.ctypes.data, n), "ntl_index_build_device")
 
 
 def gather_events(ctx, rank, world, dist, torch):
-    "pair events of every rank -> rank 0's device event log (NCCL all_gather of padded buffers)"
+    "pair events of every rank -> rank 0's device event log, in rank order = global read order"
     import ctypes as C
+    from ntlink_b200 import dist as nd
     n, dptr = C.c_uint64(), C.c_void_p()
     ctx._check(ctx.lib.ntl_events_device(ctx.h, C.byref(n), C.byref(dptr)), "events_device")
     dev = torch.device("cuda", torch.cuda.current_device())
-    cnt = torch.tensor([n.value], device=dev, dtype=torch.int64)
-    cnts = [torch.zeros(1, device=dev, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(cnts, cnt)
-    cnts = [int(c.item()) for c in cnts]
-    mmax = max(max(cnts), 1)
-    send = torch.zeros(mmax * 6, device=dev, dtype=torch.int32)
+    mine = torch.empty((n.value, 6), device=dev, dtype=torch.int32)
     if n.value:
-        ctx._check(ctx.lib.ntl_copy_device(ctx.h, send.data_ptr(), dptr, n.value * 24), "copy")
-    recv = [torch.zeros(mmax * 6, device=dev, dtype=torch.int32) for _ in range(world)]
-    dist.all_gather(recv, send)
+        ctx._check(ctx.lib.ntl_copy_device(ctx.h, mine.data_ptr(), dptr, n.value * 24), "copy")
+    allev = nd.gather_events(mine, dist)
     torch.cuda.synchronize()
     if rank == 0:
         ctx.events_reset()
-        for r in range(world):
-            if cnts[r]:
-                ctx._check(ctx.lib.ntl_events_append_device(ctx.h, recv[r].data_ptr(), cnts[r]), "append")
+        if allev.shape[0]:
+            ctx._check(ctx.lib.ntl_events_append_device(ctx.h, allev.data_ptr(), int(allev.shape[0])), "append")
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -265,7 +247,7 @@ def run_gpu(args, rank, world, local_rank):
             ctx.index_build_resident(K, W)
         else:
             build_index_distributed(ctx, contigs, rank, world, dist, torch)
-        st = ctx.map_resident(prm, first_ordinal=0)
+        st = ctx.map_resident(prm, first_ordinal=rank * len(reads))
         if world > 1:
             gather_events(ctx, rank, world, dist, torch)
         if rank == 0:
@@ -303,7 +285,7 @@ def run_gpu(args, rank, world, local_rank):
         import ctypes as C
         from ntlink_b200 import _lib
         mo = _lib.MapOut()
-        ctx._check(ctx.lib.ntl_map_reads(ctx.h, pr.seq.ctypes.data, pr.offsets.ctypes.data, len(pr), 0, C.byref(prm), C.byref(mo)),
+        ctx._check(ctx.lib.ntl_map_reads(ctx.h, pr.seq.ctypes.data, pr.offsets.ctypes.data, len(pr), rank * len(pr), C.byref(prm), C.byref(mo)),
                    "ntl_map_reads")
         d2h["bytes"] = int(mo.n_hits) * 24 + int(mo.n_events) * 24 + (len(pr) + 1) * 16
         if world > 1:

@@ -38,8 +38,10 @@ def fixture_file(tmpdir, name):
     "Materialise tests/golden/inputs/<name>.gz as tmpdir/<name>; returns the path"
     dst = os.path.join(str(tmpdir), name)
     if not os.path.exists(dst):
-        with open(dst, "wb") as fout:
+        tmp = f"{dst}.{os.getpid()}.tmp"          # atomic: several test processes may share tmpdir
+        with open(tmp, "wb") as fout:
             fout.write(gunzip_bytes(os.path.join(GOLD, "inputs", name + ".gz")))
+        os.replace(tmp, dst)
     return dst
 
 
