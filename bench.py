@@ -195,22 +195,29 @@ def build_index_distributed(ctx, contigs, rank, world, dist, torch):
                                               cl.ctypes.data, rk.ctypes.data, n), "ntl_index_build_device")
 
 
+_event_gather = None
+
+
 def gather_events(ctx, rank, world, dist, torch):
-    "pair events of every rank -> rank 0's device event log, in rank order = global read order"
+    "pair events of every rank -> rank 0's device event log, in rank order = global read order (one NCCL all_gather)"
     import ctypes as C
     from ntlink_b200 import dist as nd
+    global _event_gather
+    if _event_gather is None:
+        _event_gather = nd.EventGather()
     n, dptr = C.c_uint64(), C.c_void_p()
     ctx._check(ctx.lib.ntl_events_device(ctx.h, C.byref(n), C.byref(dptr)), "events_device")
     dev = torch.device("cuda", torch.cuda.current_device())
     mine = torch.empty((n.value, 6), device=dev, dtype=torch.int32)
     if n.value:
         ctx._check(ctx.lib.ntl_copy_device(ctx.h, mine.data_ptr(), dptr, n.value * 24), "copy")
-    allev = nd.gather_events(mine, dist)
-    torch.cuda.synchronize()
+    torch.cuda.current_stream().synchronize()
+    parts = _event_gather.gather(mine, dist)
     if rank == 0:
         ctx.events_reset()
-        if allev.shape[0]:
-            ctx._check(ctx.lib.ntl_events_append_device(ctx.h, allev.data_ptr(), int(allev.shape[0])), "append")
+        for p in parts:
+            if p.shape[0]:
+                ctx._check(ctx.lib.ntl_events_append_device(ctx.h, p.contiguous().data_ptr(), int(p.shape[0])), "append")
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -228,6 +235,9 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     contigs, reads = make_inputs(rank, world)
+    # replicated target index: small targets are sketched redundantly on every GPU (cheaper than a collective);
+    # large ones are sketched in contig shards and the minimizer triples all-gathered over NCCL
+    shard_target = args.shard_target == "always" or (args.shard_target == "auto" and int(contigs.offsets[-1]) >= (256 << 20))
     ctx = Context(local_rank)
     for opt, env in (("cand_c", "NTL_CAND_C"), ("strip_len", "NTL_STRIP_LEN"),
                      ("pipeline_min_bases", "NTL_PIPE_MIN")):                      # tuning sweeps only
@@ -243,7 +253,7 @@ def run_gpu(args, rank, world, local_rank):
 
     def step_resident():
         ctx.events_reset()
-        if world == 1:
+        if world == 1 or not shard_target:
             ctx.index_build_resident(K, W)
         else:
             build_index_distributed(ctx, contigs, rank, world, dist, torch)
@@ -278,7 +288,7 @@ def run_gpu(args, rank, world, local_rank):
 
     def step_e2e():
         ctx.events_reset()
-        if world == 1:
+        if world == 1 or not shard_target:
             ctx.build_index_from_sequences(pc, K, W, want_sketch=False)
         else:
             build_index_distributed(ctx, pc, rank, world, dist, torch)
@@ -328,7 +338,10 @@ def run_gpu(args, rank, world, local_rank):
                                        "(4% sub, 3% ins, 3% del), k=32 w=100 z=1000",
                            "read_bases_per_gpu": read_bases, "reads_per_gpu": len(reads), "contigs": len(contigs),
                            "k": K, "w": W, "z": Z, "l2": "inputs larger than L2 (150 MB ASCII reads per step)",
-                           "step": "target sketch + index build + read sketch + lookup + chain + events + tally"},
+                           "step": "target sketch + index build + read sketch + lookup + chain + events + tally",
+                           "multi_gpu": ("reads sharded, index replicated (%s), events gathered with NCCL to rank 0"
+                                         % ("target sketched in contig shards + NCCL all-gather" if shard_target else
+                                            "small target sketched on every GPU")) if world > 1 else "n/a"},
                 "e2e": {"value": e2e, "unit": "Gbp/s",
                         "h2d_bytes_per_step": int(len(pc.seq) + len(pr.seq) + 8 * (len(pc) + len(pr) + 2)),
                         "d2h_bytes_per_step": int(d2h.get("bytes", 0)), "ms_per_step": 1e3 * t_e2e / args.steps},
@@ -362,6 +375,8 @@ def main():
     ap.add_argument("--impl", default="ntlink_b200", choices=["ntlink_b200", "reference"])
     ap.add_argument("--cpu-reads", type=int, default=1500, help="reads in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shard-target", default="auto", choices=["auto", "always", "never"],
+                    help="N>1: sketch the target in contig shards + NCCL all-gather (auto: targets >= 256 Mbp)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

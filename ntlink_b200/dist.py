@@ -57,3 +57,36 @@ def gather_triples(hash_i64, ctg_i32, posf_i32, dist, group=None):
 def gather_events(events_i32, dist, group=None):
     "pair events (n x 6 int32, layout of ntl_event) of all ranks concatenated in rank order = global read order"
     return torch.cat(all_gather_var(events_i32.reshape(-1, 6), dist, group), dim=0)
+
+
+class EventGather:
+    """Gathers the pair events of all ranks with ONE collective and no size round trip: every rank sends a fixed
+    capacity buffer whose first row carries its event count; the capacity grows (and the gather is repeated) only
+    when some rank overflowed it."""
+
+    def __init__(self, capacity=4096):
+        self.cap = capacity
+        self.send = None
+        self.recv = None
+
+    def _ensure(self, device, world):
+        if self.send is None or self.send.shape[0] != self.cap + 1 or self.send.device != device:
+            self.send = torch.zeros((self.cap + 1, 6), device=device, dtype=torch.int32)
+            self.recv = [torch.zeros_like(self.send) for _ in range(world)]
+
+    def gather(self, events_i32, dist, group=None):
+        "events_i32: (n, 6) int32 on the group's device. Returns (list of per-rank event tensors)."
+        world = dist.get_world_size(group)
+        n = int(events_i32.shape[0])
+        while True:
+            self._ensure(events_i32.device, world)
+            self.send[0, 0] = n
+            m = min(n, self.cap)
+            if m:
+                self.send[1:1 + m] = events_i32[:m]
+            dist.all_gather(self.recv, self.send, group=group)
+            counts = torch.stack([r[0, 0] for r in self.recv]).tolist()      # the only synchronisation
+            if max(counts) <= self.cap:
+                return [r[1:1 + c] for r, c in zip(self.recv, counts)]
+            self.cap = int(max(counts) * 2)
+            self.send = None

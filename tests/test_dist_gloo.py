@@ -51,6 +51,9 @@ def _worker(rank, world, port, tmp, case):
     mine = tem.run_emu_events(tmp, case, r0, r1)
     allev = nd.gather_events(torch.from_numpy(mine.view(np.int32).copy()), dist).numpy().view(np.uint32)
     assert np.array_equal(allev, full), "sharded events differ from the single-process events"
+    # the one-collective gather used by bench.py (capacity grows when a rank overflows it)
+    parts = nd.EventGather(capacity=8).gather(torch.from_numpy(mine.view(np.int32).copy()), dist)
+    assert np.array_equal(torch.cat(parts).numpy().view(np.uint32), full)
     dist.barrier()
     dist.destroy_process_group()
 
