@@ -261,7 +261,7 @@ def run_gpu(args, rank, world, local_rank):
         if world > 1:
             gather_events(ctx, rank, world, dist, torch)
         if rank == 0:
-            stats["pairs"] = len(ctx.pairs())
+            stats["pairs"] = len(ctx.pairs_raw()[0])
         stats.update(st)
 
     for _ in range(args.warmup):
@@ -301,7 +301,7 @@ def run_gpu(args, rank, world, local_rank):
         if world > 1:
             gather_events(ctx, rank, world, dist, torch)
         if rank == 0:
-            d2h["pairs"] = len(ctx.pairs())
+            d2h["pairs"] = len(ctx.pairs_raw()[0])
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()

@@ -296,13 +296,17 @@ class Context:
         self._check(self.lib.ntl_events_count(self.h, C.byref(n)), "ntl_events_count")
         return n.value
 
-    def pairs(self):
-        """[(src, tgt, flags, n, anchor, gaps int32[n])] in first-seen order (the reference's dict order)."""
+    def pairs_raw(self):
+        "the pair table as arrays: (n_pairs x 10 uint32 view of ntl_pair, gaps int32[]) in first-seen order"
         po = _lib.PairsOut()
         self._check(self.lib.ntl_pairs_finish(self.h, C.byref(po)), "ntl_pairs_finish")
         n = po.n_pairs
         raw = _np_from(po.pairs, n * 10, np.uint32).reshape(-1, 10) if n else np.empty((0, 10), np.uint32)
-        gaps = _np_from(po.gaps, po.n_gaps, np.int32)
+        return raw, _np_from(po.gaps, po.n_gaps, np.int32)
+
+    def pairs(self):
+        """[(src, tgt, flags, n, anchor, gaps int32[n])] in first-seen order (the reference's dict order)."""
+        raw, gaps = self.pairs_raw()
         out = []
         for row in raw:
             goff = int(row[6]) | (int(row[7]) << 32)

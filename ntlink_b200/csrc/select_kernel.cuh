@@ -20,6 +20,7 @@ constexpr int SEL_CAP = 2560;      // candidates staged per block (30 KB)
 __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restrict__ seq_off,
                                                          const uint32_t* __restrict__ strip_off, SkParams P, CandView V,
                                                          uint8_t* __restrict__ sel, uint32_t* __restrict__ selcnt,
+                                                         unsigned long long* __restrict__ selmask,
                                                          GapRec* __restrict__ gaps, uint32_t* __restrict__ gap_head,
                                                          SketchStatus* __restrict__ st) {
     __shared__ uint64_t sh_h[SEL_CAP];
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
     __shared__ uint8_t sh_t[SEL_CAP];             // staged strip number of every staged candidate
     __shared__ uint32_t sh_q[SEL_NL], sh_fs[SEL_NL], sh_es[SEL_NL], sh_idx0[SEL_NL], sh_n[SEL_NL], sh_np[SEL_NL];
     __shared__ uint32_t sh_sel[SEL_STRIPS];
+    __shared__ unsigned long long sh_mask[SEL_STRIPS];   // bit j = candidate j of the strip is a minimizer (j < 64)
     __shared__ uint32_t sh_bad;                   // the staged range cannot be used -> whole block falls back
 
     const uint32_t nstrips = st->nstrips;
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
     const uint32_t tid = threadIdx.x;
 
     if (tid == 0) sh_bad = 0;
-    if (tid < SEL_STRIPS) sh_sel[tid] = 0;
+    if (tid < SEL_STRIPS) { sh_sel[tid] = 0; sh_mask[tid] = 0ull; }
     __syncthreads();
     // per staged strip: candidate count and sequence bounds; offsets by a tiny serial scan (nl <= 38)
     if (tid < nl) {
@@ -142,7 +144,10 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
                 }
             }
             sel[gid] = selected ? 1 : 0;
-            if (selected) atomicAdd(&sh_sel[t - (b0 - l0)], 1u);
+            if (selected) {
+                atomicAdd(&sh_sel[t - (b0 - l0)], 1u);
+                if (j < 64) atomicOr(&sh_mask[t - (b0 - l0)], 1ull << j);
+            }
             if (gap_len >= w) queue_gap(gaps, gap_head, st, P, sh_q[t], (V.cands[gid].posf & POS_MASK) + 1, gap_end, s, j, gap_len);
         }
     } else {
@@ -154,14 +159,17 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
                 const SelectResult r = select_candidate(V, s, j, sh_fs[t], sh_es[t], w, sh_np[t]);
                 const uint64_t gid = cand_gid(V, s, j);
                 sel[gid] = r.selected ? 1 : 0;
-                if (r.selected) atomicAdd(&sh_sel[t - (b0 - l0)], 1u);
+                if (r.selected) {
+                    atomicAdd(&sh_sel[t - (b0 - l0)], 1u);
+                    if (j < 64) atomicOr(&sh_mask[t - (b0 - l0)], 1ull << j);
+                }
                 if (r.gap_len >= w)
                     queue_gap(gaps, gap_head, st, P, sh_q[t], (V.cands[gid].posf & POS_MASK) + 1, r.gap_end, s, j, r.gap_len);
             }
         }
     }
     __syncthreads();
-    if (tid < b1 - b0) selcnt[b0 + tid] = sh_sel[tid];
+    if (tid < b1 - b0) { selcnt[b0 + tid] = sh_sel[tid]; selmask[b0 + tid] = sh_mask[tid]; }
 }
 
 }  // namespace

@@ -21,47 +21,49 @@ namespace ntl {
 namespace {
 
 // ------------------------------------------------------------------------------------------- pack
-__device__ __forceinline__ uint32_t base_code(uint32_t c) {
-    // A/a=0 C/c=1 G/g=2 T/t=3 else 4. c & 0xDF folds case; then exact compares (predicated selects).
-    c &= 0xDFu;
-    uint32_t r = 4u;
-    r = (c == 0x41u) ? 0u : r;
-    r = (c == 0x43u) ? 1u : r;
-    r = (c == 0x47u) ? 2u : r;
-    r = (c == 0x54u) ? 3u : r;
-    return r;
+// four ASCII bases (one 32-bit word) -> four 4-bit codes in the low 16 bits: A/a=0 C/c=1 G/g=2 T/t=3, anything else 4.
+// SIMD within the register: (x>>1 ^ x>>2) & 3 is the classic ACGT code; the byte is valid iff it equals the letter that
+// code stands for (A 0x41, C 0x43, G 0x47, T 0x54 after case folding), checked for all four bytes at once.
+__device__ __forceinline__ uint32_t pack4(uint32_t w) {
+    const uint32_t x = w & 0xDFDFDFDFu;
+    const uint32_t c2 = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+    const uint32_t b0 = c2 & 0x01010101u, b1 = (c2 >> 1) & 0x01010101u;
+    const uint32_t expect = 0x41414141u + 2u * c2 + 2u * b1 + 11u * (b0 & b1);
+    const uint32_t d = x ^ expect;                                           // non-zero byte <=> invalid base
+    const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    const uint32_t m = nz >> 7;                                              // 0x01 per invalid byte
+    const uint32_t code = (c2 & ~(m * 3u)) | (m << 2);
+    const uint32_t t = code | (code >> 4);                                   // byte0 = c0|c1<<4, byte2 = c2|c3<<4
+    return __byte_perm(t, 0u, 0x4420);
 }
+
+constexpr int PACK_CHUNKS = 4;   // 16-byte chunks per thread, loaded up front (memory-level parallelism)
 
 __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ seq, uint64_t nbases,
                                               uint32_t* __restrict__ packed /* 8 bases per word */) {
-    // one thread = 16 bases = one 128-bit load, one 64-bit store
-    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t b0 = chunk * 16;
-    if (b0 >= nbases) return;
-    uint32_t w[4];
-    if (b0 + 16 <= nbases) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(seq + b0));
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-    } else {
-        for (int i = 0; i < 4; i++) {
-            uint32_t x = 0;
-            for (int j = 0; j < 4; j++) {
-                const uint64_t b = b0 + 4 * i + j;
-                const uint32_t ch = b < nbases ? seq[b] : (uint32_t)'N';
-                x |= ch << (8 * j);
+    const uint64_t chunk0 = (uint64_t)blockIdx.x * (blockDim.x * PACK_CHUNKS) + threadIdx.x;
+    uint4 v[PACK_CHUNKS];
+#pragma unroll
+    for (int i = 0; i < PACK_CHUNKS; i++) {
+        const uint64_t b0 = (chunk0 + (uint64_t)i * blockDim.x) * 16;
+        if (b0 + 16 <= nbases) v[i] = __ldg(reinterpret_cast<const uint4*>(seq + b0));
+        else {
+            uint32_t w[4] = {0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu};   // 'N'
+            for (int j = 0; j < 16; j++) {
+                const uint64_t b = b0 + j;
+                if (b < nbases) w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)seq[b] << (8 * (j & 3)));
             }
-            w[i] = x;
+            v[i] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
-    uint32_t o[2] = {0, 0};
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t code = base_code((w[i] >> (8 * j)) & 0xFFu);
-            o[i >> 1] |= code << (4 * ((i & 1) * 4 + j));
-        }
-    *reinterpret_cast<uint2*>(packed + chunk * 2) = make_uint2(o[0], o[1]);
+    for (int i = 0; i < PACK_CHUNKS; i++) {
+        const uint64_t chunk = chunk0 + (uint64_t)i * blockDim.x;
+        if (chunk * 16 >= nbases) continue;
+        const uint32_t o0 = pack4(v[i].x) | (pack4(v[i].y) << 16);
+        const uint32_t o1 = pack4(v[i].z) | (pack4(v[i].w) << 16);
+        *reinterpret_cast<uint2*>(packed + chunk * 2) = make_uint2(o0, o1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------- strips
@@ -365,6 +367,7 @@ namespace {
 
 // ------------------------------------------------------------------------------------------- emit
 __global__ void __launch_bounds__(128) k_emit(SkParams P, CandView V, const uint8_t* __restrict__ sel,
+                                              const unsigned long long* __restrict__ selmask,
                                               const uint32_t* __restrict__ selbase, const GapRec* __restrict__ gaps,
                                               const uint32_t* __restrict__ gap_head, const Cand* __restrict__ extras,
                                               uint64_t* __restrict__ out_hash, uint32_t* __restrict__ out_posf,
@@ -379,6 +382,18 @@ __global__ void __launch_bounds__(128) k_emit(SkParams P, CandView V, const uint
     if (end > P.out_cap) { atomicOr(&st->err, SKERR_OUT); return; }
     const uint32_t head = gap_head[s];
     const uint32_t c = V.cnt[s];
+    if (head == NONE32 && c <= 64 && c <= V.cap) {
+        // common case: no gap attached, the selected candidates come as a bit mask -> one iteration per minimizer
+        unsigned long long m = selmask[s];
+        const Cand* base = V.cands + (uint64_t)s * V.cap;
+        while (m) {
+            const int j = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const Cand e = base[j];
+            out_hash[o] = second_hash(e.h0, P.mult); out_posf[o] = e.posf; o++;
+        }
+        return;
+    }
     if (head != NONE32) {
         for (uint32_t g = head; g != NONE32; g = gaps[g].next)
             if (gaps[g].j == NONE32)
@@ -470,6 +485,7 @@ retry:
     NTL_CUDA(c, W.vbase.ensure(((size_t)nstrips_max + 2) * 4));
     NTL_CUDA(c, W.ovf_off.ensure(((size_t)nstrips_max + 1) * 4));
     NTL_CUDA(c, W.selcnt.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.selmask.ensure(((size_t)nstrips_max + 1) * 8));
     NTL_CUDA(c, W.selbase.ensure(((size_t)nstrips_max + 2) * 4));
     NTL_CUDA(c, W.gap_head.ensure(((size_t)nstrips_max + 1) * 4));
     NTL_CUDA(c, W.gaps.ensure((size_t)gaps_cap * sizeof(GapRec)));
@@ -496,7 +512,7 @@ retry:
     NTL_CUDA(c, cudaMemsetAsync(W.packed.as<char>() + 64 + total_bases / 2, 0x44, 192, c->stream));
 
     tick(c, T_PACK);
-    k_pack<<<div_up(div_up(total_bases, 16), 256), 256, 0, c->stream>>>(d_seq, total_bases, d_packed);
+    k_pack<<<div_up(div_up(total_bases, 16), 256 * PACK_CHUNKS), 256, 0, c->stream>>>(d_seq, total_bases, d_packed);
     k_strip_count<<<div_up(nseq, 256), 256, 0, c->stream>>>(d_off, nseq, k, w, S, W.scnt.as<uint32_t>(), nseq_dev);
     c->launches += 2;
     NTL_TRY(exclusive_scan_u32(c, W.scnt.as<uint32_t>(), W.strip_off.as<uint32_t>(), nseq_dev, nseq, W.blocksums));
@@ -521,7 +537,7 @@ retry:
     V.cands = W.slots.as<Cand>(); V.cnt = W.cnt.as<uint32_t>(); V.ovf_off = W.ovf_off.as<uint32_t>();
     V.vbase = W.vbase.as<uint32_t>(); V.cap = cap; V.pool_base = P.pool_base;
     k_select<<<div_up(nstrips_max, SEL_STRIPS), SEL_THREADS, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
-                                                             W.selcnt.as<uint32_t>(), W.gaps.as<GapRec>(),
+                                                             W.selcnt.as<uint32_t>(), W.selmask.as<unsigned long long>(), W.gaps.as<GapRec>(),
                                                              W.gap_head.as<uint32_t>(), st);
     k_seq_gaps<<<div_up(nseq, 128), 128, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.has_cand.as<uint8_t>(),
                                                         W.gaps.as<GapRec>(), W.gap_head.as<uint32_t>(), st);
@@ -560,7 +576,7 @@ retry:
     NTL_CUDA(c, out.hash.ensure((size_t)out_cap * 8 + 8));
     NTL_CUDA(c, out.posf.ensure((size_t)out_cap * 4 + 4));
     P.out_cap = out_cap;
-    k_emit<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(P, V, W.sel.as<uint8_t>(), W.selbase.as<uint32_t>(), W.gaps.as<GapRec>(),
+    k_emit<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(P, V, W.sel.as<uint8_t>(), W.selmask.as<unsigned long long>(), W.selbase.as<uint32_t>(), W.gaps.as<GapRec>(),
                                                            W.gap_head.as<uint32_t>(), W.extras.as<Cand>(), out.hash.as<uint64_t>(),
                                                            out.posf.as<uint32_t>(), st);
     k_seq_offsets<<<div_up((uint64_t)nseq + 1, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), W.selbase.as<uint32_t>(), nseq,

@@ -128,3 +128,24 @@ def test_larger_than_l2_properties(ctx):
     interior = np.ones(len(d), bool)
     interior[starts[(starts > 0) & (starts < len(sk.pos))] - 1] = False
     assert (d[interior] > 0).all()
+
+
+def test_indexlr_cli_drop_in(tmp_path):
+    "the indexlr-compatible executable: same argv as ntLink:199/223, TSV on stdout, file or stdin (gzip too)"
+    import gzip
+    import subprocess
+    import sys
+    env = dict(__import__("os").environ, PYTHONPATH=util.REPO)
+    tgt = util.fixture_file(tmp_path, "scaffolds_1.fa")
+    out = subprocess.check_output([sys.executable, util.REPO + "/bin/indexlr", "--long", "--pos", "--strand", "-k", "32",
+                                   "-w", "250", "-t", "4", tgt], env=env)
+    assert out == util.expected_output("scaffolds_1.fa.k32.w250.tsv")
+    reads = util.fixture_file(tmp_path, "long_reads_4_top5.fa")
+    gz = gzip.compress(open(reads, "rb").read())
+    out = subprocess.run([sys.executable, "-m", "ntlink_b200.indexlr", "--long", "--pos", "--strand", "--len", "-k", "40",
+                          "-w", "100", "-t", "2", "--chunk-bases", "30000", "-"], input=gz, env=env, cwd=util.REPO,
+                         stdout=subprocess.PIPE, check=True).stdout
+    assert out == util.oracle_indexlr(reads, 40, 100, length=True)
+    out = subprocess.check_output([sys.executable, "-m", "ntlink_b200.indexlr", "--long", "--pos", "-k", "15", "-w", "5",
+                                   tgt], env=env, cwd=util.REPO)
+    assert out == util.oracle_indexlr(tgt, 15, 5, strand=False)
