@@ -93,10 +93,36 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nblocks];
 }
+// small arrays (the strip table, per-read counters, the pair table): one block does the whole scan in one launch
+constexpr uint32_t SCAN_SMALL_MAX = 1u << 16;
+__global__ void __launch_bounds__(1024) k_scan_small(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                     const uint32_t* __restrict__ n_dev) {
+    __shared__ uint32_t sm[33];
+    const uint32_t n = *n_dev;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += 1024 * 4) {
+        const uint32_t i0 = base + threadIdx.x * 4;
+        uint32_t v[4], s = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { v[i] = (i0 + i < n) ? in[i0 + i] : 0; s += v[i]; }
+        uint32_t total;
+        uint32_t ex = block_excl_scan(s, sm, &total) + carry;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { if (i0 + i < n) out[i0 + i] = ex; ex += v[i]; }
+        carry += total;
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
 }  // namespace
 
 int exclusive_scan_u32(ntl_ctx* c, const uint32_t* in, uint32_t* out, const uint32_t* n_dev, uint32_t n_max,
                        DevBuf& blocksums) {
+    if (n_max <= SCAN_SMALL_MAX) {
+        k_scan_small<<<1, 1024, 0, c->stream>>>(in, out, n_dev);
+        c->launches += 1;
+        NTL_CUDA(c, cudaGetLastError());
+        return NTL_OK;
+    }
     const uint32_t nblocks = n_max ? (n_max + SCAN_TILE - 1) / SCAN_TILE : 1;
     NTL_CUDA(c, blocksums.ensure(((size_t)nblocks + 1) * sizeof(uint32_t)));
     k_scan_reduce<<<nblocks, SCAN_THREADS, 0, c->stream>>>(in, n_dev, blocksums.as<uint32_t>());

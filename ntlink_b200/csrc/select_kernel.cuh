@@ -15,7 +15,7 @@ constexpr int SEL_THREADS = 256;
 constexpr int SEL_STRIPS = 32;     // strips decided per block
 constexpr int SEL_CTX = 3;         // context strips staged on each side
 constexpr int SEL_NL = SEL_STRIPS + 2 * SEL_CTX;
-constexpr int SEL_CAP = 2560;      // candidates staged per block (30 KB)
+constexpr int SEL_CAP = 2560;      // candidates staged per block (40 KB)
 
 __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restrict__ seq_off,
                                                          const uint32_t* __restrict__ strip_off, SkParams P, CandView V,
@@ -23,11 +23,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
                                                          unsigned long long* __restrict__ selmask,
                                                          GapRec* __restrict__ gaps, uint32_t* __restrict__ gap_head,
                                                          SketchStatus* __restrict__ st) {
-    __shared__ uint64_t sh_h[SEL_CAP];
-    __shared__ uint32_t sh_i[SEL_CAP];
+    __shared__ uint4 sh_c[SEL_CAP];               // staged candidate: {h0.lo, h0.hi, valid-k-mer index, staged strip}
     __shared__ uint32_t sh_off[SEL_NL + 1];       // compact offset of every staged strip
     __shared__ uint32_t sh_cnt[SEL_NL];
-    __shared__ uint8_t sh_t[SEL_CAP];             // staged strip number of every staged candidate
     __shared__ uint32_t sh_q[SEL_NL], sh_fs[SEL_NL], sh_es[SEL_NL], sh_idx0[SEL_NL], sh_n[SEL_NL], sh_np[SEL_NL];
     __shared__ uint32_t sh_sel[SEL_STRIPS];
     __shared__ unsigned long long sh_mask[SEL_STRIPS];   // bit j = candidate j of the strip is a minimizer (j < 64)
@@ -74,9 +72,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
             const uint32_t s = l0 + t, c = sh_cnt[t], o = sh_off[t], vb = V.vbase[s];
             for (uint32_t j = tid & 31; j < c; j += 32) {
                 const Cand cd = V.cands[(uint64_t)s * V.cap + j];
-                sh_h[o + j] = cd.h0;
-                sh_i[o + j] = vb + cd.lord;
-                sh_t[o + j] = (uint8_t)t;
+                sh_c[o + j] = make_uint4((uint32_t)cd.h0, (uint32_t)(cd.h0 >> 32), vb + cd.lord, t);
             }
         }
     }
@@ -88,13 +84,14 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
         const uint32_t e_begin = sh_off[b0 - l0], e_end = sh_off[b1 - l0];
         const int64_t first_idx = V.vbase[l0], end_idx = V.vbase[l1];   // valid k-mers covered by the staged strips
         for (uint32_t e = e_begin + tid; e < e_end; e += SEL_THREADS) {
-            const uint32_t t = sh_t[e], s = l0 + t, j = e - sh_off[t];
+            const uint4 me = sh_c[e];
+            const uint32_t t = me.w, s = l0 + t, j = e - sh_off[t];
             const uint32_t fs = sh_fs[t], es = sh_es[t];
             const int32_t w32 = (int32_t)w, W1s = w32 - 1;
             const uint32_t idx0u = sh_idx0[t];
             const int64_t idx0 = idx0u, n = sh_n[t];
-            const uint64_t val = sh_h[e];
-            const uint32_t idxu = sh_i[e];
+            const uint64_t val = ((uint64_t)me.y << 32) | me.x;
+            const uint32_t idxu = me.z;
             const int64_t idx = idxu, rel = idx - idx0;
             const uint32_t e_lo = sh_off[(fs > l0 ? fs : l0) - l0];      // staged candidates of the same sequence
             const uint32_t e_hi = sh_off[(es < l1 ? es : l1) - l0];
@@ -103,9 +100,10 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
             int64_t A = -1;
             for (uint32_t p = e; p > e_lo;) {
                 p--;
-                const int32_t d = (int32_t)(idxu - sh_i[p]);
+                const uint4 cp = sh_c[p];
+                const int32_t d = (int32_t)(idxu - cp.z);
                 if (d >= w32) { A = W1s; break; }
-                if (sh_h[p] < val) { A = d - 1; break; }
+                if ((((uint64_t)cp.y << 32) | cp.x) < val) { A = d - 1; break; }
             }
             if (A < 0) {
                 if (fs >= l0) A = rel;                                   // the sequence starts inside the staged range
@@ -116,13 +114,14 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
             int64_t B = -1;
             uint32_t gap_len = 0, gap_end = 0;
             bool gap_known = true;
-            if (e + 1 < e_hi) gap_len = sh_i[e + 1] - idxu - 1;
+            if (e + 1 < e_hi) gap_len = sh_c[e + 1].z - idxu - 1;
             else if (es <= l1) { gap_len = (uint32_t)(idx0 + n - 1 - idx); gap_end = sh_np[t]; }
             else gap_known = false;
             for (uint32_t p = e + 1; p < e_hi; p++) {
-                const int32_t d = (int32_t)(sh_i[p] - idxu);
+                const uint4 cp = sh_c[p];
+                const int32_t d = (int32_t)(cp.z - idxu);
                 if (d >= w32) { B = W1s; break; }
-                if (sh_h[p] <= val) { B = d - 1; break; }
+                if ((((uint64_t)cp.y << 32) | cp.x) <= val) { B = d - 1; break; }
             }
             if (B < 0) {
                 if (es <= l1) B = idx0 + n - 1 - idx;                    // the sequence ends inside the staged range
@@ -139,7 +138,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
                 int64_t hi_w = rel; if (n - (int64_t)w < hi_w) hi_w = n - (int64_t)w; if (rel + B - W1 < hi_w) hi_w = rel + B - W1;
                 selected = lo_w <= hi_w;
                 if (gap_len >= w && e + 1 < e_hi) {                      // position of the neighbour that ends the stretch
-                    const uint32_t t2 = sh_t[e + 1];
+                    const uint32_t t2 = sh_c[e + 1].w;
                     gap_end = V.cands[(uint64_t)(l0 + t2) * V.cap + (e + 1 - sh_off[t2])].posf & POS_MASK;
                 }
             }

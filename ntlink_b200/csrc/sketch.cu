@@ -121,17 +121,25 @@ struct SlotEmit {
 //    irregular (sequence tail, first output block, blocks containing N) goes through the generic block.
 struct H32 { uint32_t flo, fhi, rlo, rhi; };
 
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
+
+// one base: fh' = srol(fh) ^ t.f ; rh' = sror(rh ^ t.r) on 32-bit halves, 7 integer ops per strand.
+// LOP3 truth tables (A=0xF0, B=0xCC, C=0xAA): 0x6A = (A&B)^C, 0x28 = (A^B)&C, 0x96 = A^B^C, 0xD8 = (A&~C)|(B&C), 0xF8 = A|(B&C)
 __device__ __forceinline__ void roll32(H32& h, const uint4 t) {
-    const uint32_t a = h.flo << 1;
-    const uint32_t b = __funnelshift_l(h.flo, h.fhi, 1);
-    const uint32_t c = h.fhi >> 30;
-    const uint32_t lo = a ^ (h.fhi & 1u) ^ t.x;            // bit32 -> bit0
-    const uint32_t hi = b ^ ((b ^ c) & 2u) ^ t.y;          // bit63 -> bit33
+    const uint32_t a = h.flo + h.flo;                              // bits 1..31 of the low word
+    const uint32_t b = __funnelshift_l(h.flo, h.fhi, 1);           // high word shifted, bit 31 of lo carried in
+    const uint32_t c = h.fhi >> 30;                                // bit63 lands on bit 1
+    const uint32_t lo = a ^ lop3<0x6A>(h.fhi, 1u, t.x);            // bit32 -> bit0, xor table
+    const uint32_t hi = lop3<0x96>(b, lop3<0x28>(b, c, 2u), t.y);  // bit63 -> bit33, xor table
     const uint32_t xlo = h.rlo ^ t.z, xhi = h.rhi ^ t.w;
     const uint32_t rl = __funnelshift_r(xlo, xhi, 1);
-    const uint32_t s = xhi >> 1;
-    const uint32_t u = (s & ~1u) | (xlo & 1u);             // bit0 -> bit32
-    const uint32_t rh = u | ((xhi << 30) & 0x80000000u);   // bit33 -> bit63
+    const uint32_t u = lop3<0xD8>(xhi >> 1, xlo, 1u);              // bit0 -> bit32
+    const uint32_t rh = lop3<0xF8>(u, xhi << 30, 0x80000000u);     // bit33 -> bit63
     h.flo = lo; h.fhi = hi; h.rlo = rl; h.rhi = rh;
 }
 
@@ -200,7 +208,7 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
     bool out_live = false;
     for (int32_t t0 = 0; t0 < T; t0 += 32) {
         const int32_t sb = t0 >> 5;
-        uint32_t xi[5], xo[5];
+        uint32_t xi[5], xo[5] = {0, 0, 0, 0, 0};
         const uint4 Bin = chunks[ci_in + sb + 1];
         pick5(Ain, Bin, r_in, xi);
         Ain = Bin;
@@ -211,16 +219,24 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
             pick5(Aout, Bout, r_out, xo);
             Aout = Bout;
         }
-#pragma unroll
+        // the four 8-step blocks share ONE copy of the unrolled step code (keeps the kernel inside the instruction cache)
+#pragma unroll 1
         for (int b = 0; b < 4; b++) {
             const int32_t t = t0 + 8 * b;
             if (t >= T) break;
-            const uint32_t wi = __funnelshift_r(xi[b], xi[b + 1], sh_in);
+            uint32_t xa, xb, ya, yb;
+            switch (b) {
+                case 0: xa = xi[0]; xb = xi[1]; ya = xo[0]; yb = xo[1]; break;
+                case 1: xa = xi[1]; xb = xi[2]; ya = xo[1]; yb = xo[2]; break;
+                case 2: xa = xi[2]; xb = xi[3]; ya = xo[2]; yb = xo[3]; break;
+                default: xa = xi[3]; xb = xi[4]; ya = xo[3]; yb = xo[4]; break;
+            }
+            const uint32_t wi = __funnelshift_r(xa, xb, sh_in);
             uint32_t wo;
             const int32_t o = t - (int32_t)k;
             if (o <= -8) wo = 0x44444444u;
             else {
-                wo = __funnelshift_r(xo[b], xo[b + 1], sh_out);
+                wo = __funnelshift_r(ya, yb, sh_out);
                 if (o < 0) {                                          // the first -o steps still push out virtual bases
                     const uint32_t m = (1u << (4u * (uint32_t)(-o))) - 1u;
                     wo = (wo & ~m) | (0x44444444u & m);
