@@ -143,7 +143,7 @@ void ntl_destroy(ntl_ctx* c) {
     Results* R = res_of(c);
     SketchWork& W = c->sw;
     DevBuf* sb[] = {&W.packed, &W.scnt, &W.strip_off, &W.blocksums, &W.slots, &W.cnt, &W.nv, &W.vbase, &W.ovf_off, &W.sel,
-                    &W.selcnt, &W.selmask, &W.selbase, &W.gaps, &W.gap_head, &W.extras, &W.has_cand, &W.status, &W.tbl};
+                    &W.selcnt, &W.selmask, &W.selbase, &W.strip_seq, &W.gaps, &W.gap_head, &W.extras, &W.has_cand, &W.status, &W.tbl};
     for (DevBuf* b : sb) b->release();
     MapWork& M = c->mw;
     DevBuf* mb[] = {&M.hit_tmp, &M.hit_flag, &M.hit_pref, &M.hits, &M.runs, &M.mark, &M.hit_off, &M.nruns, &M.events,

@@ -75,7 +75,7 @@ enum { T_PACK = NTL_T_PACK, T_DENSE = NTL_T_DENSE, T_SELECT = NTL_T_SELECT, T_GA
        T_TOTAL = NTL_T_TOTAL, T_NUM = NTL_T_NUM };
 
 struct SketchWork {           // device workspace of the sketch pipeline (reused across calls)
-    DevBuf packed, scnt, strip_off, blocksums, slots, cnt, nv, vbase, ovf_off, sel, selcnt, selmask, selbase,
+    DevBuf packed, scnt, strip_off, blocksums, slots, cnt, nv, vbase, ovf_off, sel, selcnt, selmask, selbase, strip_seq,
         gaps, gap_head, extras, has_cand, status, tbl;
     uint32_t tbl_k = 0;       // k the device roll table was built for
 };

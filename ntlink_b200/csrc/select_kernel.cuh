@@ -18,7 +18,8 @@ constexpr int SEL_NL = SEL_STRIPS + 2 * SEL_CTX;
 constexpr int SEL_CAP = 2560;      // candidates staged per block (40 KB)
 
 __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restrict__ seq_off,
-                                                         const uint32_t* __restrict__ strip_off, SkParams P, CandView V,
+                                                         const uint32_t* __restrict__ strip_off,
+                                                         const uint32_t* __restrict__ strip_seq, SkParams P, CandView V,
                                                          uint8_t* __restrict__ sel, uint32_t* __restrict__ selcnt,
                                                          unsigned long long* __restrict__ selmask,
                                                          GapRec* __restrict__ gaps, uint32_t* __restrict__ gap_head,
@@ -49,17 +50,25 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
         uint32_t c = V.cnt[s];
         if (c > V.cap) { sh_bad = 1; c = 0; }
         sh_cnt[tid] = c;
-        const uint32_t q = seq_of_strip(strip_off, P.nseq, s);
+        const uint32_t q = strip_seq[s];
         const uint32_t fs = strip_off[q], es = strip_off[q + 1];
         sh_q[tid] = q; sh_fs[tid] = fs; sh_es[tid] = es;
         sh_idx0[tid] = V.vbase[fs]; sh_n[tid] = V.vbase[es] - V.vbase[fs];
         sh_np[tid] = seq_npos(seq_off[q + 1] - seq_off[q], P.k, P.w);
     }
     __syncthreads();
-    if (tid == 0) {
-        uint32_t acc = 0;
-        for (uint32_t t = 0; t < nl; t++) { sh_off[t] = acc; acc += sh_cnt[t]; }
-        sh_off[nl] = acc;
+    if (tid < 32) {                               // exclusive scan of <= 64 counts by one warp (two per lane)
+        const uint32_t a = tid < nl ? sh_cnt[tid] : 0, b = tid + 32 < nl ? sh_cnt[tid + 32] : 0;
+        uint32_t x = a, y = b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x2 = __shfl_up_sync(0xffffffffu, x, d), y2 = __shfl_up_sync(0xffffffffu, y, d);
+            if (tid >= (uint32_t)d) { x += x2; y += y2; }
+        }
+        const uint32_t tot_a = __shfl_sync(0xffffffffu, x, 31);
+        if (tid < nl) sh_off[tid] = x - a;
+        if (tid + 32 < nl) sh_off[tid + 32] = tot_a + y - b;
+        if (tid == 31) sh_off[nl] = tot_a + y;
     }
     __syncthreads();
     const uint32_t total = sh_off[nl];
@@ -83,47 +92,74 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
     if (staged) {
         const uint32_t e_begin = sh_off[b0 - l0], e_end = sh_off[b1 - l0];
         const int64_t first_idx = V.vbase[l0], end_idx = V.vbase[l1];   // valid k-mers covered by the staged strips
-        for (uint32_t e = e_begin + tid; e < e_end; e += SEL_THREADS) {
-            const uint4 me = sh_c[e];
-            const uint32_t t = me.w, s = l0 + t, j = e - sh_off[t];
-            const uint32_t fs = sh_fs[t], es = sh_es[t];
-            const int32_t w32 = (int32_t)w, W1s = w32 - 1;
-            const uint32_t idx0u = sh_idx0[t];
-            const int64_t idx0 = idx0u, n = sh_n[t];
+        const int32_t w32 = (int32_t)w, W1s = w32 - 1;
+        // Uniform trip count for the whole block and explicit reconvergence (__syncwarp) after each scan: the scans
+        // have data-dependent lengths, and without the barriers the lanes of a warp run the long tail below one
+        // small group at a time.
+        for (uint32_t eb = e_begin; eb < e_end; eb += SEL_THREADS) {
+            const uint32_t e = eb + tid;
+            const bool act = e < e_end;
+            uint4 me = make_uint4(0, 0, 0, 0);
+            uint32_t t = 0, e_lo = 0, e_hi = 0;
+            if (act) {
+                me = sh_c[e];
+                t = me.w;
+                const uint32_t fs0 = sh_fs[t], es0 = sh_es[t];
+                e_lo = sh_off[(fs0 > l0 ? fs0 : l0) - l0];               // staged candidates of the same sequence
+                e_hi = sh_off[(es0 < l1 ? es0 : l1) - l0];
+            }
             const uint64_t val = ((uint64_t)me.y << 32) | me.x;
             const uint32_t idxu = me.z;
-            const int64_t idx = idxu, rel = idx - idx0;
-            const uint32_t e_lo = sh_off[(fs > l0 ? fs : l0) - l0];      // staged candidates of the same sequence
-            const uint32_t e_hi = sh_off[(es < l1 ? es : l1) - l0];
-            bool need_fallback = false;
-            // left: first strictly smaller value
-            int64_t A = -1;
-            for (uint32_t p = e; p > e_lo;) {
-                p--;
-                const uint4 cp = sh_c[p];
-                const int32_t d = (int32_t)(idxu - cp.z);
-                if (d >= w32) { A = W1s; break; }
-                if ((((uint64_t)cp.y << 32) | cp.x) < val) { A = d - 1; break; }
+            // left: first strictly smaller value (single-exit loop)
+            int32_t A32 = -1;
+            {
+                uint32_t p = e;
+                bool go = act && p > e_lo;
+                while (go) {
+                    p--;
+                    const uint4 cp = sh_c[p];
+                    const int32_t d = (int32_t)(idxu - cp.z);
+                    const bool far = d >= w32;
+                    const bool smaller = (((uint64_t)cp.y << 32) | cp.x) < val;
+                    if (far | smaller) { A32 = far ? W1s : d - 1; go = false; }
+                    else go = p > e_lo;
+                }
             }
-            if (A < 0) {
+            __syncwarp();
+            // right: first smaller-or-equal value
+            int32_t B32 = -1;
+            {
+                uint32_t p = e + 1;
+                bool go = act && p < e_hi;
+                while (go) {
+                    const uint4 cp = sh_c[p];
+                    const int32_t d = (int32_t)(cp.z - idxu);
+                    const bool far = d >= w32;
+                    const bool smaller = (((uint64_t)cp.y << 32) | cp.x) <= val;
+                    if (far | smaller) { B32 = far ? W1s : d - 1; go = false; }
+                    else { p++; go = p < e_hi; }
+                }
+            }
+            __syncwarp();
+            if (!act) continue;
+            const uint32_t s = l0 + t, j = e - sh_off[t];
+            const uint32_t fs = sh_fs[t], es = sh_es[t];
+            const int64_t idx0 = sh_idx0[t], n = sh_n[t];
+            const int64_t idx = idxu, rel = idx - idx0;
+            bool need_fallback = false;
+            int64_t A = A32, B = B32;
+            if (A32 < 0) {
                 if (fs >= l0) A = rel;                                   // the sequence starts inside the staged range
                 else if (idx - first_idx >= W1) A = W1;                  // everything earlier is out of reach
                 else need_fallback = true;
             }
-            // right: first smaller-or-equal value; the immediate neighbour bounds the candidate-free stretch
-            int64_t B = -1;
+            // the immediate right neighbour bounds the candidate-free stretch
             uint32_t gap_len = 0, gap_end = 0;
             bool gap_known = true;
             if (e + 1 < e_hi) gap_len = sh_c[e + 1].z - idxu - 1;
             else if (es <= l1) { gap_len = (uint32_t)(idx0 + n - 1 - idx); gap_end = sh_np[t]; }
             else gap_known = false;
-            for (uint32_t p = e + 1; p < e_hi; p++) {
-                const uint4 cp = sh_c[p];
-                const int32_t d = (int32_t)(cp.z - idxu);
-                if (d >= w32) { B = W1s; break; }
-                if ((((uint64_t)cp.y << 32) | cp.x) <= val) { B = d - 1; break; }
-            }
-            if (B < 0) {
+            if (B32 < 0) {
                 if (es <= l1) B = idx0 + n - 1 - idx;                    // the sequence ends inside the staged range
                 else if (end_idx - idx > W1) B = W1;
                 else need_fallback = true;

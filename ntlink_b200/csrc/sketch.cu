@@ -100,6 +100,14 @@ __device__ __forceinline__ uint32_t seq_of_strip(const uint32_t* __restrict__ st
     return lo;
 }
 
+// strip -> sequence table, computed once per batch (k_dense, k_overflow and k_select then need one load instead of a
+// 14-step dependent binary search per thread)
+__global__ void k_strip_seq(const uint32_t* __restrict__ strip_off, uint32_t nseq, uint32_t* __restrict__ strip_seq) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= strip_off[nseq]) return;
+    strip_seq[s] = seq_of_strip(strip_off, nseq, s);
+}
+
 struct SlotEmit {
     uint4* p;          // next slot (a Cand is exactly one uint4: h0.lo, h0.hi, posf, lord)
     int32_t room;      // free slots left; keeps counting below zero so that cap - room = total candidates
@@ -272,7 +280,7 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
 }
 
 __global__ void __launch_bounds__(128) k_dense(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
-                                               const uint32_t* __restrict__ strip_off, SkParams P,
+                                               const uint32_t* __restrict__ strip_off, const uint32_t* __restrict__ strip_seq, SkParams P,
                                                const RollEntry* __restrict__ tbl_g, Cand* __restrict__ slots,
                                                uint32_t* __restrict__ cnt, uint32_t* __restrict__ nv,
                                                uint8_t* __restrict__ has_cand, SketchStatus* __restrict__ st) {
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(128) k_dense(const uint32_t* __restrict__ pack
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) st->nstrips = nstrips;
     if (s >= nstrips) return;
-    const uint32_t q = seq_of_strip(strip_off, P.nseq, s);
+    const uint32_t q = strip_seq[s];
     const uint64_t gseq = seq_off[q];
     const uint32_t np = seq_npos(seq_off[q + 1] - gseq, P.k, P.w);
     const uint32_t p0 = (s - strip_off[q]) * P.S;
@@ -312,7 +320,7 @@ struct PoolEmit {
 
 // strips whose candidate count exceeded the slot capacity: reserve room in the pool and run them again
 __global__ void __launch_bounds__(128) k_overflow(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
-                                                  const uint32_t* __restrict__ strip_off, SkParams P,
+                                                  const uint32_t* __restrict__ strip_off, const uint32_t* __restrict__ strip_seq, SkParams P,
                                                   const RollEntry* __restrict__ tbl_g, Cand* __restrict__ cands,
                                                   const uint32_t* __restrict__ cnt, uint32_t* __restrict__ ovf_off,
                                                   SketchStatus* __restrict__ st) {
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(128) k_overflow(const uint32_t* __restrict__ p
     const uint32_t off = atomicAdd(&st->pool_used, cnt[s]);
     if ((uint64_t)off + cnt[s] > P.pool_cap) { atomicOr(&st->err, SKERR_POOL); ovf_off[s] = 0; return; }
     ovf_off[s] = off;
-    const uint32_t q = seq_of_strip(strip_off, P.nseq, s);
+    const uint32_t q = strip_seq[s];
     const uint64_t gseq = seq_off[q];
     const uint32_t np = seq_npos(seq_off[q + 1] - gseq, P.k, P.w);
     const uint32_t p0 = (s - strip_off[q]) * P.S;
@@ -502,6 +510,7 @@ retry:
     NTL_CUDA(c, W.ovf_off.ensure(((size_t)nstrips_max + 1) * 4));
     NTL_CUDA(c, W.selcnt.ensure(((size_t)nstrips_max + 1) * 4));
     NTL_CUDA(c, W.selmask.ensure(((size_t)nstrips_max + 1) * 8));
+    NTL_CUDA(c, W.strip_seq.ensure(((size_t)nstrips_max + 1) * 4));
     NTL_CUDA(c, W.selbase.ensure(((size_t)nstrips_max + 2) * 4));
     NTL_CUDA(c, W.gap_head.ensure(((size_t)nstrips_max + 1) * 4));
     NTL_CUDA(c, W.gaps.ensure((size_t)gaps_cap * sizeof(GapRec)));
@@ -533,18 +542,19 @@ retry:
     c->launches += 2;
     NTL_TRY(exclusive_scan_u32(c, W.scnt.as<uint32_t>(), W.strip_off.as<uint32_t>(), nseq_dev, nseq, W.blocksums));
     k_fill_u32<<<296, 256, 0, c->stream>>>(W.gap_head.as<uint32_t>(), NONE32, (uint64_t)nstrips_max + 1);
-    c->launches += 1;
+    k_strip_seq<<<div_up(nstrips_max, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), nseq, W.strip_seq.as<uint32_t>());
+    c->launches += 2;
     tock(c, T_PACK);
 
     tick(c, T_DENSE);
-    k_dense<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), P,
+    k_dense<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,
                                                             W.tbl.as<RollEntry>(), W.slots.as<Cand>(), W.cnt.as<uint32_t>(),
                                                             W.nv.as<uint32_t>(), W.has_cand.as<uint8_t>(), st);
     tock(c, T_DENSE);
     c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases;
 
     tick(c, T_SELECT);
-    k_overflow<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), P,
+    k_overflow<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,
                                                                W.tbl.as<RollEntry>(), W.slots.as<Cand>(), W.cnt.as<uint32_t>(),
                                                                W.ovf_off.as<uint32_t>(), st);
     c->launches += 1;
@@ -552,7 +562,7 @@ retry:
     CandView V;
     V.cands = W.slots.as<Cand>(); V.cnt = W.cnt.as<uint32_t>(); V.ovf_off = W.ovf_off.as<uint32_t>();
     V.vbase = W.vbase.as<uint32_t>(); V.cap = cap; V.pool_base = P.pool_base;
-    k_select<<<div_up(nstrips_max, SEL_STRIPS), SEL_THREADS, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
+    k_select<<<div_up(nstrips_max, SEL_STRIPS), SEL_THREADS, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
                                                              W.selcnt.as<uint32_t>(), W.selmask.as<unsigned long long>(), W.gaps.as<GapRec>(),
                                                              W.gap_head.as<uint32_t>(), st);
     k_seq_gaps<<<div_up(nseq, 128), 128, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.has_cand.as<uint8_t>(),
