@@ -324,13 +324,18 @@ def run_gpu(args, rank, world, local_rank):
         e2e = total_bases * args.steps / t_e2e / 1e9
         peak, peak_kind = measured_peak()
         n_mx = stats["mx"]
-        dense_ms = tm["dense"] / max(1, tm["dense_launches"])
-        # algorithmic bytes of the sketch per dense launch (1.0 B/base ASCII + 13 B/minimizer);
-        # each step has two dense launches (target, reads): average bytes per launch over the timed region
-        bases_per_launch = tm["dense_bases"] / max(1, tm["dense_launches"])
+        # roofline of the dominant kernel: k_dense over the read batch (one launch per step; the 5 Mbp target launch is
+        # excluded). Algorithmic bytes per launch: 1.0 B/base of ASCII + 13 B per minimizer.
+        dense_ms = tm["big_dense_ms"] / max(1, tm["big_dense_launches"])
+        bases_per_launch = tm["big_dense_bases"] / max(1, tm["big_dense_launches"])
         mx_per_base = n_mx / read_bases
         alg_bytes = bases_per_launch * (1.0 + 13.0 * mx_per_base)
         achieved = alg_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as fin:
+                traffic = json.load(fin).get("k_dense_reads_launch_dram_bytes")
         line = {"metric": "long_read_gbp_per_s_sketched_mapped", "value": value, "unit": "Gbp/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -348,10 +353,12 @@ def run_gpu(args, rank, world, local_rank):
                 "gpu_launches": int(tm["launches"]),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "k_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                             "ms_per_launch": dense_ms, "launches": int(tm["dense_launches"]),
+                             "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                             "ms_per_launch": dense_ms, "launches": int(tm["big_dense_launches"]),
                              "algorithmic_bytes_per_launch": alg_bytes,
-                             "note": "integer-ALU bound kernel (rolling ntHash); HBM fraction reported as the metric asks"},
+                             "note": "integer-ALU bound kernel (rolling ntHash: ncu alu pipe 83 %, DRAM 11 %, "
+                                     "profiles/r1_k_dense_ncu_full.txt); HBM fraction reported as the metric asks; traffic = "
+                                     "dram read+write bytes of the same launch from ncu --set full (profiles/r1_traffic.json)"},
                 "stage_ms_per_step": {k: tm[k] / args.steps for k in ("pack", "dense", "select", "gap", "emit", "lookup",
                                                                       "chain", "tally", "index")},
                 "counts": {"read_minimizers": int(n_mx), "hits": int(stats["hits"]), "runs": int(stats["runs"]),

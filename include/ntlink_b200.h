@@ -207,6 +207,9 @@ enum { NTL_T_PACK = 0, NTL_T_DENSE, NTL_T_SELECT, NTL_T_GAP, NTL_T_EMIT, NTL_T_L
 int ntl_timing_reset(ntl_ctx* ctx);
 int ntl_timing(ntl_ctx* ctx, double* ms_accum /* [NTL_T_NUM] */, uint64_t* launches, uint64_t* dense_launches,
                uint64_t* dense_bases);
+/* the dominant kernel (k_dense) alone, restricted to launches over at least min 16 Mbp (the read batches): accumulated
+ * device time, launches and bases since ntl_timing_reset -- what bench.py's roofline block is computed from */
+int ntl_timing_dense(ntl_ctx* ctx, double* ms_accum, uint64_t* launches, uint64_t* bases);
 int ntl_device_sync(ntl_ctx* ctx);
 /* CUDA-event stopwatch on the library's stream: ntl_mark(ctx, 0) ... work ... ntl_mark(ctx, 1); after a sync
  * ntl_mark_elapsed gives the device time between the two marks in milliseconds */

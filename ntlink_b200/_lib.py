@@ -97,6 +97,7 @@ SIGNATURES = {
     "ntl_index_build_resident": (C.c_int, [_VP, C.c_int, C.c_int]),
     "ntl_timing_reset": (C.c_int, [_VP]),
     "ntl_timing": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P, _U64P, _U64P]),
+    "ntl_timing_dense": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P, _U64P]),
     "ntl_device_sync": (C.c_int, [_VP]),
     "ntl_mark": (C.c_int, [_VP, C.c_int]),
     "ntl_mark_elapsed": (C.c_int, [_VP, C.POINTER(C.c_double)]),

@@ -339,6 +339,9 @@ class Context:
         self._check(self.lib.ntl_timing(self.h, ms, C.byref(a), C.byref(b), C.byref(c)), "ntl_timing")
         d = {name: ms[i] for i, name in enumerate(_lib.T_NAMES)}
         d.update(launches=a.value, dense_launches=b.value, dense_bases=c.value)
+        ms1, n1, b1 = C.c_double(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.ntl_timing_dense(self.h, C.byref(ms1), C.byref(n1), C.byref(b1)), "ntl_timing_dense")
+        d.update(big_dense_ms=ms1.value, big_dense_launches=n1.value, big_dense_bases=b1.value)
         return d
 
     def mark(self, which):

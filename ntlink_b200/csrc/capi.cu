@@ -606,6 +606,14 @@ int ntl_timing_reset(ntl_ctx* c) {
     if (!c) return NTL_ERR_ARG;
     for (int i = 0; i < T_NUM; i++) c->ms_accum[i] = 0;
     c->launches = 0; c->dense_launches = 0; c->dense_bases = 0;
+    c->big_dense_ms = 0; c->big_dense_launches = 0; c->big_dense_bases = 0;
+    return NTL_OK;
+}
+int ntl_timing_dense(ntl_ctx* c, double* ms_accum, uint64_t* launches, uint64_t* bases) {
+    if (!c) return NTL_ERR_ARG;
+    if (ms_accum) *ms_accum = c->big_dense_ms;
+    if (launches) *launches = c->big_dense_launches;
+    if (bases) *bases = c->big_dense_bases;
     return NTL_OK;
 }
 int ntl_timing(ntl_ctx* c, double* ms_accum, uint64_t* launches, uint64_t* dense_launches, uint64_t* dense_bases) {

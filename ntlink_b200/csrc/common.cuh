@@ -131,6 +131,9 @@ struct ntl_ctx {
     uint64_t launches = 0;                 // kernels launched since ntl_timing_reset
     uint64_t dense_launches = 0;
     uint64_t dense_bases = 0;
+    uint64_t last_dense_bases = 0;         // size of the most recent k_dense launch
+    double big_dense_ms = 0;               // k_dense launches over >= 16 Mbp only (read batches)
+    uint64_t big_dense_launches = 0, big_dense_bases = 0;
     // tally state (pairs accumulated over calls)
     ntl::DevBuf tl_events;                 // all events appended so far
     uint64_t tl_n_events = 0;
@@ -170,7 +173,12 @@ inline void collect_timing(ntl_ctx* c) {
     for (int s = 0; s < T_NUM; s++) {
         if (!c->ev_used[s]) continue;
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->ev[2 * s], c->ev[2 * s + 1]) == cudaSuccess) c->ms_accum[s] += ms;
+        if (cudaEventElapsedTime(&ms, c->ev[2 * s], c->ev[2 * s + 1]) == cudaSuccess) {
+            c->ms_accum[s] += ms;
+            if (s == T_DENSE && c->last_dense_bases >= (16ull << 20)) {
+                c->big_dense_ms += ms; c->big_dense_launches += 1; c->big_dense_bases += c->last_dense_bases;
+            }
+        }
         c->ev_used[s] = false;
     }
 }
