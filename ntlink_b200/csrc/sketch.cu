@@ -138,6 +138,8 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 
 // one base: fh' = srol(fh) ^ t.f ; rh' = sror(rh ^ t.r) on 32-bit halves, 7 integer ops per strand.
 // LOP3 truth tables (A=0xF0, B=0xCC, C=0xAA): 0x6A = (A&B)^C, 0x28 = (A^B)&C, 0x96 = A^B^C, 0xD8 = (A&~C)|(B&C), 0xF8 = A|(B&C)
+// (Tried: writing the shifts as mul/mulhi so that they issue on the idle FMA pipe -- IMAD.HI is slow enough that it
+// was a net loss on B200; the funnel-shift form below is the fastest measured.)
 __device__ __forceinline__ void roll32(H32& h, const uint4 t) {
     const uint32_t a = h.flo + h.flo;                              // bits 1..31 of the low word
     const uint32_t b = __funnelshift_l(h.flo, h.fhi, 1);           // high word shifted, bit 31 of lo carried in
