@@ -109,13 +109,20 @@ __global__ void k_strip_seq(const uint32_t* __restrict__ strip_off, uint32_t nse
 }
 
 struct SlotEmit {
-    uint4* p;          // next slot (a Cand is exactly one uint4: h0.lo, h0.hi, posf, lord)
-    int32_t room;      // free slots left; keeps counting below zero so that cap - room = total candidates
+    uint4* base;       // slot array of the strip (a Cand is exactly one uint4: h0.lo, h0.hi, posf, lord)
+    uint32_t cap;
+    uint32_t count;    // keeps counting past cap so that the strip's total is known
+    // checked form (generic blocks)
     __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) {
-        if (room > 0) *p = make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), pos | (fwd ? FWD_BIT : 0u), lord);
-        p++;
-        room--;
+        if (count < cap) base[count] = make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), pos | (fwd ? FWD_BIT : 0u), lord);
+        count++;
     }
+    // unchecked form: the caller guarantees room for the whole 8-step block
+    __device__ __forceinline__ void fast(uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) {
+        base[count] = make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), pos | (fwd ? FWD_BIT : 0u), lord);
+        count++;
+    }
+    __device__ __forceinline__ bool room_for_block() const { return count + 8 <= cap; }
 };
 
 // ---- the hot loop, device-only formulation --------------------------------------------------------------------
@@ -260,8 +267,8 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
-            } else if (clean && t >= lead && t + 8 <= T && t - last_bad >= (int32_t)k) {
-                // interior: 8 valid, in-range k-mers
+            } else if (clean && t >= lead && t + 8 <= T && t - last_bad >= (int32_t)k && emit.room_for_block()) {
+                // interior: 8 valid, in-range k-mers, and room for 8 candidates
                 const uint32_t ce = (wi & 0x0F0F0F0Fu) * 8u + (wo & 0x0F0F0F0Fu);
                 const uint32_t co = ((wi >> 4) & 0x0F0F0F0Fu) * 8u + ((wo >> 4) & 0x0F0F0F0Fu);
                 const uint32_t pos0 = p0 + (uint32_t)(t - lead);
@@ -270,7 +277,7 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
                     roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
                     const uint64_t fh = ((uint64_t)h.fhi << 32) | h.flo, rh = ((uint64_t)h.rhi << 32) | h.rlo;
                     const uint64_t h0 = fh + rh;
-                    if ((uint32_t)(h0 >> 32) < tau_hi) emit(h0, pos0 + j, fh <= rh, nv + j);
+                    if ((uint32_t)(h0 >> 32) < tau_hi) emit.fast(h0, pos0 + j, fh <= rh, nv + j);
                 }
                 nv += 8;
             } else {
@@ -302,9 +309,9 @@ __global__ void __launch_bounds__(128) k_dense(const uint32_t* __restrict__ pack
     const uint32_t np = seq_npos(seq_off[q + 1] - gseq, P.k, P.w);
     const uint32_t p0 = (s - strip_off[q]) * P.S;
     const uint32_t n = min(P.S, np - p0);
-    SlotEmit em{reinterpret_cast<uint4*>(slots + (uint64_t)s * P.cap), (int32_t)P.cap};
+    SlotEmit em{reinterpret_cast<uint4*>(slots + (uint64_t)s * P.cap), P.cap, 0u};
     const uint32_t nvalid = process_strip_dev(packed, gseq, p0, n, P.k, tbl_s, (threadIdx.x & 15u) << 4, P.tau_hi, em);
-    const uint32_t count = (uint32_t)((int32_t)P.cap - em.room);
+    const uint32_t count = em.count;
     cnt[s] = count;
     nv[s] = nvalid;
     if (count) has_cand[q] = 1;
