@@ -195,29 +195,31 @@ def build_index_distributed(ctx, contigs, rank, world, dist, torch):
                                               cl.ctypes.data, rk.ctypes.data, n), "ntl_index_build_device")
 
 
-_event_gather = None
+_gather_buf = {}
 
 
 def gather_events(ctx, rank, world, dist, torch):
-    "pair events of every rank -> rank 0's device event log, in rank order = global read order (one NCCL all_gather)"
+    """pair events of every rank -> rank 0's device event log, in rank order = global read order: the library writes
+    {count, events} into a fixed-capacity device buffer, ONE NCCL all_gather moves them, rank 0 imports the result."""
     import ctypes as C
-    from ntlink_b200 import dist as nd
-    global _event_gather
-    if _event_gather is None:
-        _event_gather = nd.EventGather()
-    n, dptr = C.c_uint64(), C.c_void_p()
-    ctx._check(ctx.lib.ntl_events_device(ctx.h, C.byref(n), C.byref(dptr)), "events_device")
     dev = torch.device("cuda", torch.cuda.current_device())
-    mine = torch.empty((n.value, 6), device=dev, dtype=torch.int32)
-    if n.value:
-        ctx._check(ctx.lib.ntl_copy_device(ctx.h, mine.data_ptr(), dptr, n.value * 24), "copy")
-    torch.cuda.current_stream().synchronize()
-    parts = _event_gather.gather(mine, dist)
-    if rank == 0:
-        ctx.events_reset()
-        for p in parts:
-            if p.shape[0]:
-                ctx._check(ctx.lib.ntl_events_append_device(ctx.h, p.contiguous().data_ptr(), int(p.shape[0])), "append")
+    while True:
+        cap = _gather_buf.get("cap", 8192)
+        if _gather_buf.get("send") is None or _gather_buf["send"].shape[0] != (cap + 1) * 6:
+            _gather_buf["send"] = torch.zeros((cap + 1) * 6, device=dev, dtype=torch.int32)
+            _gather_buf["recv"] = torch.zeros(world * (cap + 1) * 6, device=dev, dtype=torch.int32)
+        n = C.c_uint64()
+        ctx._check(ctx.lib.ntl_events_export(ctx.h, _gather_buf["send"].data_ptr(), cap, C.byref(n)), "ntl_events_export")
+        dist.all_gather_into_tensor(_gather_buf["recv"], _gather_buf["send"])
+        counts = _gather_buf["recv"].view(world, -1)[:, 0].tolist()      # every rank sees every count: same decision
+        if max(counts) <= cap:
+            if rank == 0:
+                ovf = C.c_int(0)
+                ctx._check(ctx.lib.ntl_events_import_gathered(ctx.h, _gather_buf["recv"].data_ptr(), world, cap, C.byref(ovf)),
+                           "ntl_events_import_gathered")
+            return
+        _gather_buf["cap"] = int(max(counts)) * 2
+        _gather_buf["send"] = None
 
 
 def run_gpu(args, rank, world, local_rank):

@@ -165,6 +165,13 @@ int ntl_events_append(ntl_ctx* ctx, const ntl_event* events, uint64_t n);    /* 
 int ntl_events_count(ntl_ctx* ctx, uint64_t* n);
 int ntl_events_device(ntl_ctx* ctx, uint64_t* n, void** d_events);            /* device pointer for NCCL */
 int ntl_events_append_device(ntl_ctx* ctx, const void* d_events, uint64_t n);
+/* multi-GPU exchange of the event logs with ONE fixed-size collective (ntlink_b200/dist.py): export writes a header
+ * row {count,0,0,0,0,0} followed by at most cap_events events (rows of 6 int32 = ntl_event) into a caller-owned
+ * DEVICE buffer of (cap_events+1) rows; import_gathered appends the events of `world` such buffers laid out back to
+ * back (the all-gather result), in rank order = global read order. *overflow is set when some rank had more than
+ * cap_events events (nothing is imported then: grow the buffers and repeat). */
+int ntl_events_export(ntl_ctx* ctx, void* d_dst, uint64_t cap_events, uint64_t* n_out);
+int ntl_events_import_gathered(ntl_ctx* ctx, const void* d_src, uint32_t world, uint64_t cap_events, int* overflow);
 int ntl_pairs_finish(ntl_ctx* ctx, ntl_pairs_out* out);
 
 /* ---- host text emitters (byte-identical to the reference's files) -------------------------------

@@ -82,6 +82,8 @@ SIGNATURES = {
     "ntl_events_count": (C.c_int, [_VP, _U64P]),
     "ntl_events_device": (C.c_int, [_VP, _U64P, C.POINTER(_VP)]),
     "ntl_events_append_device": (C.c_int, [_VP, _VP, C.c_uint64]),
+    "ntl_events_export": (C.c_int, [_VP, _VP, C.c_uint64, _U64P]),
+    "ntl_events_import_gathered": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.POINTER(C.c_int)]),
     "ntl_pairs_finish": (C.c_int, [_VP, C.POINTER(PairsOut)]),
     "ntl_format_sketch_tsv": (C.c_int64, [C.POINTER(SketchOut), _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.POINTER(_VP)]),
     "ntl_format_verbose": (C.c_int64, [C.POINTER(MapOut), _VP, _VP, _VP, _VP, C.c_int, C.POINTER(_VP)]),

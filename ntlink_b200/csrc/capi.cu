@@ -521,6 +521,44 @@ int ntl_events_append_device(ntl_ctx* c, const void* d_events, uint64_t n) {
     return events_append_impl(c, d_events, n, cudaMemcpyDeviceToDevice);
 }
 
+int ntl_events_export(ntl_ctx* c, void* d_dst, uint64_t cap_events, uint64_t* n_out) {
+    if (!c || !d_dst) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    const uint64_t n = c->tl_n_events, m = std::min(n, cap_events);
+    NTL_CUDA(c, c->h_status.ensure(256));
+    uint32_t* hdr = c->h_status.as<uint32_t>() + 32;       // pinned scratch (second half of the status block)
+    hdr[0] = (uint32_t)n; hdr[1] = hdr[2] = hdr[3] = hdr[4] = hdr[5] = 0;
+    NTL_CUDA(c, cudaMemcpyAsync(d_dst, hdr, 24, cudaMemcpyHostToDevice, c->stream));
+    if (m) NTL_CUDA(c, cudaMemcpyAsync((char*)d_dst + 24, c->tl_events.p, m * sizeof(Event), cudaMemcpyDeviceToDevice, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_out) *n_out = n;
+    return NTL_OK;
+}
+
+int ntl_events_import_gathered(ntl_ctx* c, const void* d_src, uint32_t world, uint64_t cap_events, int* overflow) {
+    if (!c || !d_src || !world || !overflow) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    const size_t stride = (cap_events + 1) * sizeof(Event);
+    std::vector<uint32_t> cnt(world);
+    NTL_CUDA(c, cudaMemcpy2DAsync(cnt.data(), 4, d_src, stride, 4, world, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint64_t total = 0;
+    *overflow = 0;
+    for (uint32_t r = 0; r < world; r++) { if (cnt[r] > cap_events) *overflow = 1; total += cnt[r]; }
+    if (*overflow) return NTL_OK;
+    c->tl_n_events = 0;
+    const size_t need = (total + 1) * sizeof(Event);
+    if (need > c->tl_events.cap) NTL_CUDA(c, c->tl_events.ensure(need));
+    uint64_t o = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        if (cnt[r]) NTL_CUDA(c, cudaMemcpyAsync(c->tl_events.as<Event>() + o, (const char*)d_src + r * stride + sizeof(Event),
+                                               (size_t)cnt[r] * sizeof(Event), cudaMemcpyDeviceToDevice, c->stream));
+        o += cnt[r];
+    }
+    c->tl_n_events = total;
+    return NTL_OK;
+}
+
 int ntl_pairs_finish(ntl_ctx* c, ntl_pairs_out* out) {
     if (!c || !out) return NTL_ERR_ARG;
     Results* R = res_of(c);
