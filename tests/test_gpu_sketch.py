@@ -149,3 +149,23 @@ def test_indexlr_cli_drop_in(tmp_path):
     out = subprocess.check_output([sys.executable, "-m", "ntlink_b200.indexlr", "--long", "--pos", "-k", "15", "-w", "5",
                                    tgt], env=env, cwd=util.REPO)
     assert out == util.oracle_indexlr(tgt, 15, 5, strand=False)
+
+
+def test_btllib_shaped_iterator(ctx, tmp_path):
+    "btllib.Indexlr / SeqReader shapes used by ntlink_patch_gaps.py (k20 w10) on top of the GPU sketcher"
+    from ntlink_b200 import btllib_shim as btllib
+    path = util.fixture_file(tmp_path, "long_reads_4_top5.fa")
+    names, seq, offs = util.load_fasta_batch(path)
+    oh, op, os_, oo = util.oracle_sketch_batch(seq, offs, 20, 10)
+    with btllib.Indexlr(path, 20, 10, btllib.IndexlrFlag.LONG_MODE, 4, ctx=ctx) as idx:
+        recs = list(idx)
+    assert [r.id for r in recs] == names and [r.readlen for r in recs] == np.diff(offs).astype(int).tolist()
+    for i, r in enumerate(recs):
+        a, b = int(oo[i]), int(oo[i + 1])
+        assert [m.out_hash for m in r.minimizers] == oh[a:b].tolist()
+        assert [m.pos for m in r.minimizers] == op[a:b].tolist()
+        assert [m.forward for m in r.minimizers] == [bool(x) for x in os_[a:b]]
+    with btllib.SeqReader(path, btllib.SeqReaderFlag.LONG_MODE) as rd:
+        got = [(r.id, r.seq) for r in rd]
+    raw = seq.tobytes().decode()
+    assert got == [(n, raw[int(offs[i]):int(offs[i + 1])]) for i, n in enumerate(names)]
