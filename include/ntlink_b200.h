@@ -142,6 +142,15 @@ int ntl_map_sketch(ntl_ctx* ctx, const uint64_t* hash, const uint32_t* pos_stran
                    const uint32_t* read_len, uint32_t nreads, uint64_t first_read_ordinal,
                    const ntl_params* prm, ntl_map_out* out);
 
+/* Checkpoint path: the pair events of reads whose accepted runs/hits are already known (parsed from a
+ * verbose_mapping.tsv). Replaces NtLink.find_scaffold_pairs_checkpoints / parse_verbose_entries
+ * (bin/ntlink_pair.py:437-488): arrays in the layout of ntl_map_out, read_len[r] = the reference's substitute read
+ * length (largest first/last read position of the read's runs, :487). Needs the contig lengths / name ranks of an
+ * index (ntl_index_build with n = 0 is enough). Events are appended to the ctx's event log. */
+int ntl_tally_mappings(ntl_ctx* ctx, const uint32_t* hit_off, const uint32_t* nruns, const ntl_run* runs, const ntl_hit* hits,
+                       const uint32_t* read_len, uint32_t nreads, uint64_t first_read_ordinal, const ntl_params* prm,
+                       uint64_t* n_events_out);
+
 /* ---- pair tally ---------------------------------------------------------------------------------
  * Replaces the `pairs` accumulator of find_scaffold_pairs (bin/ntlink_pair.py:327-332): per normalised pair the
  * gap estimates in read order, the anchor count, and the order in which pairs were first seen. */

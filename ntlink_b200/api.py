@@ -283,6 +283,22 @@ class Context:
                                             C.byref(prm), C.byref(mo)), "ntl_map_sketch")
         return MapResult(mo)
 
+    def tally_mappings(self, hit_off, nruns, runs, hits, read_len, prm, first_ordinal=0):
+        """Checkpoint path (bin/ntlink_pair.py:437-488): pair events of reads whose accepted runs/hits are known.
+        runs: (n,3) uint32 {ctg,start,count}; hits: (n,3) uint32 {ctg,ctg_pos_strand,read_pos_strand}; layout as in MapResult.
+        Returns the number of events appended to the event log."""
+        ho = np.ascontiguousarray(hit_off, np.uint32)
+        nr = np.ascontiguousarray(nruns, np.uint32)
+        ru = np.ascontiguousarray(runs, np.uint32).reshape(-1, 3)
+        hi = np.ascontiguousarray(hits, np.uint32).reshape(-1, 3)
+        rl = np.ascontiguousarray(read_len, np.uint32)
+        if len(ho) != len(nr) + 1 or len(rl) != len(nr) or len(ru) < int(ho[-1]) or len(hi) < int(ho[-1]):
+            raise ValueError("tally_mappings: inconsistent array sizes")
+        ne = C.c_uint64()
+        self._check(self.lib.ntl_tally_mappings(self.h, _ptr(ho), _ptr(nr), _ptr(ru), _ptr(hi), _ptr(rl), len(nr), first_ordinal,
+                                                C.byref(prm), C.byref(ne)), "ntl_tally_mappings")
+        return ne.value
+
     # ---- pairs
     def events_reset(self):
         self._check(self.lib.ntl_events_reset(self.h), "ntl_events_reset")

@@ -10,7 +10,7 @@
 namespace ntl {
 int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids);
 int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, uint32_t nreads, uint64_t first_ordinal,
-               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out);
+               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out, const PreMappings* pre = nullptr);
 int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>& gaps);
 int read_len_device(ntl_ctx* c, const uint64_t* d_off, uint32_t nreads, DevBuf& out);
 
@@ -482,6 +482,25 @@ int ntl_map_sketch(ntl_ctx* c, const uint64_t* hash, const uint32_t* pos_strand,
         b = e;
     }
     fill_map_out(c, out, nreads, mx_off[nreads] - mx_off[0], hits_total, runs_total, ev_total);
+    return NTL_OK;
+}
+
+int ntl_tally_mappings(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const ntl_run* runs, const ntl_hit* hits,
+                       const uint32_t* read_len, uint32_t nreads, uint64_t first_read_ordinal, const ntl_params* prm,
+                       uint64_t* n_events_out) {
+    if (!c || !hit_off || !nruns || !read_len || !prm || prm->k <= 0) { if (c) c->err = "ntl_tally_mappings: bad argument"; return NTL_ERR_ARG; }
+    if (!c->index.built) { c->err = "ntl_tally_mappings: contig lengths / name ranks missing (build or load an index first)"; return NTL_ERR_STATE; }
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    const uint32_t nh = nreads ? hit_off[nreads] : 0;
+    if (nh && (!runs || !hits)) { c->err = "ntl_tally_mappings: bad argument"; return NTL_ERR_ARG; }
+    NTL_CUDA(c, R->read_len.ensure(((size_t)nreads + 1) * 4));
+    if (nreads) NTL_CUDA(c, cudaMemcpyAsync(R->read_len.p, read_len, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
+    PreMappings pre{hit_off, nruns, reinterpret_cast<const Run*>(runs), reinterpret_cast<const Hit*>(hits), nh};
+    MapStatus cs; uint64_t log_base = 0;
+    NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), nreads, first_read_ordinal, prm, &cs, &log_base, &pre));
+    NTL_TRY(finish_call(c));
+    if (n_events_out) *n_events_out = cs.n_events;
     return NTL_OK;
 }
 

@@ -67,7 +67,7 @@ struct MapStatus {
     uint32_t n_runs;        // accepted (read, contig) runs
     uint32_t pad[12];
 };
-enum : uint32_t { MAPERR_EVENTS = 1 };
+enum : uint32_t { MAPERR_EVENTS = 1, MAPERR_ASSERT = 2 };
 
 // per-stage device timings (CUDA events on ctx->stream), milliseconds; stage ids are NTL_T_* of the public header
 enum { T_PACK = NTL_T_PACK, T_DENSE = NTL_T_DENSE, T_SELECT = NTL_T_SELECT, T_GAP = NTL_T_GAP, T_EMIT = NTL_T_EMIT,
@@ -94,6 +94,10 @@ struct TargetIndex {
     uint32_t ncontig = 0;
     uint64_t n_inserted = 0;
     bool built = false;
+};
+
+struct PreMappings {          // accepted runs/hits supplied by the host (checkpoint path), ntl_map_out layout
+    const uint32_t* hit_off; const uint32_t* nruns; const Run* runs; const Hit* hits; uint32_t n_hits;
 };
 
 struct TallyWork {

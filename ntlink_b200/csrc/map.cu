@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(128) k_events(const Hit* __restrict__ hits, co
         else {
             const uint32_t o = hit_off[r];
             ne = tally_read(hits + o, runs + o, nr, read_len[r], first_ordinal + r, ctg_len, name_rank, P, events + eo);
+            for (uint32_t i = 0; i < ne; i++) if (events[eo + i].flags & 8u) atomicOr(&st->err, MAPERR_ASSERT);
         }
     }
     ev_cnt[r] = ne;
@@ -221,6 +222,17 @@ __global__ void k_pairs_compact(const unsigned long long* __restrict__ keys, con
 
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
 
+// checkpoint path: event capacity per read from the uploaded run counts
+__global__ void k_evmax(const uint32_t* __restrict__ nruns, uint32_t nreads, int32_t f, uint32_t* __restrict__ evmax,
+                        MapStatus* __restrict__ st, uint32_t* __restrict__ nreads_dev, uint32_t n_hits) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) { *nreads_dev = nreads; st->n_hits = n_hits; }
+    if (r >= nreads) return;
+    const uint32_t nr = nruns[r];
+    evmax[r] = max_events(nr, f);
+    if (nr) atomicAdd(&st->n_runs, nr);
+}
+
 // counters -> pinned (UVA-mapped) host memory without using a copy engine
 __global__ void k_publish_map(const MapStatus* __restrict__ st, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
                               uint32_t* __restrict__ host) {
@@ -289,11 +301,13 @@ int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids) {
 
 // Lookup + chain + events for the reads whose sketch is `sk` (device). d_read_len: device read lengths.
 // Results are left in c->mw (hits, runs, nruns, hit_off, events log segment); the counters are returned.
+// With `pre` set the lookup and chaining are skipped: the accepted runs/hits come from the host (checkpoint path,
+// bin/ntlink_pair.py:437-488) and only the pair events are computed.
 int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, uint32_t nreads, uint64_t first_ordinal,
-               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out) {
+               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out, const PreMappings* pre) {
     if (!c->index.built) { c->err = "map: no target index (call ntl_index_build first)"; return NTL_ERR_STATE; }
     MapWork& M = c->mw;
-    const uint32_t n = sk.n_mx;
+    const uint32_t n = pre ? pre->n_hits : sk.n_mx;
     MapParams P;
     P.k = prm->k; P.z = prm->z; P.f = prm->f; P.x = prm->x; P.x_is_zero = (prm->x == 0.0);
     P.sensitive = prm->sensitive; P.repeat_filter = prm->repeat_filter;
@@ -319,6 +333,19 @@ int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, u
     int attempt = 0;
 
     NTL_CUDA(c, cudaMemsetAsync(st, 0, sizeof(MapStatus) + 64, c->stream));
+    if (pre) {
+        NTL_CUDA(c, cudaMemcpyAsync(M.hit_off.p, pre->hit_off, ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+        NTL_CUDA(c, cudaMemcpyAsync(M.nruns.p, pre->nruns, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
+        if (n) {
+            NTL_CUDA(c, cudaMemcpyAsync(M.runs.p, pre->runs, (size_t)n * sizeof(Run), cudaMemcpyHostToDevice, c->stream));
+            NTL_CUDA(c, cudaMemcpyAsync(M.hits.p, pre->hits, (size_t)n * sizeof(Hit), cudaMemcpyHostToDevice, c->stream));
+        }
+        tick(c, T_CHAIN);
+        k_evmax<<<div_up(std::max<uint32_t>(nreads, 1), 256), 256, 0, c->stream>>>(M.nruns.as<uint32_t>(), nreads, P.f, evmax, st, nreads_dev, n);
+        c->launches++;
+        goto events_stage;
+    }
+    {
     IndexView ix{c->index.table.as<IdxEntry>(), c->index.slots - 1, c->index.special.as<IdxSpecial>()};
     tick(c, T_LOOKUP);
     k_lookup<<<div_up(std::max<uint32_t>(n, 1), 256), 256, 0, c->stream>>>(sk.hash.as<uint64_t>(), sk.posf.as<uint32_t>(), n, ix,
@@ -342,6 +369,8 @@ int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, u
                                                           c->index.ctg_len.as<uint32_t>(), P, M.nruns.as<uint32_t>(), evmax, st);
         c->launches++;
     }
+    }
+events_stage:
     NTL_TRY(exclusive_scan_u32(c, evmax, ev_off, nreads_dev, nreads, M.blocksums));
 retry_events:
     NTL_CUDA(c, M.events.ensure((size_t)ev_cap * sizeof(Event)));
@@ -360,6 +389,10 @@ retry_events:
     MapStatus hs = *c->h_status.as<MapStatus>();
     const uint32_t n_events = nreads ? *(uint32_t*)(c->h_status.as<char>() + 64) : 0;
     const uint32_t ev_need = nreads ? *(uint32_t*)(c->h_status.as<char>() + 68) : 0;
+    if (hs.err & MAPERR_ASSERT) {
+        c->err = "an assertion of the reference would fail (bin/ntlink_pair.py:225 / :173-184): minimizer order or overhang";
+        return NTL_ERR_ASSERT;
+    }
     if (hs.err & MAPERR_EVENTS) {
         if (++attempt > 2) { c->err = "map: event buffer exhausted"; return NTL_ERR_WORKSPACE; }
         ev_cap = ev_need + 1024;

@@ -235,6 +235,10 @@ NTL_HD bool make_event(const Hit* hits, const Run& ri, const Run& rj, uint32_t r
     }
     ev.gap = (int32_t)gap;
     if (ri.count > 1 && rj.count > 1) ev.flags |= 4u;
+    // the reference asserts mx_i_pos < mx_j_pos (pair:225) and a, b >= 0 (pair:173-184); this cannot fail for
+    // mappings produced by the chaining above, but a hand-made / lifted-over checkpoint file can violate it. Such an
+    // event is flagged (bit 3) and always written so that the caller can abort like the reference does.
+    if (!(pos_of(ti.rposf) < pos_of(fj.rposf)) || a < 0 || b < 0) { ev.flags |= 8u; return true; }
     const int64_t ag = gap < 0 ? -gap : gap;
     return ag <= (int64_t)read_len;
 }
@@ -276,7 +280,7 @@ NTL_HD uint32_t tally_read(const Hit* hits, const Run* runs, uint32_t nr, uint32
                 bool dup = false;                                  // check_added (pair:324-325)
                 for (uint32_t q = 0; q < n_adj; q++)
                     if (out[q].src == ev.src && out[q].tgt == ev.tgt && ((out[q].flags ^ ev.flags) & 3u) == 0) { dup = true; break; }
-                if (!dup) { ev.read = read_ord; ev.ord = ne; out[ne++] = ev; }
+                if (!dup || (ev.flags & 8u)) { ev.read = read_ord; ev.ord = ne; out[ne++] = ev; }
             }
         }
         prev = i;

@@ -126,6 +126,53 @@ def parse_sketch_tsv(lines, with_len):
             np.array(posf, np.uint32), np.array(off, np.uint64))
 
 
+def parse_verbose_mappings(lines, contig_index):
+    """verbose_mapping.tsv -> the arrays of Context.tally_mappings, following parse_verbose_entries (pair:466-488):
+    one run per line, hit_count = number of listed hits (the num_hits column is not used), 'read length' = the largest
+    first/last read position over the read's runs, reads = maximal blocks of consecutive lines with the same read id.
+    A contig listed twice within a read refers both times to its LAST listing (the reference keeps one dict entry)."""
+    hit_off, nruns, read_len, runs, hits = [0], [], [], [], []
+    cur, group = None, []
+
+    def flush():
+        if not group:
+            return
+        base = hit_off[-1]
+        last = {}
+        local = []
+        for ctg, toks in group:
+            start = len(hits) - base
+            for tok in toks:
+                c, r = tok.split("_")
+                cp, cs = c.split(":")
+                rp, rs = r.split(":")
+                hits.append((ctg, int(cp) | (0x80000000 if cs == "+" else 0), int(rp) | (0x80000000 if rs == "+" else 0)))
+            last[ctg] = (ctg, start, len(toks))
+            local.append(ctg)
+        positions = []
+        for ctg in local:
+            run = last[ctg]
+            runs.append(run)
+            positions += [hits[base + run[1]][2] & 0x7FFFFFFF, hits[base + run[1] + run[2] - 1][2] & 0x7FFFFFFF]
+        # holey layout: the read's region holds max(#hits, #runs) slots in both arrays
+        width = max(len(hits) - base, len(local))
+        hits.extend([(0, 0, 0)] * (base + width - len(hits)))
+        runs.extend([(0, 0, 0)] * (base + width - len(runs)))
+        nruns.append(len(local))
+        read_len.append(max(positions))
+        hit_off.append(base + width)
+
+    for line in lines:
+        read_id, contig_id, _, mx_hits = line.strip().split("\t")
+        if read_id != cur:
+            flush()
+            cur, group = read_id, []
+        group.append((contig_index[contig_id], mx_hits.split(" ")))
+    flush()
+    return (np.array(hit_off, np.uint32), np.array(nruns, np.uint32), np.array(runs, np.uint32).reshape(-1, 3),
+            np.array(hits, np.uint32).reshape(-1, 3), np.array(read_len, np.uint32))
+
+
 def parse_arguments(argv=None):
     "same options as bin/ntlink_pair.py:508-536, plus the fused-path options"
     p = argparse.ArgumentParser(description="ntLink pairing stage on a B200 (drop-in for ntlink_pair.py)")
@@ -139,7 +186,7 @@ def parse_arguments(argv=None):
     p.add_argument("-a", help="Minimum number of anchoring long reads for an edge", type=int, default=1)
     p.add_argument("-f", help="Maximum number of contigs in a run for full transitive edge addition", default=10, type=int)
     p.add_argument("-x", help="Fudge factor allowed between mapping block lengths on read and assembly", type=float, default=0)
-    p.add_argument("-c", "--checkpoint", help="Mappings checkpoint file (not supported by the GPU path)", required=False)
+    p.add_argument("-c", "--checkpoint", help="Mappings checkpoint file", required=False)
     p.add_argument("--pairs", help="Output pairs TSV file", action="store_true")
     p.add_argument("--paf", help="Output mappings in PAF-like format", action="store_true")
     p.add_argument("--sensitive", help="Run more sensitive read mapping", action="store_true")
@@ -221,6 +268,40 @@ class NtLink:
                 pf.close()
         return pairs_dict(self.ctx.pairs(), self.contigs.names)
 
+    def find_scaffold_pairs_checkpoints(self, chunk_lines=2_000_000):
+        """replaces pair:437-464: re-tally the pairs from the checkpoint verbose_mapping.tsv; the accepted runs go to
+        the GPU in chunks cut at read boundaries and only the pair events are computed there"""
+        a = self.args
+        print(datetime.datetime.today(), ": Finding pairs", file=sys.stdout)
+        self.contigs = api.read_sequences(a.s)
+        self.lengths = {n: int(l) for n, l in zip(self.contigs.names, self.contigs.lengths)}
+        # lengths and name ranks only: the checkpoint path never touches the target minimizers (pair:571-575)
+        none = np.empty(0, np.uint32)
+        self.ctx.build_index(np.empty(0, np.uint64), none, none, self.contigs.lengths.astype(np.uint32), self.contigs.names)
+        idx = {n: i for i, n in enumerate(self.contigs.names)}
+        prm = self.ctx.params(a.k, a.w or 1, a.z, a.f, a.x, a.sensitive, a.repeat_filter)
+        self.ctx.events_reset()
+        ordinal = 0
+
+        def submit(lines):
+            nonlocal ordinal
+            if lines:
+                arrays = parse_verbose_mappings(lines, idx)
+                self.ctx.tally_mappings(*arrays, prm, ordinal)
+                ordinal += len(arrays[1])
+
+        with open(a.checkpoint) as fin:
+            pending, last_id = [], None
+            for line in fin:
+                read_id = line.split("\t", 1)[0]
+                if len(pending) >= chunk_lines and read_id != last_id:
+                    submit(pending)
+                    pending = []
+                pending.append(line)
+                last_id = read_id
+            submit(pending)
+        return pairs_dict(self.ctx.pairs(), self.contigs.names)
+
     def _emit(self, res, reads, read_len, vf, pf):
         if vf is not None:
             vf.write(res.verbose_bytes(reads, self.contigs, threads=self.args.t))
@@ -231,13 +312,16 @@ class NtLink:
         a = self.args
         print("Running pairing stage of ntLink ...\n")
         try:
-            if a.checkpoint or os.path.isfile(a.p + ".verbose_mapping.tsv"):
-                # the reference re-tallies from the checkpoint file (pair:565-575) and never reads the sketches;
-                # that path is O(file) Python and not part of the GPU hot path
-                raise NtlinkPairError("checkpoint file found: run the reference ntlink_pair.py for the checkpoint path, "
-                                      "or remove " + a.p + ".verbose_mapping.tsv")
-            self.read_minimizers()
-            pairs = self.find_scaffold_pairs()
+            if os.path.isfile(a.p + ".verbose_mapping.tsv"):       # pair:565-566
+                a.checkpoint = a.p + ".verbose_mapping.tsv"
+            if a.checkpoint:
+                print("Found checkpoint file, bypassing read mapping...\n")
+                if a.paf:
+                    print("Warning: --paf specified, but not compatible with checkpoint")
+                pairs = self.find_scaffold_pairs_checkpoints()
+            else:
+                self.read_minimizers()
+                pairs = self.find_scaffold_pairs()
             pairs = filter_pairs_distances(pairs, self.lengths)
             pairs = filter_weak_anchor_pairs(pairs, a.a)
             if a.pairs:

@@ -409,6 +409,39 @@ def map_reads(read_tsv_lines, index, lengths, prm, verbose_out=None, paf_out=Non
     return pairs
 
 
+def retally_from_verbose(verbose_lines, lengths, prm):
+    """Checkpoint path (bin/ntlink_pair.py:437-488): re-tally the pairs from a verbose_mapping.tsv. Quirks kept:
+    hit_count is the number of parsed hits, the 'read length' is the largest first/last read position of the read's
+    runs (:487), a contig listed twice keeps only its last run (:467)."""
+    pairs = {}
+
+    def flush(group):
+        if not group:
+            return
+        order, by_ctg, positions = [], {}, []
+        for ctg, hits_str in group:
+            hits = []
+            for tok in hits_str.split(" "):
+                c, r = tok.split("_")
+                cp, cs = c.split(":")
+                rp, rs = r.split(":")
+                hits.append(Hit(None, int(cp), cs, int(rp), rs))
+            order.append(ctg)
+            by_ctg[ctg] = hits
+            positions += [hits[0].read_pos, hits[-1].read_pos]
+        tally([(c, by_ctg[c]) for c in order], max(positions), pairs, lengths, prm)
+
+    cur, group = None, []
+    for line in verbose_lines:
+        read_id, ctg, _, hits_str = line.strip().split("\t")
+        if read_id != cur:
+            flush(group)
+            cur, group = read_id, []
+        group.append((ctg, hits_str))
+    flush(group)
+    return pairs
+
+
 def run(files, target_fasta, target_tsv, prefix, prm, verbose=False, pairs_out=False, paf=False):
     "NtLink.main without the checkpoint path (pair:560-607)"
     with (sys.stdin if target_tsv == "-" else open(target_tsv)) as fin:

@@ -131,6 +131,10 @@ CASES = {
 }
 
 
+CHECKPOINT_CASES = {"f1_default", "f2_default", "f3_default", "f4_default", "f3_sensitive", "f3_f1", "f2_f1_a3", "f3_a2_n2",
+                    "f3k20w10_default"}
+
+
 def gz_copy(src, dst):
     data = gzip.open(src, "rb").read() if src.endswith(".gz") else open(src, "rb").read()
     with gzip.GzipFile(dst, "wb", mtime=0) as fout:
@@ -197,8 +201,16 @@ def main():
         for suffix, dst in [(".verbose_mapping.tsv", "verbose_mapping.tsv"), (".paf", "paf"),
                             (".pairs.tsv", "pairs.tsv"), (f".n{opt['n']}.scaffold.dot", "scaffold.dot")]:
             gz_write(os.path.join(out_dir, dst + ".gz"), open(prefix + suffix, "rb").read())
+        # checkpoint path (bin/ntlink_pair.py:565-575,437-488): a second run finds <prefix>.verbose_mapping.tsv and
+        # re-tallies the pairs from it without reading the sketches
+        if case in CHECKPOINT_CASES:
+            for suffix in (".pairs.tsv", f".n{opt['n']}.scaffold.dot"):
+                os.remove(prefix + suffix)
+            subprocess.check_call(cmd, env=env, stdout=subprocess.DEVNULL)
+            for suffix, dst in [(".pairs.tsv", "checkpoint.pairs.tsv"), (f".n{opt['n']}.scaffold.dot", "checkpoint.scaffold.dot")]:
+                gz_write(os.path.join(out_dir, dst + ".gz"), open(prefix + suffix, "rb").read())
         manifest[case] = {"fixture": fx, "target": FIXTURES[fx][0], "reads": FIXTURES[fx][1].replace(".gz", ""),
-                          "k": k, "w": w, **opt}
+                          "k": k, "w": w, "checkpoint": case in CHECKPOINT_CASES, **opt}
         print("golden", case, "ok")
     with open(os.path.join(HERE, "manifest.json"), "w") as fout:
         json.dump(manifest, fout, indent=1, sort_keys=True)
