@@ -308,11 +308,13 @@ def run_gpu(args, rank, world, local_rank):
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     barrier()
+    ctx.timing_reset()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     barrier()
     t_e2e = time.perf_counter() - t0
+    tm_e2e = ctx.timing()
     clocks = sampler.summary()
 
     # ---------------- max over ranks
@@ -351,7 +353,9 @@ def run_gpu(args, rank, world, local_rank):
                                             "small target sketched on every GPU")) if world > 1 else "n/a"},
                 "e2e": {"value": e2e, "unit": "Gbp/s",
                         "h2d_bytes_per_step": int(len(pc.seq) + len(pr.seq) + 8 * (len(pc) + len(pr) + 2)),
-                        "d2h_bytes_per_step": int(d2h.get("bytes", 0)), "ms_per_step": 1e3 * t_e2e / args.steps},
+                        "d2h_bytes_per_step": int(d2h.get("bytes", 0)), "ms_per_step": 1e3 * t_e2e / args.steps,
+                        "kernel_stage_ms_per_step": {k: round(tm_e2e[k] / args.steps, 4) for k in
+                                                     ("pack", "dense", "select", "gap", "emit", "lookup", "chain", "tally", "index")}},
                 "gpu_launches": int(tm["launches"]),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "k_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",

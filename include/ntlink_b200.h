@@ -146,10 +146,31 @@ int ntl_map_sketch(ntl_ctx* ctx, const uint64_t* hash, const uint32_t* pos_stran
  * verbose_mapping.tsv). Replaces NtLink.find_scaffold_pairs_checkpoints / parse_verbose_entries
  * (bin/ntlink_pair.py:437-488): arrays in the layout of ntl_map_out, read_len[r] = the reference's substitute read
  * length (largest first/last read position of the read's runs, :487). Needs the contig lengths / name ranks of an
- * index (ntl_index_build with n = 0 is enough). Events are appended to the ctx's event log. */
+ * index (ntl_index_build with n = 0 is enough). Events are appended to the ctx's event log. read_len = NULL: the
+ * substitute read length is computed on the device. hit_off = NULL: use the mappings ntl_liftover_mappings left on
+ * the device (nreads must match). */
 int ntl_tally_mappings(ntl_ctx* ctx, const uint32_t* hit_off, const uint32_t* nruns, const ntl_run* runs, const ntl_hit* hits,
                        const uint32_t* read_len, uint32_t nreads, uint64_t first_read_ordinal, const ntl_params* prm,
                        uint64_t* n_events_out);
+
+/* Mapping liftover between rounds. Replaces bin/ntlink_liftover_mappings.py (liftover_ctg_mappings :61-88 and
+ * print_adjusted_mappings :90-124; called from ntLink_rounds:122-125): the accepted runs of every read are rewritten
+ * from contig coordinates to the coordinates of the scaffolds they were joined into. One ntl_agp_row per contig id of
+ * the input mappings (built from the AGP by the caller, read_agp :40-50). Output in the ntl_map_out layout with the
+ * same hit_off as the input (regions keep their size, unused slots are holes), contig ids in the new namespace; `out`
+ * may be NULL. The lifted arrays also stay on the device: ntl_tally_mappings with hit_off = NULL tallies them without
+ * another transfer (build the index of the new namespace in between; read_len = NULL selects the checkpoint read length). */
+typedef struct ntl_agp_row {
+    uint32_t new_id;      /* id of the path, or of the contig's own name if it has no AGP entry, in the new namespace */
+    uint32_t flags;       /* NTL_AGP_* */
+    uint32_t scaf_start;  /* AGP column 2 (1-based) */
+    uint32_t ctg_start;   /* AGP column 7 (1-based) */
+    uint32_t ctg_end;     /* AGP column 8 (1-based) */
+} ntl_agp_row;
+enum { NTL_AGP_IN = 1 /* has an entry */, NTL_AGP_MINUS = 2 /* orientation '-' */,
+       NTL_AGP_KEEP = 4 /* path id == contig id, or orientation not +/-: hits pass through untouched (:84-85) */ };
+int ntl_liftover_mappings(ntl_ctx* ctx, const uint32_t* hit_off, const uint32_t* nruns, const ntl_run* runs, const ntl_hit* hits,
+                          uint32_t nreads, const ntl_agp_row* agp, uint32_t ncontig, int k, ntl_map_out* out);
 
 /* ---- pair tally ---------------------------------------------------------------------------------
  * Replaces the `pairs` accumulator of find_scaffold_pairs (bin/ntlink_pair.py:327-332): per normalised pair the

@@ -283,6 +283,29 @@ class Context:
                                             C.byref(prm), C.byref(mo)), "ntl_map_sketch")
         return MapResult(mo)
 
+    def liftover_mappings(self, hit_off, nruns, runs, hits, agp_rows, k, want_result=True):
+        """bin/ntlink_liftover_mappings.py:61-124 on the GPU. agp_rows: (ncontig, 5) uint32 {new_id, flags, scaf_start,
+        ctg_start, ctg_end} (see liftover.agp_table). Returns a MapResult in the new contig namespace (or None); the
+        lifted arrays also stay on the device for tally_lifted()."""
+        ho = np.ascontiguousarray(hit_off, np.uint32)
+        nr = np.ascontiguousarray(nruns, np.uint32)
+        ru = np.ascontiguousarray(runs, np.uint32).reshape(-1, 3)
+        hi = np.ascontiguousarray(hits, np.uint32).reshape(-1, 3)
+        ag = np.ascontiguousarray(agp_rows, np.uint32).reshape(-1, 5)
+        if len(ho) != len(nr) + 1 or len(ru) < int(ho[-1]) or len(hi) < int(ho[-1]):
+            raise ValueError("liftover_mappings: inconsistent array sizes")
+        mo = _lib.MapOut()
+        self._check(self.lib.ntl_liftover_mappings(self.h, _ptr(ho), _ptr(nr), _ptr(ru), _ptr(hi), len(nr), _ptr(ag), len(ag), k,
+                                                   C.byref(mo) if want_result else None), "ntl_liftover_mappings")
+        return MapResult(mo) if want_result else None
+
+    def tally_lifted(self, nreads, prm, first_ordinal=0):
+        "pair events of the mappings the last liftover_mappings() left on the device (checkpoint read length, pair:483-487)"
+        ne = C.c_uint64()
+        self._check(self.lib.ntl_tally_mappings(self.h, None, None, None, None, None, nreads, first_ordinal, C.byref(prm),
+                                                C.byref(ne)), "ntl_tally_mappings")
+        return ne.value
+
     def tally_mappings(self, hit_off, nruns, runs, hits, read_len, prm, first_ordinal=0):
         """Checkpoint path (bin/ntlink_pair.py:437-488): pair events of reads whose accepted runs/hits are known.
         runs: (n,3) uint32 {ctg,start,count}; hits: (n,3) uint32 {ctg,ctg_pos_strand,read_pos_strand}; layout as in MapResult.
@@ -291,11 +314,12 @@ class Context:
         nr = np.ascontiguousarray(nruns, np.uint32)
         ru = np.ascontiguousarray(runs, np.uint32).reshape(-1, 3)
         hi = np.ascontiguousarray(hits, np.uint32).reshape(-1, 3)
-        rl = np.ascontiguousarray(read_len, np.uint32)
-        if len(ho) != len(nr) + 1 or len(rl) != len(nr) or len(ru) < int(ho[-1]) or len(hi) < int(ho[-1]):
+        rl = None if read_len is None else np.ascontiguousarray(read_len, np.uint32)
+        if len(ho) != len(nr) + 1 or (rl is not None and len(rl) != len(nr)) or len(ru) < int(ho[-1]) or len(hi) < int(ho[-1]):
             raise ValueError("tally_mappings: inconsistent array sizes")
         ne = C.c_uint64()
-        self._check(self.lib.ntl_tally_mappings(self.h, _ptr(ho), _ptr(nr), _ptr(ru), _ptr(hi), _ptr(rl), len(nr), first_ordinal,
+        self._check(self.lib.ntl_tally_mappings(self.h, _ptr(ho), _ptr(nr), _ptr(ru), _ptr(hi), None if rl is None else _ptr(rl),
+                                                len(nr), first_ordinal,
                                                 C.byref(prm), C.byref(ne)), "ntl_tally_mappings")
         return ne.value
 

@@ -6,11 +6,14 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "lift_logic.cuh"
 
 namespace ntl {
 int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids);
 int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, uint32_t nreads, uint64_t first_ordinal,
                const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out, const PreMappings* pre = nullptr);
+int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const Run* runs, const Hit* hits, uint32_t nreads,
+                    const AgpRow* agp, uint32_t ncontig, int32_t k, MapStatus* counts_out);
 int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>& gaps);
 int read_len_device(ntl_ctx* c, const uint64_t* d_off, uint32_t nreads, DevBuf& out);
 
@@ -488,20 +491,62 @@ int ntl_map_sketch(ntl_ctx* c, const uint64_t* hash, const uint32_t* pos_strand,
 int ntl_tally_mappings(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const ntl_run* runs, const ntl_hit* hits,
                        const uint32_t* read_len, uint32_t nreads, uint64_t first_read_ordinal, const ntl_params* prm,
                        uint64_t* n_events_out) {
-    if (!c || !hit_off || !nruns || !read_len || !prm || prm->k <= 0) { if (c) c->err = "ntl_tally_mappings: bad argument"; return NTL_ERR_ARG; }
+    if (!c || !prm || prm->k <= 0) { if (c) c->err = "ntl_tally_mappings: bad argument"; return NTL_ERR_ARG; }
     if (!c->index.built) { c->err = "ntl_tally_mappings: contig lengths / name ranks missing (build or load an index first)"; return NTL_ERR_STATE; }
     Results* R = res_of(c);
     cudaSetDevice(c->device);
-    const uint32_t nh = nreads ? hit_off[nreads] : 0;
-    if (nh && (!runs || !hits)) { c->err = "ntl_tally_mappings: bad argument"; return NTL_ERR_ARG; }
+    PreMappings pre{};
+    if (!hit_off) {                       // mappings left on the device by ntl_liftover_mappings
+        if (!c->mw.lifted_valid || c->mw.lifted_reads != nreads) { c->err = "ntl_tally_mappings: no lifted mappings of that size on the device"; return NTL_ERR_STATE; }
+        pre.resident = true; pre.n_hits = c->mw.lifted_hits;
+    } else {
+        if (!nruns) { c->err = "ntl_tally_mappings: bad argument"; return NTL_ERR_ARG; }
+        const uint32_t nh = nreads ? hit_off[nreads] : 0;
+        if (nh && (!runs || !hits)) { c->err = "ntl_tally_mappings: bad argument"; return NTL_ERR_ARG; }
+        pre.hit_off = hit_off; pre.nruns = nruns; pre.runs = reinterpret_cast<const Run*>(runs);
+        pre.hits = reinterpret_cast<const Hit*>(hits); pre.n_hits = nh;
+    }
+    c->mw.lifted_valid = false;
+    pre.compute_read_len = (read_len == nullptr);
     NTL_CUDA(c, R->read_len.ensure(((size_t)nreads + 1) * 4));
-    if (nreads) NTL_CUDA(c, cudaMemcpyAsync(R->read_len.p, read_len, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
-    PreMappings pre{hit_off, nruns, reinterpret_cast<const Run*>(runs), reinterpret_cast<const Hit*>(hits), nh};
+    if (nreads && read_len) NTL_CUDA(c, cudaMemcpyAsync(R->read_len.p, read_len, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
     MapStatus cs; uint64_t log_base = 0;
     NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), nreads, first_read_ordinal, prm, &cs, &log_base, &pre));
     NTL_TRY(finish_call(c));
     if (n_events_out) *n_events_out = cs.n_events;
     return NTL_OK;
+}
+
+int ntl_liftover_mappings(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const ntl_run* runs, const ntl_hit* hits,
+                          uint32_t nreads, const ntl_agp_row* agp, uint32_t ncontig, int k, ntl_map_out* out) {
+    if (!c || !hit_off || (nreads && !nruns) || (ncontig && !agp) || k <= 0) { if (c) c->err = "ntl_liftover_mappings: bad argument"; return NTL_ERR_ARG; }
+    const uint32_t nh = nreads ? hit_off[nreads] : 0;
+    if (nh && (!runs || !hits)) { c->err = "ntl_liftover_mappings: bad argument"; return NTL_ERR_ARG; }
+    for (uint32_t r = 0; r < nreads; r++)
+        if (hit_off[r + 1] < hit_off[r]) { c->err = "ntl_liftover_mappings: hit_off must be non-decreasing"; return NTL_ERR_ARG; }
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    static_assert(sizeof(ntl_agp_row) == sizeof(AgpRow), "ntl_agp_row layout");
+    MapStatus cs;
+    NTL_TRY(liftover_device(c, hit_off, nruns, reinterpret_cast<const Run*>(runs), reinterpret_cast<const Hit*>(hits), nreads,
+                            reinterpret_cast<const AgpRow*>(agp), ncontig, k, &cs));
+    if (out) {
+        MapWork& M = c->mw;
+        NTL_TRY(begin_map_results(c, nreads));
+        if (R->runs.reserve(((size_t)nh + 1) * sizeof(ntl_run)) || R->hits.reserve(((size_t)nh + 1) * sizeof(ntl_hit))) { c->err = "pinned alloc failed"; return NTL_ERR_CUDA; }
+        memcpy(R->hit_off.at<uint32_t>(0), hit_off, ((size_t)nreads + 1) * 4);      // the regions do not move
+        memset(R->ev_off.at<uint32_t>(0), 0, ((size_t)nreads + 1) * 4);
+        memset(R->ev_cnt.at<uint32_t>(0), 0, ((size_t)nreads + 1) * 4);
+        if (nreads) NTL_CUDA(c, cudaMemcpyAsync(R->nruns.at<uint32_t>(0), M.nruns.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (nh) {
+            NTL_CUDA(c, cudaMemcpyAsync(R->runs.at<ntl_run>(0), M.runs.p, (size_t)nh * sizeof(ntl_run), cudaMemcpyDeviceToHost, c->stream));
+            NTL_CUDA(c, cudaMemcpyAsync(R->hits.at<ntl_hit>(0), M.hits.p, (size_t)nh * sizeof(ntl_hit), cudaMemcpyDeviceToHost, c->stream));
+        }
+        NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+        fill_map_out(c, out, nreads, 0, nh, cs.n_runs, 0);
+        out->n_hits = cs.n_hits;          // hits that survived (the arrays keep their holey size hit_off[nreads])
+    }
+    return finish_call(c);
 }
 
 // ------------------------------------------------------------------------------------------- pairs

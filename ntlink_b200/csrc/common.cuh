@@ -98,6 +98,8 @@ struct TargetIndex {
 
 struct PreMappings {          // accepted runs/hits supplied by the host (checkpoint path), ntl_map_out layout
     const uint32_t* hit_off; const uint32_t* nruns; const Run* runs; const Hit* hits; uint32_t n_hits;
+    bool resident;            // the arrays are already in MapWork (left there by liftover_device): no upload
+    bool compute_read_len;    // read length = largest first/last read position of the read's runs (pair:483-487)
 };
 
 struct TallyWork {
@@ -106,6 +108,9 @@ struct TallyWork {
 
 struct MapWork {
     DevBuf hit_tmp, hit_flag, hit_pref, hits, runs, mark, hit_off, nruns, events, status, read_len, ev_cnt, blocksums;
+    DevBuf lift_runs, lift_nruns, lift_agp;     // liftover inputs
+    bool lifted_valid = false;                  // hits/runs/nruns/hit_off hold the output of the last liftover
+    uint32_t lifted_reads = 0, lifted_hits = 0;
 };
 
 }  // namespace ntl
@@ -170,6 +175,17 @@ int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg
 // scan utility (scan.cu): exclusive prefix sum of in[0..n) into out[0..n], out[n] = total; n read from the device
 int exclusive_scan_u32(ntl_ctx* c, const uint32_t* in, uint32_t* out, const uint32_t* n_dev, uint32_t n_max,
                        DevBuf& blocksums);
+// Small fills as ONE kernel instead of cudaMemsetAsync: the driver may route a memset through a copy engine, where it
+// would queue behind the large host->device copy of the next batch (measured: kernels of a batch ran ~2x longer while
+// a copy was in flight).
+struct FillSegs { void* p[4]; uint64_t n[4]; uint32_t v[4]; };
+static __global__ void k_fill_segs(FillSegs s) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint8_t* p = (uint8_t*)s.p[q];
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n[q]; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint8_t)s.v[q];
+    }
+}
 inline void tick(ntl_ctx* c, int stage) { cudaEventRecord(c->ev[2 * stage], c->stream); }
 inline void tock(ntl_ctx* c, int stage) { cudaEventRecord(c->ev[2 * stage + 1], c->stream); c->ev_used[stage] = true; }
 // after a stream synchronize: fold the recorded stage times into the accumulators

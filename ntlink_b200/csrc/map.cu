@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "lift_logic.cuh"
 
 namespace ntl {
 
@@ -222,15 +223,47 @@ __global__ void k_pairs_compact(const unsigned long long* __restrict__ keys, con
 
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
 
+// liftover: one thread per read (bin/ntlink_liftover_mappings.py:61-124)
+__global__ void __launch_bounds__(128) k_liftover(const Hit* __restrict__ hits, const Run* __restrict__ runs,
+                                                  const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ nruns,
+                                                  uint32_t nreads, const AgpRow* __restrict__ agp, uint32_t ncontig, int32_t k,
+                                                  Hit* __restrict__ hits_out, Run* __restrict__ runs_out,
+                                                  uint32_t* __restrict__ nruns_out, uint32_t* __restrict__ tmp_id,
+                                                  uint32_t* __restrict__ tmp_kept, MapStatus* __restrict__ st) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreads) return;
+    const uint32_t o = hit_off[r], cap = hit_off[r + 1] - o;
+    uint32_t err = 0, nout = 0, nh = 0;
+    const uint32_t nr = nruns[r];
+    if (nr) nout = lift_read(hits + o, runs + o, nr, cap, agp, ncontig, k, hits_out + o, runs_out + o, tmp_id + o, tmp_kept + o, &err);
+    nruns_out[r] = nout;
+    for (uint32_t i = 0; i < nout; i++) nh += runs_out[o + i].count;
+    if (nout) { atomicAdd(&st->n_runs, nout); atomicAdd(&st->n_hits, nh); }
+    if (err) atomicOr(&st->err, err << 8);
+}
+
 // checkpoint path: event capacity per read from the uploaded run counts
+// With read_len_out the reference's substitute read length is computed too: the largest first/last read position
+// over the read's runs (bin/ntlink_pair.py:483-487).
 __global__ void k_evmax(const uint32_t* __restrict__ nruns, uint32_t nreads, int32_t f, uint32_t* __restrict__ evmax,
-                        MapStatus* __restrict__ st, uint32_t* __restrict__ nreads_dev, uint32_t n_hits) {
+                        MapStatus* __restrict__ st, uint32_t* __restrict__ nreads_dev, uint32_t n_hits,
+                        const uint32_t* __restrict__ hit_off, const Run* __restrict__ runs, const Hit* __restrict__ hits,
+                        uint32_t* __restrict__ read_len_out) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r == 0) { *nreads_dev = nreads; st->n_hits = n_hits; }
     if (r >= nreads) return;
     const uint32_t nr = nruns[r];
     evmax[r] = max_events(nr, f);
     if (nr) atomicAdd(&st->n_runs, nr);
+    if (read_len_out) {
+        const uint32_t o = hit_off[r];
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < nr; i++) {
+            const Run ru = runs[o + i];
+            m = max(m, max(pos_of(hits[o + ru.start].rposf), pos_of(hits[o + ru.start + ru.count - 1].rposf)));
+        }
+        read_len_out[r] = m;
+    }
 }
 
 // counters -> pinned (UVA-mapped) host memory without using a copy engine
@@ -299,6 +332,57 @@ int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids) {
     return NTL_OK;
 }
 
+// Liftover of host mappings (ntl_map_out layout) through the AGP table. The lifted runs/hits stay in c->mw (hit_off,
+// nruns, runs, hits) -- exactly where map_device(pre->resident) expects them -- and the counters are returned.
+int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const Run* runs, const Hit* hits, uint32_t nreads,
+                    const AgpRow* agp, uint32_t ncontig, int32_t k, MapStatus* counts_out) {
+    MapWork& M = c->mw;
+    const uint32_t n = nreads ? hit_off[nreads] : 0;
+    NTL_CUDA(c, M.hits.ensure((size_t)n * sizeof(Hit) + 16));
+    NTL_CUDA(c, M.runs.ensure((size_t)n * sizeof(Run) + 16));
+    NTL_CUDA(c, M.hit_tmp.ensure((size_t)n * sizeof(Hit) + 16));          // input hits
+    NTL_CUDA(c, M.lift_runs.ensure((size_t)n * sizeof(Run) + 16));        // input runs
+    NTL_CUDA(c, M.hit_flag.ensure((size_t)n * 4 + 16));                    // scratch: new ids
+    NTL_CUDA(c, M.hit_pref.ensure((size_t)n * 4 + 16));                    // scratch: kept counts + flags
+    NTL_CUDA(c, M.hit_off.ensure(((size_t)nreads + 2) * 4));
+    NTL_CUDA(c, M.nruns.ensure(((size_t)nreads + 2) * 4));
+    NTL_CUDA(c, M.lift_nruns.ensure(((size_t)nreads + 2) * 4));
+    NTL_CUDA(c, M.lift_agp.ensure(((size_t)ncontig + 1) * sizeof(AgpRow)));
+    NTL_CUDA(c, M.status.ensure(sizeof(MapStatus) + 64));
+    NTL_CUDA(c, c->h_status.ensure(256));
+    MapStatus* st = M.status.as<MapStatus>();
+    {
+        FillSegs fs{};
+        fs.p[0] = st; fs.n[0] = sizeof(MapStatus) + 64;
+        k_fill_segs<<<1, 256, 0, c->stream>>>(fs);
+        c->launches++;
+    }
+    NTL_CUDA(c, cudaMemcpyAsync(M.hit_off.p, hit_off, ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    if (nreads) NTL_CUDA(c, cudaMemcpyAsync(M.lift_nruns.p, nruns, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n) {
+        NTL_CUDA(c, cudaMemcpyAsync(M.lift_runs.p, runs, (size_t)n * sizeof(Run), cudaMemcpyHostToDevice, c->stream));
+        NTL_CUDA(c, cudaMemcpyAsync(M.hit_tmp.p, hits, (size_t)n * sizeof(Hit), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (ncontig) NTL_CUDA(c, cudaMemcpyAsync(M.lift_agp.p, agp, (size_t)ncontig * sizeof(AgpRow), cudaMemcpyHostToDevice, c->stream));
+    if (nreads) {
+        k_liftover<<<div_up(nreads, 128), 128, 0, c->stream>>>(M.hit_tmp.as<Hit>(), M.lift_runs.as<Run>(), M.hit_off.as<uint32_t>(),
+                                                             M.lift_nruns.as<uint32_t>(), nreads, M.lift_agp.as<AgpRow>(), ncontig, k,
+                                                             M.hits.as<Hit>(), M.runs.as<Run>(), M.nruns.as<uint32_t>(),
+                                                             M.hit_flag.as<uint32_t>(), M.hit_pref.as<uint32_t>(), st);
+        c->launches++;
+    }
+    k_publish_map<<<1, 32, 0, c->stream>>>(st, &st->n_hits, &st->n_runs, c->h_status.as<uint32_t>());
+    c->launches++;
+    NTL_CUDA(c, cudaGetLastError());
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    const MapStatus hs = *c->h_status.as<MapStatus>();
+    if (hs.err & (LIFTERR_LAYOUT << 8)) { c->err = "liftover: malformed mappings (runs out of order / out of their read's region, or unknown contig id)"; return NTL_ERR_ARG; }
+    if (hs.err & (LIFTERR_RANGE << 8)) { c->err = "liftover: a lifted position does not fit in 31 bits"; return NTL_ERR_ARG; }
+    *counts_out = hs;
+    M.lifted_reads = nreads; M.lifted_hits = n; M.lifted_valid = true;
+    return NTL_OK;
+}
+
 // Lookup + chain + events for the reads whose sketch is `sk` (device). d_read_len: device read lengths.
 // Results are left in c->mw (hits, runs, nruns, hit_off, events log segment); the counters are returned.
 // With `pre` set the lookup and chaining are skipped: the accepted runs/hits come from the host (checkpoint path,
@@ -332,16 +416,25 @@ int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, u
     uint32_t ev_cap = std::max<uint32_t>(1 << 16, 4 * nreads);
     int attempt = 0;
 
-    NTL_CUDA(c, cudaMemsetAsync(st, 0, sizeof(MapStatus) + 64, c->stream));
+    {
+        FillSegs fs{};
+        fs.p[0] = st; fs.n[0] = sizeof(MapStatus) + 64;
+        k_fill_segs<<<1, 256, 0, c->stream>>>(fs);
+        c->launches++;
+    }
     if (pre) {
-        NTL_CUDA(c, cudaMemcpyAsync(M.hit_off.p, pre->hit_off, ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-        NTL_CUDA(c, cudaMemcpyAsync(M.nruns.p, pre->nruns, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
-        if (n) {
-            NTL_CUDA(c, cudaMemcpyAsync(M.runs.p, pre->runs, (size_t)n * sizeof(Run), cudaMemcpyHostToDevice, c->stream));
-            NTL_CUDA(c, cudaMemcpyAsync(M.hits.p, pre->hits, (size_t)n * sizeof(Hit), cudaMemcpyHostToDevice, c->stream));
+        if (!pre->resident) {
+            NTL_CUDA(c, cudaMemcpyAsync(M.hit_off.p, pre->hit_off, ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+            NTL_CUDA(c, cudaMemcpyAsync(M.nruns.p, pre->nruns, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
+            if (n) {
+                NTL_CUDA(c, cudaMemcpyAsync(M.runs.p, pre->runs, (size_t)n * sizeof(Run), cudaMemcpyHostToDevice, c->stream));
+                NTL_CUDA(c, cudaMemcpyAsync(M.hits.p, pre->hits, (size_t)n * sizeof(Hit), cudaMemcpyHostToDevice, c->stream));
+            }
         }
         tick(c, T_CHAIN);
-        k_evmax<<<div_up(std::max<uint32_t>(nreads, 1), 256), 256, 0, c->stream>>>(M.nruns.as<uint32_t>(), nreads, P.f, evmax, st, nreads_dev, n);
+        k_evmax<<<div_up(std::max<uint32_t>(nreads, 1), 256), 256, 0, c->stream>>>(
+            M.nruns.as<uint32_t>(), nreads, P.f, evmax, st, nreads_dev, n, M.hit_off.as<uint32_t>(), M.runs.as<Run>(), M.hits.as<Hit>(),
+            pre->compute_read_len ? const_cast<uint32_t*>(d_read_len) : nullptr);
         c->launches++;
         goto events_stage;
     }
@@ -396,7 +489,8 @@ retry_events:
     if (hs.err & MAPERR_EVENTS) {
         if (++attempt > 2) { c->err = "map: event buffer exhausted"; return NTL_ERR_WORKSPACE; }
         ev_cap = ev_need + 1024;
-        NTL_CUDA(c, cudaMemsetAsync(&st->err, 0, 4, c->stream));
+        k_set_u32<<<1, 1, 0, c->stream>>>(&st->err, 0u);
+        c->launches++;
         goto retry_events;
     }
     NTL_TRY(grow_preserve(c, c->tl_events, c->tl_n_events * sizeof(Event), (c->tl_n_events + n_events + 1) * sizeof(Event)));

@@ -538,12 +538,17 @@ retry:
         NTL_CUDA(c, cudaStreamSynchronize(c->stream));   // tbl is a stack array
         W.tbl_k = k;
     }
-    NTL_CUDA(c, cudaMemsetAsync(st, 0, sizeof(SketchStatus) + 64, c->stream));
-    NTL_CUDA(c, cudaMemsetAsync(W.has_cand.p, 0, (size_t)nseq + 1, c->stream));
     // layout: [64 B front pad | packed bases | >= 192 B tail pad]; d_packed points at the first real chunk
     uint32_t* const d_packed = reinterpret_cast<uint32_t*>(W.packed.as<char>() + 64);
-    NTL_CUDA(c, cudaMemsetAsync(W.packed.p, 0x44, 64, c->stream));
-    NTL_CUDA(c, cudaMemsetAsync(W.packed.as<char>() + 64 + total_bases / 2, 0x44, 192, c->stream));
+    {
+        FillSegs fs;
+        fs.p[0] = st; fs.n[0] = sizeof(SketchStatus) + 64; fs.v[0] = 0;
+        fs.p[1] = W.has_cand.p; fs.n[1] = (size_t)nseq + 1; fs.v[1] = 0;
+        fs.p[2] = W.packed.p; fs.n[2] = 64; fs.v[2] = 0x44;
+        fs.p[3] = W.packed.as<char>() + 64 + total_bases / 2; fs.n[3] = 192; fs.v[3] = 0x44;
+        k_fill_segs<<<std::max<uint32_t>(1, std::min<uint32_t>(div_up((uint64_t)nseq + 1, 256), 148)), 256, 0, c->stream>>>(fs);
+        c->launches += 1;
+    }
 
     tick(c, T_PACK);
     k_pack<<<div_up(div_up(total_bases, 16), 256 * PACK_CHUNKS), 256, 0, c->stream>>>(d_seq, total_bases, d_packed);

@@ -126,12 +126,14 @@ def parse_sketch_tsv(lines, with_len):
             np.array(posf, np.uint32), np.array(off, np.uint64))
 
 
-def parse_verbose_mappings(lines, contig_index):
+def parse_verbose_mappings(lines, contig_index, share_repeated=True, with_ids=False):
     """verbose_mapping.tsv -> the arrays of Context.tally_mappings, following parse_verbose_entries (pair:466-488):
     one run per line, hit_count = number of listed hits (the num_hits column is not used), 'read length' = the largest
     first/last read position over the read's runs, reads = maximal blocks of consecutive lines with the same read id.
-    A contig listed twice within a read refers both times to its LAST listing (the reference keeps one dict entry)."""
-    hit_off, nruns, read_len, runs, hits = [0], [], [], [], []
+    share_repeated: a contig listed twice within a read refers both times to its LAST listing (the reference keeps one
+    dict entry, pair:470-472); the liftover reads the same file line by line and passes False.
+    with_ids: also return the read id of every block."""
+    hit_off, nruns, read_len, runs, hits, ids = [0], [], [], [], [], []
     cur, group = None, []
 
     def flush():
@@ -140,18 +142,19 @@ def parse_verbose_mappings(lines, contig_index):
         base = hit_off[-1]
         last = {}
         local = []
-        for ctg, toks in group:
+        for n_line, (ctg, toks) in enumerate(group):
             start = len(hits) - base
             for tok in toks:
                 c, r = tok.split("_")
                 cp, cs = c.split(":")
                 rp, rs = r.split(":")
                 hits.append((ctg, int(cp) | (0x80000000 if cs == "+" else 0), int(rp) | (0x80000000 if rs == "+" else 0)))
-            last[ctg] = (ctg, start, len(toks))
-            local.append(ctg)
+            key = ctg if share_repeated else n_line
+            last[key] = (ctg, start, len(toks))
+            local.append(key)
         positions = []
-        for ctg in local:
-            run = last[ctg]
+        for key in local:
+            run = last[key]
             runs.append(run)
             positions += [hits[base + run[1]][2] & 0x7FFFFFFF, hits[base + run[1] + run[2] - 1][2] & 0x7FFFFFFF]
         # holey layout: the read's region holds max(#hits, #runs) slots in both arrays
@@ -161,6 +164,7 @@ def parse_verbose_mappings(lines, contig_index):
         nruns.append(len(local))
         read_len.append(max(positions))
         hit_off.append(base + width)
+        ids.append(cur)
 
     for line in lines:
         read_id, contig_id, _, mx_hits = line.strip().split("\t")
@@ -169,8 +173,9 @@ def parse_verbose_mappings(lines, contig_index):
             cur, group = read_id, []
         group.append((contig_index[contig_id], mx_hits.split(" ")))
     flush()
-    return (np.array(hit_off, np.uint32), np.array(nruns, np.uint32), np.array(runs, np.uint32).reshape(-1, 3),
-            np.array(hits, np.uint32).reshape(-1, 3), np.array(read_len, np.uint32))
+    out = (np.array(hit_off, np.uint32), np.array(nruns, np.uint32), np.array(runs, np.uint32).reshape(-1, 3),
+           np.array(hits, np.uint32).reshape(-1, 3), np.array(read_len, np.uint32))
+    return out + (ids,) if with_ids else out
 
 
 def parse_arguments(argv=None):

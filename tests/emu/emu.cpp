@@ -1,7 +1,7 @@
 // emu.cpp -- TEST INFRASTRUCTURE ONLY. Host emulation of the CUDA kernels' per-thread logic.
 //
 // The container that builds this repo has no GPU. To debug the kernel logic (ntlink_b200/csrc/sketch_logic.cuh,
-// map_logic.cuh) against the oracle without one, this file compiles those SAME headers with g++ and drives them
+// map_logic.cuh, lift_logic.cuh) against the oracle without one, this file compiles those SAME headers with g++ and drives them
 // with plain loops that stand in for the grid ("for every strip", "for every read") and for the scans.
 // It is built into tests/emu/_build/libntl_emu.so, loaded only by tests/test_emu_*.py, never by the product
 // (ntlink_b200/ has no CPU path: libntlink_b200.so fails to initialise without a CUDA device).
@@ -14,6 +14,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "../../ntlink_b200/csrc/lift_logic.cuh"
 #include "../../ntlink_b200/csrc/map_logic.cuh"
 #include "../../ntlink_b200/csrc/nthash.cuh"
 #include "../../ntlink_b200/csrc/sketch_logic.cuh"
@@ -247,6 +248,21 @@ int64_t emu_map(const uint64_t* t_hash, const uint32_t* t_ctg, const uint32_t* t
     }
     ev_off[nreads] = (uint32_t)ne;
     return (int64_t)ne;
+}
+
+// liftover (k_liftover): one loop iteration per read. Returns the error bits (0 = ok).
+uint32_t emu_liftover(const uint32_t* hit_off, const uint32_t* nruns, const Run* runs, const Hit* hits, uint32_t nreads,
+                      const AgpRow* agp, uint32_t ncontig, int32_t k, uint32_t* nruns_out, Run* runs_out, Hit* hits_out) {
+    uint32_t err = 0;
+    const uint32_t n = nreads ? hit_off[nreads] : 0;
+    std::vector<uint32_t> tmp_id(n + 1), tmp_kept(n + 1);
+    for (uint32_t r = 0; r < nreads; r++) {
+        const uint32_t o = hit_off[r], cap = hit_off[r + 1] - o;
+        nruns_out[r] = nruns[r] ? lift_read(hits + o, runs + o, nruns[r], cap, agp, ncontig, k, hits_out + o, runs_out + o,
+                                            tmp_id.data() + o, tmp_kept.data() + o, &err)
+                                : 0;
+    }
+    return err;
 }
 
 }  // extern "C"

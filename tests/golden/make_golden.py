@@ -135,6 +135,120 @@ CHECKPOINT_CASES = {"f1_default", "f2_default", "f3_default", "f4_default", "f3_
                     "f3k20w10_default"}
 
 
+# liftover (bin/ntlink_liftover_mappings.py, ntLink_rounds:122-125) + the round-2 checkpoint tally on its output.
+#   ref_*: the reference's own expected round-1 outputs (verbose_mapping.tsv + trimmed_scafs.agp)
+#   syn_*: the golden verbose mapping of a CASES entry + a seeded synthetic AGP (paths of 1-4 contigs in read order,
+#          both orientations, trimmed ends, identity entries, contigs missing from the AGP)
+LIFTOVER_REF = {"lift_ref_f1": ("scaffolds_1.fa.k32.w250.z1000", 32), "lift_ref_f2": ("scaffolds_2.fa.k32.w100.z1000", 32),
+                "lift_ref_f3": ("scaffolds_3.fa.k24.w250.z1000", 24), "lift_ref_f4": ("scaffolds_4.fa.k40.w100.z1000", 40)}
+LIFTOVER_SYN = {"lift_syn_f3": ("f3_default", 11), "lift_syn_f3_sensitive": ("f3_sensitive", 12), "lift_syn_f2": ("f2_default", 13),
+                "lift_syn_f3k20w10": ("f3k20w10_default", 14), "lift_syn_f1": ("f1_default", 15), "lift_syn_f3b": ("f3_default", 16)}
+
+
+def fasta_lengths(path):
+    out, name = {}, None
+    with (gzip.open(path, "rt") if path.endswith(".gz") else open(path)) as fin:
+        for line in fin:
+            if line.startswith(">"):
+                name = line[1:].split()[0]
+                out[name] = 0
+            elif name is not None:
+                out[name] += len(line.strip())
+    return out
+
+
+def synthetic_agp(verbose_text, lengths, k, seed):
+    """AGP lines + {new name: length}. Contigs are chained into paths in the order they first appear in the mapping file,
+    so that neighbours in a read often land in one path (merged runs, subsumed runs, non-monotonic runs all occur)."""
+    import random
+    rng = random.Random(seed)
+    order = []
+    for line in verbose_text.splitlines():
+        ctg = line.split("\t")[1]
+        if ctg not in order:
+            order.append(ctg)
+    lines, new_len, path_no, i = [], {}, 0, 0
+    while i < len(order):
+        roll = rng.random()
+        if roll < 0.15:                       # not in the AGP at all
+            new_len[order[i]] = lengths[order[i]]
+            i += 1
+            continue
+        if roll < 0.30:                       # identity entry: path id == contig id, coordinates untouched
+            ctg = order[i]
+            lines.append(f"{ctg}\t1\t{lengths[ctg]}\t1\tW\t{ctg}\t1\t{lengths[ctg]}\t{rng.choice('+-')}")
+            new_len[ctg] = lengths[ctg]
+            i += 1
+            continue
+        members = order[i:i + rng.randint(1, 4)]
+        i += len(members)
+        path, pos, comp = f"ntLink_{path_no}", 1, 1
+        path_no += 1
+        for j, ctg in enumerate(members):
+            if j:
+                gap = rng.choice([1, 20, 100, 431])
+                lines.append(f"{path}\t{pos}\t{pos + gap - 1}\t{comp}\tN\t{gap}\tscaffold\tyes\tpaired-ends")
+                pos += gap
+                comp += 1
+            start = 1 + (rng.randint(0, min(300, lengths[ctg] // 4)) if rng.random() < 0.5 else 0)
+            end = lengths[ctg] - (rng.randint(0, min(300, lengths[ctg] // 4)) if rng.random() < 0.5 else 0)
+            lines.append(f"{path}\t{pos}\t{pos + end - start}\t{comp}\tW\t{ctg}\t{start}\t{end}\t{rng.choice('+-')}")
+            pos += end - start + 1
+            comp += 1
+        new_len[path] = pos - 1
+    return "\n".join(lines) + "\n", new_len
+
+
+def make_liftover_goldens(work, env):
+    out_manifest = {}
+    jobs = []
+    for case, (prefix, k) in LIFTOVER_REF.items():
+        exp = os.path.join(REF, "tests", "expected_outputs")
+        verbose = open(os.path.join(exp, prefix + ".verbose_mapping.tsv")).read()
+        agp = open(os.path.join(exp, prefix + ".trimmed_scafs.agp")).read()
+        new_len = fasta_lengths(os.path.join(exp, prefix + ".ntLink.scaffolds.fa"))
+        jobs.append((case, verbose, agp, new_len, k, dict(BASE)))
+    cases_manifest = json.load(open(os.path.join(HERE, "manifest.json")))
+    for case, (src, seed) in LIFTOVER_SYN.items():
+        info = cases_manifest[src]
+        verbose = gzip.open(os.path.join(HERE, "cases", src, "verbose_mapping.tsv.gz"), "rt").read()
+        lengths = fasta_lengths(os.path.join(REF, "tests", info["target"]))
+        agp, new_len = synthetic_agp(verbose, lengths, info["k"], seed)
+        jobs.append((case, verbose, agp, new_len, info["k"], {key: info[key] for key in BASE}))
+    for case, verbose, agp, new_len, k, opt in jobs:
+        d = os.path.join(work, case)
+        os.makedirs(d)
+        open(os.path.join(d, "in.verbose_mapping.tsv"), "w").write(verbose)
+        open(os.path.join(d, "in.agp"), "w").write(agp)
+        lifted = os.path.join(d, "round2.verbose_mapping.tsv")
+        subprocess.check_call([sys.executable, os.path.join(REF, "bin", "ntlink_liftover_mappings.py"), "-m",
+                               os.path.join(d, "in.verbose_mapping.tsv"), "-a", os.path.join(d, "in.agp"), "-o", lifted,
+                               "-k", str(k)], env=env)
+        # round 2 (ntLink_rounds:137-145): the lifted file is the checkpoint of ntlink_pair.py on the scaffolds
+        fa = os.path.join(d, "round2.fa")
+        with open(fa, "w") as fout:
+            for name, length in new_len.items():
+                fout.write(f">{name}\n{'A' * length}\n")
+        cmd = [sys.executable, os.path.join(REF, "bin", "ntlink_pair.py"), "-p", os.path.join(d, "round2"), "-n", str(opt["n"]),
+               "-m", "unused.tsv", "-s", fa, "-k", str(k), "-a", str(opt["a"]), "-z", str(opt["z"]), "-f", str(opt["f"]),
+               "-x", str(opt["x"]), "--pairs", "unused_reads.tsv"]
+        ok = subprocess.call(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0
+        out_dir = os.path.join(HERE, "liftover", case)
+        os.makedirs(out_dir, exist_ok=True)
+        gz_write(os.path.join(out_dir, "in.verbose_mapping.tsv.gz"), verbose.encode())
+        gz_write(os.path.join(out_dir, "in.agp.gz"), agp.encode())
+        gz_write(os.path.join(out_dir, "lifted.verbose_mapping.tsv.gz"), open(lifted, "rb").read())
+        gz_write(os.path.join(out_dir, "round2.lengths.tsv.gz"), "".join(f"{n}\t{l}\n" for n, l in new_len.items()).encode())
+        if ok:
+            gz_write(os.path.join(out_dir, "round2.pairs.tsv.gz"), open(os.path.join(d, "round2.pairs.tsv"), "rb").read())
+            gz_write(os.path.join(out_dir, "round2.scaffold.dot.gz"),
+                     open(os.path.join(d, f"round2.n{opt['n']}.scaffold.dot"), "rb").read())
+        out_manifest[case] = {"k": k, "round2_ok": ok, **opt}
+        print("golden", case, "ok" if ok else "(round 2: the reference raises)")
+    with open(os.path.join(HERE, "liftover", "manifest.json"), "w") as fout:
+        json.dump(out_manifest, fout, indent=1, sort_keys=True)
+
+
 def gz_copy(src, dst):
     data = gzip.open(src, "rb").read() if src.endswith(".gz") else open(src, "rb").read()
     with gzip.GzipFile(dst, "wb", mtime=0) as fout:
@@ -214,6 +328,7 @@ def main():
         print("golden", case, "ok")
     with open(os.path.join(HERE, "manifest.json"), "w") as fout:
         json.dump(manifest, fout, indent=1, sort_keys=True)
+    make_liftover_goldens(work, env)
     shutil.rmtree(work)
 
 

@@ -145,8 +145,33 @@ def emu_lib():
                                 ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                 ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        lib.emu_liftover.restype = ctypes.c_uint32
+        lib.emu_liftover.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32] + \
+            [ctypes.c_void_p] * 3
         _emu = lib
     return _emu
+
+
+def lift_golden(case, what):
+    return gunzip_bytes(os.path.join(GOLD, "liftover", case, what + ".gz"))
+
+
+def lift_manifest():
+    with open(os.path.join(GOLD, "liftover", "manifest.json")) as fin:
+        return json.load(fin)
+
+
+def verbose_text(hit_off, nruns, runs, hits, read_ids, contig_names):
+    "ntl_map_out-style arrays -> verbose_mapping.tsv text (pure Python; for emulation tests)"
+    out = []
+    for r, rid in enumerate(read_ids):
+        base = int(hit_off[r])
+        for i in range(int(nruns[r])):
+            ctg, start, count = (int(v) for v in runs[base + i])
+            toks = [f"{int(h[1]) & 0x7FFFFFFF}:{'+' if int(h[1]) >> 31 else '-'}_{int(h[2]) & 0x7FFFFFFF}:{'+' if int(h[2]) >> 31 else '-'}"
+                    for h in hits[base + start: base + start + count]]
+            out.append(f"{rid}\t{contig_names[ctg]}\t{count}\t{' '.join(toks)}\n")
+    return "".join(out)
 
 
 def emu_sketch(seq, offsets, k, w, S=256, c=10.0, cap_override=0):
