@@ -12,8 +12,8 @@ namespace ntl {
 namespace {
 
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_STRIPS = 32;     // strips decided per block
-constexpr int SEL_CTX = 3;         // context strips staged on each side
+constexpr int SEL_STRIPS = 32;     // strips decided per block (upper bound; the launch passes the actual number)
+constexpr int SEL_CTX = 3;         // context strips staged on each side (upper bound, likewise)
 constexpr int SEL_NL = SEL_STRIPS + 2 * SEL_CTX;
 constexpr int SEL_CAP = 2560;      // candidates staged per block (40 KB)
 
@@ -23,7 +23,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
                                                          uint8_t* __restrict__ sel, uint32_t* __restrict__ selcnt,
                                                          unsigned long long* __restrict__ selmask,
                                                          GapRec* __restrict__ gaps, uint32_t* __restrict__ gap_head,
-                                                         SketchStatus* __restrict__ st) {
+                                                         SketchStatus* __restrict__ st, uint32_t nsb, uint32_t nctx) {
+    // nsb strips are decided per block with nctx strips of context on each side: chosen by the host so that the
+    // expected number of staged candidates fits SEL_CAP and the context covers w - 1 positions (select_shape)
     __shared__ uint4 sh_c[SEL_CAP];               // staged candidate: {h0.lo, h0.hi, valid-k-mer index, staged strip}
     __shared__ uint32_t sh_off[SEL_NL + 1];       // compact offset of every staged strip
     __shared__ uint32_t sh_cnt[SEL_NL];
@@ -33,11 +35,11 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
     __shared__ uint32_t sh_bad;                   // the staged range cannot be used -> whole block falls back
 
     const uint32_t nstrips = st->nstrips;
-    const uint32_t b0 = blockIdx.x * SEL_STRIPS;
+    const uint32_t b0 = blockIdx.x * nsb;
     if (b0 >= nstrips) return;
-    const uint32_t b1 = min(b0 + SEL_STRIPS, nstrips);
-    const uint32_t l0 = b0 > SEL_CTX ? b0 - SEL_CTX : 0;
-    const uint32_t l1 = min(b1 + SEL_CTX, nstrips);
+    const uint32_t b1 = min(b0 + nsb, nstrips);
+    const uint32_t l0 = b0 > nctx ? b0 - nctx : 0;
+    const uint32_t l1 = min(b1 + nctx, nstrips);
     const uint32_t nl = l1 - l0;
     const uint32_t tid = threadIdx.x;
 
@@ -205,6 +207,13 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
     }
     __syncthreads();
     if (tid < b1 - b0) { selcnt[b0 + tid] = sh_sel[tid]; selmask[b0 + tid] = sh_mask[tid]; }
+}
+
+// strips per block / context strips for a given expected number of candidates per strip
+inline void select_shape(double mu, uint32_t S, uint32_t w, uint32_t& nsb, uint32_t& nctx) {
+    nctx = std::min<uint32_t>(SEL_CTX, std::max<uint32_t>(1, (w - 1 + S - 1) / S));
+    const double fit = 0.85 * SEL_CAP / std::max(1.0, mu) - 2.0 * nctx;
+    nsb = (uint32_t)std::min<double>(SEL_STRIPS, std::max(1.0, fit));
 }
 
 }  // namespace

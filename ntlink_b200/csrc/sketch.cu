@@ -399,34 +399,48 @@ namespace ntl {
 namespace {
 
 // ------------------------------------------------------------------------------------------- emit
-__global__ void __launch_bounds__(128) k_emit(SkParams P, CandView V, const uint8_t* __restrict__ sel,
-                                              const unsigned long long* __restrict__ selmask,
-                                              const uint32_t* __restrict__ selbase, const GapRec* __restrict__ gaps,
-                                              const uint32_t* __restrict__ gap_head, const Cand* __restrict__ extras,
-                                              uint64_t* __restrict__ out_hash, uint32_t* __restrict__ out_posf,
-                                              SketchStatus* __restrict__ st) {
+// G lanes per strip (G = 4, 8, 16 or 32, picked from the expected number of candidates per strip): the lanes of a group
+// take the strip's candidates G at a time (coalesced 16-byte loads), the selected ones are ranked with a ballot and
+// written next to each other. Strips with a re-scanned gap attached or with overflowed slots take the serial path on
+// the group's first lane.
+constexpr int EMIT_THREADS = 256;
+template <int G>
+__global__ void __launch_bounds__(EMIT_THREADS) k_emit(SkParams P, CandView V, const uint8_t* __restrict__ sel,
+                                                       const unsigned long long* __restrict__ selmask,
+                                                       const uint32_t* __restrict__ selbase, const GapRec* __restrict__ gaps,
+                                                       const uint32_t* __restrict__ gap_head, const Cand* __restrict__ extras,
+                                                       uint64_t* __restrict__ out_hash, uint32_t* __restrict__ out_posf,
+                                                       SketchStatus* __restrict__ st) {
     const uint32_t nstrips = st->nstrips;
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0) st->n_mx = selbase[nstrips];
-    if (s >= nstrips) return;
-    uint32_t o = selbase[s];
-    const uint32_t end = selbase[s + 1];
-    if (o == end) return;
-    if (end > P.out_cap) { atomicOr(&st->err, SKERR_OUT); return; }
-    const uint32_t head = gap_head[s];
-    const uint32_t c = V.cnt[s];
-    if (head == NONE32 && c <= 64 && c <= V.cap) {
-        // common case: no gap attached, the selected candidates come as a bit mask -> one iteration per minimizer
-        unsigned long long m = selmask[s];
-        const Cand* base = V.cands + (uint64_t)s * V.cap;
-        while (m) {
-            const int j = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            const Cand e = base[j];
-            out_hash[o] = second_hash(e.h0, P.mult); out_posf[o] = e.posf; o++;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = gtid / G;
+    const uint32_t lane = threadIdx.x & 31, gl = lane % G, gshift = lane - gl;
+    const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    if (gtid == 0) st->n_mx = selbase[nstrips];
+    const bool live = s < nstrips;
+    // everything indexed by the strip is fetched up front: one memory latency instead of a chain of them
+    uint32_t o = 0, end = 0, head = NONE32, c = 0;
+    unsigned long long m = 0;
+    if (live) { o = selbase[s]; end = selbase[s + 1]; head = gap_head[s]; c = V.cnt[s]; m = selmask[s]; }
+    bool fast = live && o != end;
+    if (fast && end > P.out_cap) { if (gl == 0) atomicOr(&st->err, SKERR_OUT); fast = false; c = 0; }
+    const bool serial = fast && !(head == NONE32 && c <= V.cap);
+    if (!fast || serial) c = 0;
+    const uint64_t base = (uint64_t)s * V.cap;
+    for (uint32_t j0 = 0; __any_sync(0xffffffffu, j0 < c); j0 += G) {
+        const uint32_t j = j0 + gl;
+        bool on = false;
+        if (j < c) on = j < 64 ? ((m >> j) & 1ull) != 0 : sel[base + j] != 0;
+        const uint32_t b = (__ballot_sync(0xffffffffu, on) >> gshift) & gmask;
+        if (on) {
+            const Cand e = V.cands[base + j];
+            const uint32_t at = o + __popc(b & ((1u << gl) - 1u));
+            out_hash[at] = second_hash(e.h0, P.mult); out_posf[at] = e.posf;
         }
-        return;
+        o += __popc(b);
     }
+    if (!serial || gl != 0) return;
+    c = V.cnt[s];
     if (head != NONE32) {
         for (uint32_t g = head; g != NONE32; g = gaps[g].next)
             if (gaps[g].j == NONE32)
@@ -576,9 +590,11 @@ retry:
     CandView V;
     V.cands = W.slots.as<Cand>(); V.cnt = W.cnt.as<uint32_t>(); V.ovf_off = W.ovf_off.as<uint32_t>();
     V.vbase = W.vbase.as<uint32_t>(); V.cap = cap; V.pool_base = P.pool_base;
-    k_select<<<div_up(nstrips_max, SEL_STRIPS), SEL_THREADS, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
+    uint32_t nsb, nctx;
+    select_shape(mu, S, w, nsb, nctx);
+    k_select<<<div_up(nstrips_max, nsb), SEL_THREADS, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
                                                              W.selcnt.as<uint32_t>(), W.selmask.as<unsigned long long>(), W.gaps.as<GapRec>(),
-                                                             W.gap_head.as<uint32_t>(), st);
+                                                             W.gap_head.as<uint32_t>(), st, nsb, nctx);
     k_seq_gaps<<<div_up(nseq, 128), 128, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.has_cand.as<uint8_t>(),
                                                         W.gaps.as<GapRec>(), W.gap_head.as<uint32_t>(), st);
     c->launches += 2;
@@ -616,9 +632,16 @@ retry:
     NTL_CUDA(c, out.hash.ensure((size_t)out_cap * 8 + 8));
     NTL_CUDA(c, out.posf.ensure((size_t)out_cap * 4 + 4));
     P.out_cap = out_cap;
-    k_emit<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(P, V, W.sel.as<uint8_t>(), W.selmask.as<unsigned long long>(), W.selbase.as<uint32_t>(), W.gaps.as<GapRec>(),
-                                                           W.gap_head.as<uint32_t>(), W.extras.as<Cand>(), out.hash.as<uint64_t>(),
-                                                           out.posf.as<uint32_t>(), st);
+    {
+        int G = mu <= 12 ? 4 : mu <= 40 ? 8 : mu <= 96 ? 16 : 32;
+        if (const char* eg = getenv("NTL_EMIT_G")) G = atoi(eg);
+#define NTL_EMIT(GG)                                                                                                              \
+        k_emit<GG><<<div_up((uint64_t)nstrips_max * GG, EMIT_THREADS), EMIT_THREADS, 0, c->stream>>>(                               \
+            P, V, W.sel.as<uint8_t>(), W.selmask.as<unsigned long long>(), W.selbase.as<uint32_t>(), W.gaps.as<GapRec>(),           \
+            W.gap_head.as<uint32_t>(), W.extras.as<Cand>(), out.hash.as<uint64_t>(), out.posf.as<uint32_t>(), st)
+        if (G == 4) NTL_EMIT(4); else if (G == 8) NTL_EMIT(8); else if (G == 16) NTL_EMIT(16); else NTL_EMIT(32);
+#undef NTL_EMIT
+    }
     k_seq_offsets<<<div_up((uint64_t)nseq + 1, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), W.selbase.as<uint32_t>(), nseq,
                                                                         out.mx_off.as<uint32_t>());
     c->launches += 2;
