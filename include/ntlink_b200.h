@@ -42,7 +42,10 @@ void ntl_destroy(ntl_ctx* ctx);
 const char* ntl_last_error(const ntl_ctx* ctx);
 int ntl_version(void);
 /* tuning knobs: "strip_len" (k-mer positions per thread, multiple of 8), "cand_c" (candidate threshold,
- * expected candidates per window), "batch_bases" (bases per device batch) */
+ * expected candidates per window), "batch_bases" (bases per device batch), "pipeline_min_bases" (4x the chunk size of
+ * the pipelined ntl_map_reads), "async" (1: ntl_map_reads / ntl_map_resident enqueue the whole call without waiting for
+ * the device and synchronise once; 0: the step-by-step path the sync-free one falls back to), "graph" (1: each chunk of
+ * a sync-free call is launched as one CUDA graph) */
 int ntl_set_option(ntl_ctx* ctx, const char* name, double value);
 
 /* ---- sketch -------------------------------------------------------------------------------------
@@ -242,6 +245,9 @@ int ntl_index_build_resident(ntl_ctx* ctx, int k, int w);
 enum { NTL_T_PACK = 0, NTL_T_DENSE, NTL_T_SELECT, NTL_T_GAP, NTL_T_EMIT, NTL_T_LOOKUP, NTL_T_CHAIN, NTL_T_TALLY,
        NTL_T_INDEX, NTL_T_TOTAL, NTL_T_NUM };
 int ntl_timing_reset(ntl_ctx* ctx);
+/* counters since ntl_init: "async_calls" (calls that took the sync-free path), "async_fallbacks" (of those, how many had
+ * to be repeated on the synchronous path because a capacity bound was too small), "graph_launches" */
+int ntl_get_stat(ntl_ctx* ctx, const char* name, double* value);
 int ntl_timing(ntl_ctx* ctx, double* ms_accum /* [NTL_T_NUM] */, uint64_t* launches, uint64_t* dense_launches,
                uint64_t* dense_bases);
 /* the dominant kernel (k_dense) alone, restricted to launches over at least min 16 Mbp (the read batches): accumulated

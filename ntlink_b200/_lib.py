@@ -100,6 +100,7 @@ SIGNATURES = {
     "ntl_target_upload": (C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP]),
     "ntl_index_build_resident": (C.c_int, [_VP, C.c_int, C.c_int]),
     "ntl_timing_reset": (C.c_int, [_VP]),
+    "ntl_get_stat": (C.c_int, [_VP, C.c_char_p, C.POINTER(C.c_double)]),
     "ntl_timing": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P, _U64P, _U64P]),
     "ntl_timing_dense": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P, _U64P]),
     "ntl_device_sync": (C.c_int, [_VP]),

@@ -370,6 +370,12 @@ class Context:
     def index_build_resident(self, k, w):
         self._check(self.lib.ntl_index_build_resident(self.h, k, w), "ntl_index_build_resident")
 
+    def stat(self, name):
+        "counters since init: async_calls, async_fallbacks, graph_launches"
+        v = C.c_double()
+        self._check(self.lib.ntl_get_stat(self.h, name.encode(), C.byref(v)), "ntl_get_stat")
+        return v.value
+
     def timing_reset(self):
         self._check(self.lib.ntl_timing_reset(self.h), "ntl_timing_reset")
 

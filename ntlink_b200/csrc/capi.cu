@@ -11,7 +11,12 @@
 namespace ntl {
 int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids);
 int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, uint32_t nreads, uint64_t first_ordinal,
-               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out, const PreMappings* pre = nullptr);
+               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out, const PreMappings* pre = nullptr,
+               CallState* call = nullptr);
+int call_begin(ntl_ctx* c, CallState** call_out);
+int call_reserve_events(ntl_ctx* c, uint32_t nreads);
+int call_chunk_finish(ntl_ctx* c, CallState* call, uint32_t rb, uint32_t nreads, const HostResults* H);
+int call_end(ntl_ctx* c, CallState* call, CallState* host_out);
 int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const Run* runs, const Hit* hits, uint32_t nreads,
                     const AgpRow* agp, uint32_t ncontig, int32_t k, MapStatus* counts_out);
 int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>& gaps);
@@ -52,11 +57,18 @@ struct Results {
     cudaEvent_t h2d_done[2] = {nullptr, nullptr};
     DevBuf st_seq[2], st_off[2];
     PinnedBuf st_hoff[2];
+    // sync-free path: staging slot free again (its chunk's kernels are done), rebased offsets of every chunk of the call
+    cudaEvent_t comp_done[2] = {nullptr, nullptr};
+    std::vector<cudaGraphExec_t> chunk_execs;
+    cudaGraphExec_t resident_exec = nullptr;
+    PinnedBuf call_hoff;
+    uint64_t last_call_hits = 0, last_call_bases = 0;
 };
 }  // namespace ntl
 
 using namespace ntl;
 
+static double host_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static Results* res_of(ntl_ctx* c) { return static_cast<Results*>(c->res); }
 
 static int finish_call(ntl_ctx* c) {
@@ -134,6 +146,8 @@ int ntl_init(int device, ntl_ctx** out) {
     cudaStreamCreateWithFlags(&res_of(c)->copy_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&res_of(c)->h2d_done[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&res_of(c)->h2d_done[1], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&res_of(c)->comp_done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&res_of(c)->comp_done[1], cudaEventDisableTiming);
     for (int i = 0; i < T_NUM; i++) { c->ev_used[i] = false; c->ms_accum[i] = 0; }
     *out = c;
     return NTL_OK;
@@ -165,7 +179,11 @@ void ntl_destroy(ntl_ctx* c) {
                      &R->ev_cnt, &R->events};
     for (HostVec* v : hv) v->b.release();
     R->h_off.release();
-    for (int i = 0; i < 2; i++) { R->st_seq[i].release(); R->st_off[i].release(); R->st_hoff[i].release(); cudaEventDestroy(R->h2d_done[i]); }
+    for (int i = 0; i < 2; i++) { R->st_seq[i].release(); R->st_off[i].release(); R->st_hoff[i].release(); cudaEventDestroy(R->h2d_done[i]); cudaEventDestroy(R->comp_done[i]); }
+    R->call_hoff.release();
+    for (cudaGraphExec_t e : R->chunk_execs) if (e) cudaGraphExecDestroy(e);
+    R->chunk_execs.clear();
+    if (R->resident_exec) cudaGraphExecDestroy(R->resident_exec);
     cudaStreamSynchronize(R->copy_stream);
     cudaStreamDestroy(R->copy_stream);
     c->h_status.release();
@@ -187,6 +205,10 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
     } else if (!strcmp(name, "cand_c")) {
         if (!(value > 0)) { c->err = "cand_c must be positive"; return NTL_ERR_ARG; }
         c->cand_c = value;
+    } else if (!strcmp(name, "async")) {
+        c->async_mode = value != 0.0;
+    } else if (!strcmp(name, "graph")) {
+        c->graph_mode = value != 0.0;
     } else if (!strcmp(name, "pipeline_min_bases")) {
         if (value < 1024 || value > 3.9e9) { c->err = "pipeline_min_bases out of range"; return NTL_ERR_ARG; }
         c->pipeline_min_bases = (uint64_t)value;
@@ -393,12 +415,191 @@ static void fill_map_out(ntl_ctx* c, ntl_map_out* out, uint32_t nreads, uint64_t
     out->ev_off = R->ev_off.at<uint32_t>(0); out->ev_cnt = R->ev_cnt.at<uint32_t>(0); out->events = R->events.at<ntl_event>(0);
 }
 
+// Sync-free form of ntl_map_reads: every chunk's copy, sketch, mapping and result write-back is enqueued without waiting
+// for the device; ONE synchronisation ends the call. Capacities come from bounds and from what earlier calls needed; if
+// any of them turns out too small (or a reference assertion fails) *ok is false, nothing has been committed, and the
+// caller repeats the call on the synchronous path, which sizes everything exactly and reports errors precisely.
+static int map_reads_async(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t nreads, uint64_t first_read_ordinal,
+                           const ntl_params* prm, ntl_map_out* out, bool* ok) {
+    Results* R = res_of(c);
+    *ok = false;
+    const double host_tin = host_now_us();
+    const uint64_t total_bases = offsets[nreads] - offsets[0];
+    // chunks: about pipeline_min_bases / 4 each (20 Mbp by default: no per-chunk round trip to amortise any more, and the
+    // part of the call that cannot overlap the copy is the last chunk's compute), at most batch_bases
+    std::vector<uint32_t> bounds;
+    const uint64_t target = std::max<uint64_t>(1ull << 20, c->pipeline_min_bases / 4);
+    const uint64_t nb_target = std::max<uint64_t>(1, (total_bases + target / 2) / target);
+    uint64_t per_chunk = (total_bases + nb_target - 1) / nb_target + (1u << 18);
+    if (per_chunk > c->batch_bases) per_chunk = c->batch_bases;
+    plan_batches(offsets, nreads, per_chunk, bounds);
+    const size_t nch = bounds.size() - 1;
+    uint64_t max_nb = 0; uint32_t max_ns = 0, mx_bound_total = 0;
+    for (size_t i = 0; i < nch; i++) {
+        const uint64_t nb = offsets[bounds[i + 1]] - offsets[bounds[i]];
+        if (nb >= (1ull << 32) - 4096) return NTL_OK;          // let the synchronous path report it
+        max_nb = std::max(max_nb, nb); max_ns = std::max(max_ns, bounds[i + 1] - bounds[i]);
+        const uint64_t b = std::min<uint64_t>(nb, (uint64_t)(2.6 * (double)nb / ((double)prm->w + 1.0)) + 8ull * (bounds[i + 1] - bounds[i]) + 4096);
+        if ((uint64_t)mx_bound_total + b >= (1ull << 31)) return NTL_OK;
+        mx_bound_total += (uint32_t)b;
+    }
+    // host result arrays: hits <= minimizers; keep the pinned arrays moderate with the hit rate seen so far
+    uint64_t hits_cap = mx_bound_total;
+    if (hits_cap > (4u << 20)) {
+        const double rate = R->last_call_bases ? (double)R->last_call_hits / (double)R->last_call_bases : 0.01;
+        hits_cap = std::min<uint64_t>(hits_cap, std::max<uint64_t>(4u << 20, (uint64_t)(3.0 * rate * (double)total_bases) + (1u << 20)));
+    }
+    const uint64_t ev_cap_total = std::max<uint64_t>((uint64_t)std::max<uint32_t>(c->ev_cap_hint, 1u << 16) * 2, 8ull * nreads);
+    NTL_TRY(begin_map_results(c, nreads));
+    if (R->runs.reserve((hits_cap + 1) * sizeof(ntl_run)) || R->hits.reserve((hits_cap + 1) * sizeof(ntl_hit)) ||
+        R->events.reserve((ev_cap_total + 1) * sizeof(ntl_event))) { c->err = "pinned alloc failed"; return NTL_ERR_CUDA; }
+    HostResults H;
+    H.hit_off = R->hit_off.at<uint32_t>(0); H.nruns = R->nruns.at<uint32_t>(0);
+    H.ev_off = R->ev_off.at<uint32_t>(0); H.ev_cnt = R->ev_cnt.at<uint32_t>(0);
+    H.runs = R->runs.at<Run>(0); H.hits = R->hits.at<Hit>(0); H.events = R->events.at<Event>(0);
+    H.hits_cap = (uint32_t)std::min<uint64_t>(hits_cap, 0xFFFFFFF0u); H.ev_cap = (uint32_t)std::min<uint64_t>(ev_cap_total, 0xFFFFFFF0u);
+    // staging: two device slots, the rebased offsets of ALL chunks in one pinned array (nothing is reused while in flight)
+    for (int sl = 0; sl < 2 && (size_t)sl < nch; sl++) {
+        NTL_CUDA(c, R->st_seq[sl].ensure(max_nb + 256));
+        NTL_CUDA(c, R->st_off[sl].ensure(((size_t)max_ns + 1) * 8));
+    }
+    NTL_CUDA(c, R->call_hoff.ensure(((size_t)nreads + nch + 1) * 8));
+    NTL_CUDA(c, R->read_len.ensure(((size_t)max_ns + 1) * 4));
+    uint64_t* ho_all = R->call_hoff.as<uint64_t>();
+    std::vector<size_t> ho_at(nch);
+    {
+        size_t at = 0;
+        for (size_t i = 0; i < nch; i++) {
+            ho_at[i] = at;
+            const uint64_t base = offsets[bounds[i]];
+            for (uint32_t r = bounds[i]; r <= bounds[i + 1]; r++) ho_all[at++] = offsets[r] - base;
+        }
+    }
+    auto enqueue_copy = [&](size_t i) -> int {
+        const int sl = (int)(i & 1);
+        const uint64_t base = offsets[bounds[i]], nb = offsets[bounds[i + 1]] - base;
+        const uint32_t ns = bounds[i + 1] - bounds[i];
+        if (i >= 2) NTL_CUDA(c, cudaStreamWaitEvent(R->copy_stream, R->comp_done[sl], 0));   // slot's previous chunk is done with it
+        if (nb) NTL_CUDA(c, cudaMemcpyAsync(R->st_seq[sl].p, seq + base, nb, cudaMemcpyHostToDevice, R->copy_stream));
+        NTL_CUDA(c, cudaMemcpyAsync(R->st_off[sl].p, ho_all + ho_at[i], ((size_t)ns + 1) * 8, cudaMemcpyHostToDevice, R->copy_stream));
+        NTL_CUDA(c, cudaEventRecord(R->h2d_done[sl], R->copy_stream));
+        return NTL_OK;
+    };
+    CallState* call = nullptr;
+    NTL_TRY(call_begin(c, &call));
+    // NTL_TRACE: device timeline of the call (copy / compute end of every chunk, relative to the start of the call)
+    const bool trace = getenv("NTL_TRACE") != nullptr;
+    const double host_t0 = host_now_us();
+    std::vector<cudaEvent_t> tr_copy, tr_comp;
+    cudaEvent_t tr_start = nullptr;
+    if (trace) {
+        cudaEventCreate(&tr_start); cudaEventRecord(tr_start, c->stream);
+        cudaStreamWaitEvent(R->copy_stream, tr_start, 0);
+        tr_copy.resize(nch); tr_comp.resize(nch);
+        for (size_t i = 0; i < nch; i++) { cudaEventCreate(&tr_copy[i]); cudaEventCreate(&tr_comp[i]); }
+    }
+    if (nch) { NTL_TRY(enqueue_copy(0)); if (trace) cudaEventRecord(tr_copy[0], R->copy_stream); }
+    const bool use_graph = c->graph_mode != 0;
+    // executable graphs are kept across calls (one per chunk position) and updated in place: the topology of a chunk's
+    // graph never changes, only kernel arguments and grid sizes do
+    std::vector<cudaGraphExec_t>& execs = R->chunk_execs;
+    NTL_TRY(sketch_prepare(c, (uint32_t)prm->k));
+    tick(c, T_TOTAL);
+    for (size_t i = 0; i < nch; i++) {
+        const int sl = (int)(i & 1);
+        const uint32_t b = bounds[i], ns = bounds[i + 1] - b;
+        const uint64_t nb = offsets[bounds[i + 1]] - offsets[b];
+        if (i + 1 < nch) { NTL_TRY(enqueue_copy(i + 1)); if (trace) cudaEventRecord(tr_copy[i + 1], R->copy_stream); }
+        if (use_graph) {
+            // The ~60 launches of a chunk go into ONE CUDA graph: while a host->device copy is in flight every single
+            // kernel launch costs several microseconds more (its launch data is fetched over the same PCIe link), a
+            // graph launch pays that once. Capture + instantiation run on the host while the copy is still under way.
+            NTL_TRY(call_reserve_events(c, ns));
+            const double h0 = trace ? host_now_us() : 0;
+            cudaGraph_t graph = nullptr;
+            NTL_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            c->capturing = true; c->no_stage_timing = true;
+            int rc = sketch_device(c, R->st_seq[sl].as<uint8_t>(), R->st_off[sl].as<uint64_t>(), ns, nb, (uint32_t)prm->k, (uint32_t)prm->w,
+                                   c->dsk, call);
+            if (rc == NTL_OK) rc = read_len_device(c, R->st_off[sl].as<uint64_t>(), ns, R->read_len);
+            if (rc == NTL_OK) rc = map_device(c, c->dsk, R->read_len.as<uint32_t>(), ns, first_read_ordinal + b, prm, nullptr, nullptr, nullptr, call);
+            if (rc == NTL_OK) rc = call_chunk_finish(c, call, b, ns, &H);
+            c->capturing = false; c->no_stage_timing = false;
+            const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            const double h1 = trace ? host_now_us() : 0;
+            if (rc != NTL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) { c->err = std::string("graph capture: ") + cudaGetErrorString(ce); return NTL_ERR_CUDA; }
+            cudaGraphExec_t exec = i < execs.size() ? execs[i] : nullptr;
+            if (exec) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(exec, graph, &info) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(exec);
+                    exec = nullptr;
+                }
+            }
+            if (!exec) {
+                const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+                if (ie != cudaSuccess) { cudaGraphDestroy(graph); if (i < execs.size()) execs[i] = nullptr; c->err = std::string("graph instantiate: ") + cudaGetErrorString(ie); return NTL_ERR_CUDA; }
+            }
+            cudaGraphDestroy(graph);
+            if (i < execs.size()) execs[i] = exec; else execs.push_back(exec);
+            NTL_CUDA(c, cudaStreamWaitEvent(c->stream, R->h2d_done[sl], 0));
+            const double h2 = trace ? host_now_us() : 0;
+            NTL_CUDA(c, cudaGraphLaunch(exec, c->stream));
+            c->n_graph_launches++;
+            if (trace) fprintf(stderr, "[ntl] chunk %zu host: capture %.0f us, instantiate %.0f us, launch %.0f us (at %.0f us)\n", i, h1 - h0, h2 - h1,
+                               host_now_us() - h2, host_now_us() - host_t0);
+        } else {
+        NTL_CUDA(c, cudaStreamWaitEvent(c->stream, R->h2d_done[sl], 0));
+        NTL_TRY(sketch_device(c, R->st_seq[sl].as<uint8_t>(), R->st_off[sl].as<uint64_t>(), ns, nb, (uint32_t)prm->k, (uint32_t)prm->w,
+                              c->dsk, call));
+        NTL_TRY(read_len_device(c, R->st_off[sl].as<uint64_t>(), ns, R->read_len));
+        NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), ns, first_read_ordinal + b, prm, nullptr, nullptr, nullptr, call));
+        NTL_TRY(call_chunk_finish(c, call, b, ns, &H));
+        }
+        NTL_CUDA(c, cudaEventRecord(R->comp_done[sl], c->stream));
+        if (trace) cudaEventRecord(tr_comp[i], c->stream);
+    }
+    tock(c, T_TOTAL);
+    CallState hs;
+    NTL_TRY(call_end(c, call, &hs));
+    collect_timing(c);
+    if (trace) {
+        fprintf(stderr, "[ntl] call synchronised at %.0f us (host clock; %.0f us of set-up before it)\n", host_now_us() - host_t0, host_t0 - host_tin);
+        cudaStreamSynchronize(R->copy_stream);
+        for (size_t i = 0; i < nch; i++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, tr_start, tr_copy[i]); cudaEventElapsedTime(&b, tr_start, tr_comp[i]);
+            fprintf(stderr, "[ntl] chunk %zu (%u reads): copy done %7.3f ms, compute done %7.3f ms\n", i, bounds[i + 1] - bounds[i], a, b);
+            cudaEventDestroy(tr_copy[i]); cudaEventDestroy(tr_comp[i]);
+        }
+        cudaEventDestroy(tr_start);
+    }
+    if (hs.err) return NTL_OK;                                  // *ok stays false
+    R->last_call_hits = hs.hits_total; R->last_call_bases = total_bases;
+    R->runs.used = (size_t)hs.hits_total * sizeof(ntl_run); R->hits.used = (size_t)hs.hits_total * sizeof(ntl_hit);
+    R->events.used = (size_t)hs.ev_total * sizeof(ntl_event);
+    fill_map_out(c, out, nreads, hs.mx_total, hs.hits_total, hs.runs_total, hs.ev_total);
+    c->dsk.n_mx = nch == 1 ? hs.mx_total : 0;                  // the bound is of no use to anyone after the call
+    *ok = true;
+    return NTL_OK;
+}
+
 int ntl_map_reads(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t nreads, uint64_t first_read_ordinal,
                   const ntl_params* prm, ntl_map_out* out) {
     if (!c || (!seq && nreads) || !offsets || !prm || !out || prm->k <= 0 || prm->w <= 0) { if (c) c->err = "ntl_map_reads: bad argument"; return NTL_ERR_ARG; }
     if (!c->index.built) { c->err = "ntl_map_reads: no target index"; return NTL_ERR_STATE; }
     Results* R = res_of(c);
     cudaSetDevice(c->device);
+    if (c->async_mode && nreads) {
+        bool ok = false;
+        NTL_TRY(map_reads_async(c, seq, offsets, nreads, first_read_ordinal, prm, out, &ok));
+        c->n_async_calls++;
+        if (ok) return NTL_OK;
+        c->n_async_fallbacks++;
+        if (getenv("NTL_TRACE")) fprintf(stderr, "[ntl] sync-free call fell back to the synchronous path\n");
+    }
     NTL_TRY(begin_map_results(c, nreads));
     // Pipelined: the host->device copy of batch i+1 (copy stream, double-buffered staging) overlaps the kernels of
     // batch i (compute stream). Batches of about a quarter of the call so that the overlap pays off.
@@ -475,7 +676,7 @@ int ntl_map_sketch(ntl_ctx* c, const uint64_t* hash, const uint32_t* pos_strand,
         }
         NTL_CUDA(c, cudaMemcpyAsync(sk.mx_off.p, off32.data(), ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, c->stream));
         if (nr) NTL_CUDA(c, cudaMemcpyAsync(R->read_len.p, read_len + b, (size_t)nr * 4, cudaMemcpyHostToDevice, c->stream));
-        sk.n_mx = (uint32_t)n; sk.nseq = nr;
+        sk.n_mx = (uint32_t)n; sk.nseq = nr; sk.n_dev = nullptr;
         MapStatus cs; uint64_t log_base = 0;
         NTL_TRY(map_device(c, sk, R->read_len.as<uint32_t>(), nr, first_read_ordinal + b, prm, &cs, &log_base));
         tock(c, T_TOTAL);
@@ -657,6 +858,65 @@ int ntl_map_resident(ntl_ctx* c, uint64_t first_read_ordinal, const ntl_params* 
     Results* R = res_of(c);
     cudaSetDevice(c->device);
     if (!R->r_nreads) { c->err = "ntl_map_resident: no resident reads"; return NTL_ERR_STATE; }
+    if (c->async_mode) {
+        // sync-free: sketch + mapping enqueued back to back (as one CUDA graph, updated in place from call to call),
+        // one synchronisation at the end (see map_reads_async)
+        CallState* call = nullptr;
+        NTL_TRY(call_begin(c, &call));
+        auto enqueue = [&]() -> int {
+            tick(c, T_TOTAL);
+            NTL_TRY(sketch_device(c, R->r_seq.as<uint8_t>(), R->r_off.as<uint64_t>(), R->r_nreads, R->r_bases, (uint32_t)prm->k,
+                                  (uint32_t)prm->w, c->dsk, call));
+            NTL_TRY(read_len_device(c, R->r_off.as<uint64_t>(), R->r_nreads, R->read_len));
+            NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), R->r_nreads, first_read_ordinal, prm, nullptr, nullptr, nullptr, call));
+            NTL_TRY(call_chunk_finish(c, call, 0, R->r_nreads, nullptr));
+            tock(c, T_TOTAL);
+            return NTL_OK;
+        };
+        if (c->graph_mode) {
+            NTL_TRY(sketch_prepare(c, (uint32_t)prm->k));
+            NTL_TRY(call_reserve_events(c, R->r_nreads));
+            cudaGraph_t graph = nullptr;
+            NTL_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            c->capturing = true;
+            const int rc = enqueue();
+            c->capturing = false;
+            const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            if (rc != NTL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) { c->err = std::string("graph capture: ") + cudaGetErrorString(ce); return NTL_ERR_CUDA; }
+            if (R->resident_exec) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(R->resident_exec, graph, &info) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(R->resident_exec);
+                    R->resident_exec = nullptr;
+                }
+            }
+            if (!R->resident_exec) {
+                const cudaError_t ie = cudaGraphInstantiate(&R->resident_exec, graph, 0);
+                if (ie != cudaSuccess) { cudaGraphDestroy(graph); R->resident_exec = nullptr; c->err = std::string("graph instantiate: ") + cudaGetErrorString(ie); return NTL_ERR_CUDA; }
+            }
+            cudaGraphDestroy(graph);
+            NTL_CUDA(c, cudaGraphLaunch(R->resident_exec, c->stream));
+            c->n_graph_launches++;
+        } else {
+            NTL_TRY(enqueue());
+        }
+        CallState hs;
+        NTL_TRY(call_end(c, call, &hs));
+        collect_timing(c);
+        c->n_async_calls++;
+        if (hs.err) c->n_async_fallbacks++;
+        if (hs.err == 0) {
+            c->dsk.n_mx = hs.mx_total;
+            if (counts) {
+                memset(counts, 0, sizeof *counts);
+                counts->n_reads = R->r_nreads; counts->n_mx = hs.mx_total; counts->n_hits = hs.hits_total; counts->n_runs = hs.runs_total;
+                counts->n_events = hs.ev_total;
+            }
+            return NTL_OK;
+        }
+    }
     tick(c, T_TOTAL);
     NTL_TRY(sketch_device(c, R->r_seq.as<uint8_t>(), R->r_off.as<uint64_t>(), R->r_nreads, R->r_bases, (uint32_t)prm->k,
                           (uint32_t)prm->w, c->dsk));
@@ -724,6 +984,14 @@ int ntl_timing(ntl_ctx* c, double* ms_accum, uint64_t* launches, uint64_t* dense
     if (launches) *launches = c->launches;
     if (dense_launches) *dense_launches = c->dense_launches;
     if (dense_bases) *dense_bases = c->dense_bases;
+    return NTL_OK;
+}
+int ntl_get_stat(ntl_ctx* c, const char* name, double* value) {
+    if (!c || !name || !value) return NTL_ERR_ARG;
+    if (!strcmp(name, "async_calls")) *value = (double)c->n_async_calls;
+    else if (!strcmp(name, "async_fallbacks")) *value = (double)c->n_async_fallbacks;
+    else if (!strcmp(name, "graph_launches")) *value = (double)c->n_graph_launches;
+    else { c->err = std::string("unknown stat ") + name; return NTL_ERR_ARG; }
     return NTL_OK;
 }
 int ntl_mark(ntl_ctx* c, int which) {

@@ -84,8 +84,25 @@ struct DeviceSketch {         // result of a sketch pass, resident on the device
     DevBuf hash;              // uint64 h1 per minimizer
     DevBuf posf;              // uint32 pos | fwd << 31
     DevBuf mx_off;            // uint32 [nseq + 1]
-    uint32_t n_mx = 0;
+    uint32_t n_mx = 0;        // exact after a synchronous pass; an UPPER BOUND after a deferred (sync-free) pass
     uint32_t nseq = 0;
+    const uint32_t* n_dev = nullptr;   // device word holding the exact count (null: n_mx is exact and host-only)
+};
+
+// Device-side state of one sync-free call (ntl_map_reads / ntl_map_resident fast path): the chunks of the call are
+// enqueued back to back without a host synchronisation in between; errors are sticky and make the host repeat the
+// call on the synchronous path, totals place each chunk's results behind the previous chunk's.
+struct CallState {
+    uint32_t err;                                            // CALLERR_* bits
+    uint32_t log_n;                                          // cursor of the device event log
+    uint32_t hits_total, ev_total, runs_total, mx_total;     // totals over the finished chunks
+    uint32_t pad[10];
+};
+enum : uint32_t { CALLERR_SKETCH = 1, CALLERR_MAP = 2, CALLERR_RESULTS = 4 };
+struct HostResults {          // pinned host arrays (device-addressable) the fast path writes results into
+    uint32_t *hit_off, *nruns, *ev_off, *ev_cnt;
+    Run* runs; Hit* hits; Event* events;
+    uint32_t hits_cap, ev_cap;
 };
 
 struct TargetIndex {
@@ -146,6 +163,15 @@ struct ntl_ctx {
     // tally state (pairs accumulated over calls)
     ntl::DevBuf tl_events;                 // all events appended so far
     uint64_t tl_n_events = 0;
+    // sync-free call state
+    ntl::DevBuf call_state;                // ntl::CallState
+    uint64_t tl_pending_bound = 0;         // events the chunks in flight may still append (capacity reserved for them)
+    uint32_t ev_cap_hint = 0;              // event buffer size that was enough so far
+    int async_mode = 1;                    // 0: always take the synchronous path (option "async")
+    uint64_t n_async_calls = 0, n_async_fallbacks = 0, n_graph_launches = 0;   // ntl_get_stat
+    int graph_mode = 1;                    // sync-free ntl_map_reads: one CUDA graph per chunk (option "graph")
+    bool capturing = false;                // c->stream is being captured: no synchronisation, no allocation-by-copy
+    bool no_stage_timing = false;          // chunk graphs of a pipelined call: several in flight, stage events meaningless
 };
 
 #define NTL_CUDA(ctx, call)                                                                      \
@@ -167,8 +193,12 @@ struct ntl_ctx {
 
 namespace ntl {
 // implemented in sketch.cu
+// call_state != null: deferred pass -- no host synchronisation, the output is sized by an upper bound, a workspace
+// overflow sets CALLERR_SKETCH in call_state->err and yields an empty sketch
 int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
-                  uint32_t k, uint32_t w, DeviceSketch& out);
+                  uint32_t k, uint32_t w, DeviceSketch& out, CallState* call_state = nullptr);
+// uploads the rolling table of k if it is not the current one (synchronises; must not run inside a stream capture)
+int sketch_prepare(ntl_ctx* c, uint32_t k);
 // implemented in map.cu
 int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg, const uint32_t* d_posf, uint64_t n,
                        const uint32_t* h_ctg_len, const uint32_t* h_name_rank, uint32_t ncontig);
@@ -186,8 +216,17 @@ static __global__ void k_fill_segs(FillSegs s) {
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n[q]; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint8_t)s.v[q];
     }
 }
-inline void tick(ntl_ctx* c, int stage) { cudaEventRecord(c->ev[2 * stage], c->stream); }
-inline void tock(ntl_ctx* c, int stage) { cudaEventRecord(c->ev[2 * stage + 1], c->stream); c->ev_used[stage] = true; }
+// inside a stream capture the records become event-record nodes of the graph (cudaEventRecordExternal), so the stage
+// times of a graph launch can be read like those of plain launches
+inline void tick(ntl_ctx* c, int stage) {
+    if (c->no_stage_timing) return;
+    cudaEventRecordWithFlags(c->ev[2 * stage], c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+inline void tock(ntl_ctx* c, int stage) {
+    if (c->no_stage_timing) return;
+    cudaEventRecordWithFlags(c->ev[2 * stage + 1], c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+    c->ev_used[stage] = true;
+}
 // after a stream synchronize: fold the recorded stage times into the accumulators
 inline void collect_timing(ntl_ctx* c) {
     for (int s = 0; s < T_NUM; s++) {

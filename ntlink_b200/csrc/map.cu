@@ -68,10 +68,12 @@ __global__ void k_expand_ctg(const uint32_t* __restrict__ mx_off, uint32_t nseq,
 }
 
 // ------------------------------------------------------------------------------------------- lookup
+// n_bound: host-side size (exact, or an upper bound after a deferred sketch); n_src: device word with the exact count
 __global__ void __launch_bounds__(256) k_lookup(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ posf,
-                                                uint32_t n, IndexView ix, Hit* __restrict__ tmp,
-                                                uint32_t* __restrict__ flag, uint32_t* __restrict__ n_dev) {
+                                                uint32_t n_bound, const uint32_t* __restrict__ n_src, IndexView ix,
+                                                Hit* __restrict__ tmp, uint32_t* __restrict__ flag, uint32_t* __restrict__ n_dev) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = n_src ? min(*n_src, n_bound) : n_bound;
     if (i == 0) *n_dev = n;
     if (i >= n) return;
     uint32_t ctg, cposf;
@@ -82,10 +84,10 @@ __global__ void __launch_bounds__(256) k_lookup(const uint64_t* __restrict__ has
 }
 
 __global__ void __launch_bounds__(256) k_compact_hits(const Hit* __restrict__ tmp, const uint32_t* __restrict__ flag,
-                                                      const uint32_t* __restrict__ pref, uint32_t n,
+                                                      const uint32_t* __restrict__ pref, const uint32_t* __restrict__ n_dev,
                                                       Hit* __restrict__ hits) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= *n_dev) return;
     if (flag[i]) hits[pref[i]] = tmp[i];
 }
 
@@ -145,12 +147,52 @@ __global__ void __launch_bounds__(128) k_events(const Hit* __restrict__ hits, co
 
 __global__ void __launch_bounds__(128) k_compact_events(const Event* __restrict__ events, const uint32_t* __restrict__ ev_off,
                                                         const uint32_t* __restrict__ ev_cnt, const uint32_t* __restrict__ ev_pref,
-                                                        uint32_t nreads, Event* __restrict__ log, MapStatus* __restrict__ st) {
+                                                        uint32_t nreads, Event* __restrict__ log, MapStatus* __restrict__ st,
+                                                        const CallState* __restrict__ call) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r == 0) st->n_events = ev_pref[nreads];
     if (r >= nreads) return;
+    if (call) log += call->log_n;                 // sync-free call: the log cursor lives on the device
     const uint32_t n = ev_cnt[r];
     for (uint32_t i = 0; i < n; i++) log[ev_pref[r] + i] = events[ev_off[r] + i];
+}
+
+// ---- sync-free call: results of a chunk -> pinned host arrays (device-addressable), then advance the call totals
+__global__ void __launch_bounds__(128) k_results_host(const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ nruns,
+                                                      const Run* __restrict__ runs, const Hit* __restrict__ hits,
+                                                      const uint32_t* __restrict__ ev_cnt, const uint32_t* __restrict__ ev_pref,
+                                                      const Event* __restrict__ log, uint32_t rb, uint32_t nreads,
+                                                      HostResults H, CallState* __restrict__ call) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > nreads) return;
+    const uint32_t hits_total = call->hits_total, ev_total = call->ev_total;
+    const uint32_t o = hit_off[r], ep = ev_pref[r];
+    H.hit_off[rb + r] = hits_total + o;
+    H.ev_off[rb + r] = ev_total + ep;
+    if (r == nreads) return;
+    const uint32_t nr = nruns[r], nh = hit_off[r + 1] - o, ne = ev_cnt[r];
+    H.nruns[rb + r] = nr;
+    H.ev_cnt[rb + r] = ne;
+    if ((uint64_t)hits_total + o + nh > H.hits_cap || (uint64_t)ev_total + ep + ne > H.ev_cap) { atomicOr(&call->err, CALLERR_RESULTS); return; }
+    for (uint32_t i = 0; i < nr; i++) H.runs[hits_total + o + i] = runs[o + i];
+    for (uint32_t i = 0; i < nh; i++) H.hits[hits_total + o + i] = hits[o + i];
+    const Event* src = log + call->log_n + ep;
+    for (uint32_t i = 0; i < ne; i++) H.events[ev_total + ep + i] = src[i];
+}
+__global__ void k_chunk_finish(const MapStatus* __restrict__ st, const uint32_t* __restrict__ n_mx, CallState* __restrict__ call) {
+    if (st->err) atomicOr(&call->err, CALLERR_MAP | (st->err << 8));
+    call->hits_total += st->n_hits; call->ev_total += st->n_events; call->log_n += st->n_events;
+    call->runs_total += st->n_runs; call->mx_total += *n_mx;
+}
+__global__ void k_call_begin(CallState* __restrict__ call, uint32_t log_n) {
+    CallState z = {};
+    z.log_n = log_n;
+    *call = z;
+}
+__global__ void k_call_publish(const CallState* __restrict__ call, uint32_t* __restrict__ host) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(call);
+    if (threadIdx.x < sizeof(CallState) / 4) host[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------- tally
@@ -332,6 +374,8 @@ int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids) {
     return NTL_OK;
 }
 
+int call_reserve_events(ntl_ctx* c, uint32_t nreads);
+
 // Liftover of host mappings (ntl_map_out layout) through the AGP table. The lifted runs/hits stay in c->mw (hit_off,
 // nruns, runs, hits) -- exactly where map_device(pre->resident) expects them -- and the counters are returned.
 int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const Run* runs, const Hit* hits, uint32_t nreads,
@@ -387,8 +431,11 @@ int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, 
 // Results are left in c->mw (hits, runs, nruns, hit_off, events log segment); the counters are returned.
 // With `pre` set the lookup and chaining are skipped: the accepted runs/hits come from the host (checkpoint path,
 // bin/ntlink_pair.py:437-488) and only the pair events are computed.
+// With `call` set (sync-free call) nothing is waited for: the event buffer is sized from what was enough before, an
+// overflow or a failed assertion sets CALLERR_MAP in call->err, the events go to the log at the device cursor call->log_n
+// and the chunk's totals are added to *call by k_chunk_finish (call_chunk_finish); counts_out stays zero.
 int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, uint32_t nreads, uint64_t first_ordinal,
-               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out, const PreMappings* pre) {
+               const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out, const PreMappings* pre, CallState* call) {
     if (!c->index.built) { c->err = "map: no target index (call ntl_index_build first)"; return NTL_ERR_STATE; }
     MapWork& M = c->mw;
     const uint32_t n = pre ? pre->n_hits : sk.n_mx;
@@ -413,7 +460,7 @@ int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, u
     uint32_t* ev_off = evmax + (nreads + 2);
     uint32_t* ev_cnt = ev_off + (nreads + 2);
     uint32_t* ev_pref = ev_cnt + (nreads + 2);
-    uint32_t ev_cap = std::max<uint32_t>(1 << 16, 4 * nreads);
+    uint32_t ev_cap = std::max<uint32_t>(std::max<uint32_t>(1 << 16, 4 * nreads), c->ev_cap_hint);
     int attempt = 0;
 
     {
@@ -441,13 +488,13 @@ int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, u
     {
     IndexView ix{c->index.table.as<IdxEntry>(), c->index.slots - 1, c->index.special.as<IdxSpecial>()};
     tick(c, T_LOOKUP);
-    k_lookup<<<div_up(std::max<uint32_t>(n, 1), 256), 256, 0, c->stream>>>(sk.hash.as<uint64_t>(), sk.posf.as<uint32_t>(), n, ix,
+    k_lookup<<<div_up(std::max<uint32_t>(n, 1), 256), 256, 0, c->stream>>>(sk.hash.as<uint64_t>(), sk.posf.as<uint32_t>(), n, sk.n_dev, ix,
                                                                          M.hit_tmp.as<Hit>(), M.hit_flag.as<uint32_t>(), n_dev);
     c->launches++;
     NTL_TRY(exclusive_scan_u32(c, M.hit_flag.as<uint32_t>(), M.hit_pref.as<uint32_t>(), n_dev, n, M.blocksums));
     if (n) {
         k_compact_hits<<<div_up(n, 256), 256, 0, c->stream>>>(M.hit_tmp.as<Hit>(), M.hit_flag.as<uint32_t>(),
-                                                            M.hit_pref.as<uint32_t>(), n, M.hits.as<Hit>());
+                                                            M.hit_pref.as<uint32_t>(), n_dev, M.hits.as<Hit>());
         c->launches++;
     }
     k_hit_offsets<<<div_up((uint64_t)nreads + 1, 256), 256, 0, c->stream>>>(sk.mx_off.as<uint32_t>(), M.hit_pref.as<uint32_t>(), nreads,
@@ -475,6 +522,21 @@ retry_events:
         c->launches++;
     }
     NTL_TRY(exclusive_scan_u32(c, ev_cnt, ev_pref, nreads_dev, nreads, M.blocksums));
+    if (call) {
+        // room for everything the chunks in flight may append, then append at the device cursor
+        NTL_TRY(call_reserve_events(c, nreads));
+        c->tl_pending_bound += ev_cap;
+        if (nreads) {
+            k_compact_events<<<div_up(nreads, 128), 128, 0, c->stream>>>(M.events.as<Event>(), ev_off, ev_cnt, ev_pref, nreads,
+                                                                       c->tl_events.as<Event>(), st, call);
+            c->launches++;
+        }
+        tock(c, T_CHAIN);
+        NTL_CUDA(c, cudaGetLastError());
+        if (counts_out) *counts_out = MapStatus{};
+        if (log_base_out) *log_base_out = 0;
+        return NTL_OK;
+    }
     // counters -> host (one synchronisation), then append the events to the device log
     k_publish_map<<<1, 32, 0, c->stream>>>(st, ev_pref + nreads, ev_off + nreads, c->h_status.as<uint32_t>());
     c->launches++;
@@ -489,6 +551,7 @@ retry_events:
     if (hs.err & MAPERR_EVENTS) {
         if (++attempt > 2) { c->err = "map: event buffer exhausted"; return NTL_ERR_WORKSPACE; }
         ev_cap = ev_need + 1024;
+        c->ev_cap_hint = std::max(c->ev_cap_hint, ev_cap + ev_cap / 4);
         k_set_u32<<<1, 1, 0, c->stream>>>(&st->err, 0u);
         c->launches++;
         goto retry_events;
@@ -496,7 +559,7 @@ retry_events:
     NTL_TRY(grow_preserve(c, c->tl_events, c->tl_n_events * sizeof(Event), (c->tl_n_events + n_events + 1) * sizeof(Event)));
     if (nreads) {
         k_compact_events<<<div_up(nreads, 128), 128, 0, c->stream>>>(M.events.as<Event>(), ev_off, ev_cnt, ev_pref, nreads,
-                                                                   c->tl_events.as<Event>() + c->tl_n_events, st);
+                                                                   c->tl_events.as<Event>() + c->tl_n_events, st, nullptr);
         c->launches++;
     }
     tock(c, T_CHAIN);
@@ -505,6 +568,63 @@ retry_events:
     *counts_out = hs;
     *log_base_out = c->tl_n_events;
     c->tl_n_events += n_events;
+    return NTL_OK;
+}
+
+// ---- sync-free call plumbing (used by capi.cu)
+// room in the device event log for one more chunk of `nreads` reads (called by map_device; capi.cu calls it ahead of
+// a stream capture, where growing the log -- a copy and a synchronisation -- is not possible)
+int call_reserve_events(ntl_ctx* c, uint32_t nreads) {
+    const uint32_t ev_cap = std::max<uint32_t>(std::max<uint32_t>(1 << 16, 4 * nreads), c->ev_cap_hint);
+    const size_t need = (c->tl_n_events + c->tl_pending_bound + ev_cap + 1) * sizeof(Event);
+    if (need <= c->tl_events.cap) return NTL_OK;
+    if (c->capturing) { c->err = "internal: event log not reserved before capture"; return NTL_ERR_STATE; }
+    return grow_preserve(c, c->tl_events, (c->tl_n_events + c->tl_pending_bound) * sizeof(Event), need);
+}
+int call_begin(ntl_ctx* c, CallState** call_out) {
+    NTL_CUDA(c, c->call_state.ensure(sizeof(CallState)));
+    NTL_CUDA(c, c->h_status.ensure(256));
+    if (c->tl_n_events >= (1ull << 31)) { c->err = "event log too large"; return NTL_ERR_WORKSPACE; }
+    c->tl_pending_bound = 0;
+    k_call_begin<<<1, 1, 0, c->stream>>>(c->call_state.as<CallState>(), (uint32_t)c->tl_n_events);
+    c->launches++;
+    *call_out = c->call_state.as<CallState>();
+    return NTL_OK;
+}
+// after map_device(call): chunk results -> host arrays (H may be null: counters only), totals advanced
+int call_chunk_finish(ntl_ctx* c, CallState* call, uint32_t rb, uint32_t nreads, const HostResults* H) {
+    MapWork& M = c->mw;
+    MapStatus* st = M.status.as<MapStatus>();
+    const uint32_t* n_dev = (const uint32_t*)((char*)M.status.p + sizeof(MapStatus));
+    const uint32_t* evmax = M.ev_cnt.as<uint32_t>();
+    const uint32_t* ev_cnt = evmax + 2 * ((size_t)nreads + 2);
+    const uint32_t* ev_pref = evmax + 3 * ((size_t)nreads + 2);
+    if (H) {
+        k_results_host<<<div_up((uint64_t)nreads + 1, 128), 128, 0, c->stream>>>(M.hit_off.as<uint32_t>(), M.nruns.as<uint32_t>(), M.runs.as<Run>(),
+                                                                               M.hits.as<Hit>(), ev_cnt, ev_pref, c->tl_events.as<Event>(), rb,
+                                                                               nreads, *H, call);
+        c->launches++;
+    }
+    k_chunk_finish<<<1, 1, 0, c->stream>>>(st, n_dev, call);
+    c->launches++;
+    NTL_CUDA(c, cudaGetLastError());
+    return NTL_OK;
+}
+// one synchronisation for the whole call; on success the host-side log size follows the device cursor
+int call_end(ntl_ctx* c, CallState* call, CallState* host_out) {
+    k_call_publish<<<1, 32, 0, c->stream>>>(call, c->h_status.as<uint32_t>());
+    c->launches++;
+    NTL_CUDA(c, cudaGetLastError());
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    *host_out = *c->h_status.as<CallState>();
+    c->tl_pending_bound = 0;
+    if (host_out->err == 0) {
+        const uint32_t appended = host_out->log_n - (uint32_t)c->tl_n_events;
+        c->ev_cap_hint = std::max(c->ev_cap_hint, std::min<uint32_t>(appended + appended / 2 + 1024, 1u << 28));
+        c->tl_n_events = host_out->log_n;
+    } else if (host_out->err & (MAPERR_EVENTS << 8)) {
+        c->ev_cap_hint = std::max<uint32_t>(c->ev_cap_hint * 4, 1u << 18);
+    }
     return NTL_OK;
 }
 

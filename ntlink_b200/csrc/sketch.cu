@@ -466,11 +466,16 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(SkParams P, CandView V, c
     }
 }
 
+// call != null (deferred pass): a sketch that hit a workspace limit is turned into an empty one and the call is flagged
 __global__ void k_seq_offsets(const uint32_t* __restrict__ strip_off, const uint32_t* __restrict__ selbase,
-                              uint32_t nseq, uint32_t* __restrict__ mx_off) {
+                              uint32_t nseq, uint32_t* __restrict__ mx_off, SketchStatus* __restrict__ st,
+                              CallState* __restrict__ call) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q <= nseq) mx_off[q] = selbase[strip_off[q]];
+    const bool bad = call != nullptr && st->err != 0;
+    if (q <= nseq) mx_off[q] = bad ? 0u : selbase[strip_off[q]];
+    if (q == 0 && bad) atomicOr(&call->err, CALLERR_SKETCH);
 }
+__global__ void k_sketch_gate(SketchStatus* __restrict__ st) { if (st->err) st->n_mx = 0; }
 
 // status block + number of strips + number of minimizers -> host-mapped memory
 __global__ void k_publish_sketch(const SketchStatus* __restrict__ st, const uint32_t* __restrict__ nstrips_p,
@@ -489,13 +494,26 @@ inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) /
 
 }  // namespace
 
+int sketch_prepare(ntl_ctx* c, uint32_t k) {
+    SketchWork& W = c->sw;
+    if (W.tbl_k == k && W.tbl.p) return NTL_OK;
+    if (c->capturing) { c->err = "internal: rolling table not prepared before capture"; return NTL_ERR_STATE; }
+    NTL_CUDA(c, W.tbl.ensure(sizeof(RollEntry) * ROLL_TABLE_ENTRIES));
+    RollEntry tbl[ROLL_TABLE_ENTRIES];
+    build_roll_table(k, tbl);
+    NTL_CUDA(c, cudaMemcpyAsync(W.tbl.p, tbl, sizeof tbl, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));   // tbl is a stack array
+    W.tbl_k = k;
+    return NTL_OK;
+}
+
 // Sketch `nseq` sequences that are already on the device (ASCII d_seq, offsets d_off). The result stays on the
 // device in `out`. One host synchronisation (to learn the number of minimizers before the final compaction).
 int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
-                  uint32_t k, uint32_t w, DeviceSketch& out) {
+                  uint32_t k, uint32_t w, DeviceSketch& out, CallState* call_state) {
     if (k == 0 || w == 0 || k > 100000 || total_bases >= (1ull << 32)) { c->err = "sketch: bad k/w or batch too large"; return NTL_ERR_ARG; }
     SketchWork& W = c->sw;
-    out.nseq = nseq; out.n_mx = 0;
+    out.nseq = nseq; out.n_mx = 0; out.n_dev = nullptr;
     NTL_CUDA(c, out.mx_off.ensure(((size_t)nseq + 1) * 4));
     if (nseq == 0 || total_bases == 0) {
         NTL_CUDA(c, cudaMemsetAsync(out.mx_off.p, 0, ((size_t)nseq + 1) * 4, c->stream));
@@ -545,13 +563,7 @@ retry:
 
     SketchStatus* st = W.status.as<SketchStatus>();
     uint32_t* nseq_dev = (uint32_t*)((char*)W.status.p + sizeof(SketchStatus));   // scan length for the strip table
-    if (W.tbl_k != k) {
-        RollEntry tbl[ROLL_TABLE_ENTRIES];
-        build_roll_table(k, tbl);
-        NTL_CUDA(c, cudaMemcpyAsync(W.tbl.p, tbl, sizeof tbl, cudaMemcpyHostToDevice, c->stream));
-        NTL_CUDA(c, cudaStreamSynchronize(c->stream));   // tbl is a stack array
-        W.tbl_k = k;
-    }
+    NTL_TRY(sketch_prepare(c, k));
     // layout: [64 B front pad | packed bases | >= 192 B tail pad]; d_packed points at the first real chunk
     uint32_t* const d_packed = reinterpret_cast<uint32_t*>(W.packed.as<char>() + 64);
     {
@@ -608,6 +620,13 @@ retry:
 
     tick(c, T_EMIT);
     NTL_TRY(exclusive_scan_u32(c, W.selcnt.as<uint32_t>(), W.selbase.as<uint32_t>(), &st->nstrips, nstrips_max, W.blocksums));
+    if (call_state) {
+        // deferred pass: the output is sized by an upper bound (random sequence has 2/(w+1) minimizers per position;
+        // 30 % head room, never more than one per position) and nobody waits for the counters
+        out_cap = (uint32_t)std::min<uint64_t>(total_bases, (uint64_t)(2.6 * (double)total_bases / ((double)w + 1.0)) + 8ull * nseq + 4096);
+        out.n_mx = out_cap;
+        goto emit;
+    }
     // total = selbase[nstrips]; fetch the counters to size the output
     // the counters reach the host through a tiny kernel that writes pinned (UVA-mapped) host memory: no copy engine
     // is involved, so this never queues behind a large host->device copy of the next batch
@@ -629,9 +648,11 @@ retry:
         out_cap = total;
         out.n_mx = total;
     }
+emit:
     NTL_CUDA(c, out.hash.ensure((size_t)out_cap * 8 + 8));
     NTL_CUDA(c, out.posf.ensure((size_t)out_cap * 4 + 4));
     P.out_cap = out_cap;
+    out.n_dev = &st->n_mx;
     {
         int G = mu <= 12 ? 4 : mu <= 40 ? 8 : mu <= 96 ? 16 : 32;
         if (const char* eg = getenv("NTL_EMIT_G")) G = atoi(eg);
@@ -643,8 +664,9 @@ retry:
 #undef NTL_EMIT
     }
     k_seq_offsets<<<div_up((uint64_t)nseq + 1, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), W.selbase.as<uint32_t>(), nseq,
-                                                                        out.mx_off.as<uint32_t>());
+                                                                        out.mx_off.as<uint32_t>(), st, call_state);
     c->launches += 2;
+    if (call_state) { k_sketch_gate<<<1, 1, 0, c->stream>>>(st); c->launches += 1; }
     tock(c, T_EMIT);
     NTL_CUDA(c, cudaGetLastError());
     return NTL_OK;

@@ -47,9 +47,25 @@ def main():
         print(json.dumps({"case": label, "ms_per_step": round(ms, 3),
                           "stages": {k: round(tm[k] / n, 3) for k in ("pack", "dense", "select", "gap", "emit", "lookup", "chain", "tally", "index")}}))
 
-    run("no copy", False)
-    run("H2D in flight", True)
-    run("no copy", False)
+    for mode in (1, 0):
+        ctx.set_option("async", mode)
+        run(f"async={mode} no copy", False)
+        run(f"async={mode} H2D in flight", True)
+    # host-side cost of enqueueing: time the enqueue of one step without waiting for it
+    import time
+    ctx.set_option("async", 1)
+    for with_copy in (False, True):
+        torch.cuda.synchronize()
+        if with_copy:
+            with torch.cuda.stream(side):
+                for _ in range(40):
+                    d.copy_(h, non_blocking=True)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ctx.events_reset(); ctx.index_build_resident(32, 100); ctx.map_resident(prm)
+        dt = (time.perf_counter() - t0) / 10
+        torch.cuda.synchronize()
+        print(json.dumps({"case": "wall per step, copy=%s" % with_copy, "ms": round(dt * 1e3, 3)}))
     ctx.close()
 
 
