@@ -256,31 +256,13 @@ static int sketch_to_host(ntl_ctx* c, const char* seq, const uint64_t* offsets, 
             NTL_CUDA(c, cudaMemcpyAsync(tmp_off.data(), c->dsk.mx_off.p, ((size_t)(e - b) + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
         }
         if (build_index) {
-            // contig ids (global) for this batch's minimizers, appended to the device-side triple arrays
+            // single batch (checked above): the index is built straight from the sketch arrays, only the contig id of
+            // every minimizer has to be materialised
             NTL_TRY(expand_contig_ids(c, c->dsk, R->ctg_ids));
-            // grow in_* preserving contents
-            DevBuf* dst[3] = {&R->in_hash, &R->in_posf, &R->in_ctg};
-            const size_t esz[3] = {8, 4, 4};
-            for (int a = 0; a < 3; a++) {
-                const size_t need = (idx_n + n + 1) * esz[a];
-                if (need > dst[a]->cap) {
-                    DevBuf nbuf;
-                    NTL_CUDA(c, nbuf.ensure(need + need / 2));
-                    if (idx_n) NTL_CUDA(c, cudaMemcpyAsync(nbuf.p, dst[a]->p, idx_n * esz[a], cudaMemcpyDeviceToDevice, c->stream));
-                    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
-                    dst[a]->release();
-                    *dst[a] = nbuf;
-                }
-            }
-            if (n) {
-                NTL_CUDA(c, cudaMemcpyAsync(R->in_hash.as<uint64_t>() + idx_n, c->dsk.hash.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
-                NTL_CUDA(c, cudaMemcpyAsync(R->in_posf.as<uint32_t>() + idx_n, c->dsk.posf.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
-                NTL_CUDA(c, cudaMemcpyAsync(R->in_ctg.as<uint32_t>() + idx_n, R->ctg_ids.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
-            }
-            idx_n += n;
+            idx_n = n;
         }
         tock(c, T_TOTAL);
-        NTL_TRY(finish_call(c));
+        if (out || !build_index) NTL_TRY(finish_call(c));
         if (out) {
             for (uint32_t i = 0; i < e - b; i++) seq_off[b + i + 1] = total + tmp_off[i + 1];
         }
@@ -293,7 +275,7 @@ static int sketch_to_host(ntl_ctx* c, const char* seq, const uint64_t* offsets, 
     if (build_index) {
         std::vector<uint32_t> len(nseq);
         for (uint32_t i = 0; i < nseq; i++) len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
-        NTL_TRY(index_build_device(c, R->in_hash.as<uint64_t>(), R->in_ctg.as<uint32_t>(), R->in_posf.as<uint32_t>(), idx_n,
+        NTL_TRY(index_build_device(c, c->dsk.hash.as<uint64_t>(), R->ctg_ids.as<uint32_t>(), c->dsk.posf.as<uint32_t>(), idx_n,
                                    len.data(), name_rank, nseq));
         NTL_TRY(finish_call(c));
     }

@@ -208,10 +208,10 @@ int exclusive_scan_u32(ntl_ctx* c, const uint32_t* in, uint32_t* out, const uint
 // Small fills as ONE kernel instead of cudaMemsetAsync: the driver may route a memset through a copy engine, where it
 // would queue behind the large host->device copy of the next batch (measured: kernels of a batch ran ~2x longer while
 // a copy was in flight).
-struct FillSegs { void* p[4]; uint64_t n[4]; uint32_t v[4]; };
+struct FillSegs { void* p[6]; uint64_t n[6]; uint32_t v[6]; };
 static __global__ void k_fill_segs(FillSegs s) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 6; q++) {
         uint8_t* p = (uint8_t*)s.p[q];
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n[q]; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint8_t)s.v[q];
     }

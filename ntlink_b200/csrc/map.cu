@@ -344,9 +344,14 @@ int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg
     NTL_CUDA(c, X.ctg_len.ensure(((size_t)ncontig + 1) * 4));
     NTL_CUDA(c, X.name_rank.ensure(((size_t)ncontig + 1) * 4));
     tick(c, T_INDEX);
-    NTL_CUDA(c, cudaMemsetAsync(X.table.p, 0xFF, slots * sizeof(IdxEntry), c->stream));
-    NTL_CUDA(c, cudaMemsetAsync(X.dupflag.p, 0, slots, c->stream));
-    NTL_CUDA(c, cudaMemsetAsync(X.special.p, 0, sizeof(IdxSpecial) + 16, c->stream));
+    {
+        FillSegs fs{};
+        fs.p[0] = X.table.p; fs.n[0] = slots * sizeof(IdxEntry); fs.v[0] = 0xFF;
+        fs.p[1] = X.dupflag.p; fs.n[1] = slots; fs.v[1] = 0;
+        fs.p[2] = X.special.p; fs.n[2] = sizeof(IdxSpecial) + 16; fs.v[2] = 0;
+        k_fill_segs<<<std::min<uint32_t>(div_up(slots * sizeof(IdxEntry), 256), 148 * 8), 256, 0, c->stream>>>(fs);
+        c->launches++;
+    }
     NTL_CUDA(c, cudaMemcpyAsync(X.ctg_len.p, h_ctg_len, (size_t)ncontig * 4, cudaMemcpyHostToDevice, c->stream));
     NTL_CUDA(c, cudaMemcpyAsync(X.name_rank.p, h_name_rank, (size_t)ncontig * 4, cudaMemcpyHostToDevice, c->stream));
     if (n) {
@@ -649,11 +654,16 @@ int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>&
     TL_CUDA(cursor.ensure(slots * 4)); TL_CUDA(gkey.ensure(n * 8)); TL_CUDA(gval.ensure(n * 4));
     TL_CUDA(nonempty.ensure(slots * 4)); TL_CUDA(ppref.ensure((slots + 1) * 4)); TL_CUDA(ndev.ensure(16));
     tick(c, T_TALLY);
-    TL_CUDA(cudaMemsetAsync(keys.p, 0xFF, slots * 8, c->stream));
-    TL_CUDA(cudaMemsetAsync(pfirst.p, 0xFF, slots * 8, c->stream));
-    TL_CUDA(cudaMemsetAsync(pn.p, 0, slots * 4, c->stream));
-    TL_CUDA(cudaMemsetAsync(panchor.p, 0, slots * 4, c->stream));
-    TL_CUDA(cudaMemsetAsync(cursor.p, 0, slots * 4, c->stream));
+    {
+        FillSegs fs{};
+        fs.p[0] = keys.p; fs.n[0] = slots * 8; fs.v[0] = 0xFF;
+        fs.p[1] = pfirst.p; fs.n[1] = slots * 8; fs.v[1] = 0xFF;
+        fs.p[2] = pn.p; fs.n[2] = slots * 4; fs.v[2] = 0;
+        fs.p[3] = panchor.p; fs.n[3] = slots * 4; fs.v[3] = 0;
+        fs.p[4] = cursor.p; fs.n[4] = slots * 4; fs.v[4] = 0;
+        k_fill_segs<<<std::min<uint32_t>(div_up(slots * 8, 256), 148 * 8), 256, 0, c->stream>>>(fs);
+        c->launches++;
+    }
     const Event* ev = c->tl_events.as<Event>();
     k_set_u32<<<1, 1, 0, c->stream>>>(ndev.as<uint32_t>(), (uint32_t)slots);
     k_tally_insert<<<div_up(n, 256), 256, 0, c->stream>>>(ev, n, keys.as<unsigned long long>(), slots - 1, pn.as<uint32_t>(),
@@ -669,18 +679,25 @@ int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>&
     rc = exclusive_scan_u32(c, nonempty.as<uint32_t>(), ppref.as<uint32_t>(), ndev.as<uint32_t>(), (uint32_t)slots, bs);
     if (rc != NTL_OK) { cleanup(); return rc; }
     uint32_t n_pairs = 0;
-    TL_CUDA(cudaMemcpyAsync(&n_pairs, ppref.as<uint32_t>() + slots, 4, cudaMemcpyDeviceToHost, c->stream));
-    TL_CUDA(cudaStreamSynchronize(c->stream));
-    TL_CUDA(out.ensure((size_t)n_pairs * sizeof(ntl_pair) + 16));
+    // a pair needs at least one event: with few events the table is copied at that bound and one synchronisation is enough
+    const bool one_sync = n * sizeof(ntl_pair) <= (8u << 20);
+    if (!one_sync) {
+        TL_CUDA(cudaMemcpyAsync(&n_pairs, ppref.as<uint32_t>() + slots, 4, cudaMemcpyDeviceToHost, c->stream));
+        TL_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    const size_t pair_cap = one_sync ? (size_t)n : (size_t)n_pairs;
+    TL_CUDA(out.ensure(pair_cap * sizeof(ntl_pair) + 16));
     k_pairs_compact<<<div_up(slots, 128), 128, 0, c->stream>>>(keys.as<unsigned long long>(), pn.as<uint32_t>(), panchor.as<uint32_t>(),
                                                               pfirst.as<unsigned long long>(), gap_off.as<uint32_t>(), ppref.as<uint32_t>(),
                                                               (uint32_t)slots, (ntl_pair*)out.p);
     c->launches++;
     tock(c, T_TALLY);
-    pairs.resize(n_pairs); gaps.resize(n);
-    TL_CUDA(cudaMemcpyAsync(pairs.data(), out.p, (size_t)n_pairs * sizeof(ntl_pair), cudaMemcpyDeviceToHost, c->stream));
+    pairs.resize(pair_cap); gaps.resize(n);
+    if (one_sync) TL_CUDA(cudaMemcpyAsync(&n_pairs, ppref.as<uint32_t>() + slots, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (pair_cap) TL_CUDA(cudaMemcpyAsync(pairs.data(), out.p, pair_cap * sizeof(ntl_pair), cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA(cudaMemcpyAsync(gaps.data(), gval.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA(cudaStreamSynchronize(c->stream));
+    pairs.resize(n_pairs);
 #undef TL_CUDA
     cleanup();
     std::sort(pairs.begin(), pairs.end(), [](const ntl_pair& a, const ntl_pair& b) { return a.first_key < b.first_key; });

@@ -567,7 +567,7 @@ retry:
     // layout: [64 B front pad | packed bases | >= 192 B tail pad]; d_packed points at the first real chunk
     uint32_t* const d_packed = reinterpret_cast<uint32_t*>(W.packed.as<char>() + 64);
     {
-        FillSegs fs;
+        FillSegs fs{};
         fs.p[0] = st; fs.n[0] = sizeof(SketchStatus) + 64; fs.v[0] = 0;
         fs.p[1] = W.has_cand.p; fs.n[1] = (size_t)nseq + 1; fs.v[1] = 0;
         fs.p[2] = W.packed.p; fs.n[2] = 64; fs.v[2] = 0x44;
