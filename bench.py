@@ -242,7 +242,7 @@ def run_gpu(args, rank, world, local_rank):
     shard_target = args.shard_target == "always" or (args.shard_target == "auto" and int(contigs.offsets[-1]) >= (256 << 20))
     ctx = Context(local_rank)
     for opt, env in (("cand_c", "NTL_CAND_C"), ("strip_len", "NTL_STRIP_LEN"),
-                     ("pipeline_min_bases", "NTL_PIPE_MIN")):                      # tuning sweeps only
+                     ("pipeline_min_bases", "NTL_PIPE_MIN"), ("async", "NTL_ASYNC"), ("graph", "NTL_GRAPH")):   # sweeps / profiling only
         if os.environ.get(env):
             ctx.set_option(opt, float(os.environ[env]))
     prm = ctx.params(K, W, Z)

@@ -120,7 +120,7 @@ struct PreMappings {          // accepted runs/hits supplied by the host (checkp
 };
 
 struct TallyWork {
-    DevBuf keys, pn, panchor, pfirst, ev_slot, gap_off, cursor, gkey, gval, nonempty, ppref, out, ndev, bs;
+    DevBuf keys, pn, panchor, pfirst, ev_slot, gap_off, cursor, gkey, gval, nonempty, ppref, out, ndev, bs, skey, sval;
 };
 
 struct MapWork {
