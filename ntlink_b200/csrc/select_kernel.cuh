@@ -11,22 +11,28 @@
 namespace ntl {
 namespace {
 
+#ifndef SEL_MINB
+#define SEL_MINB 6
+#endif
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_STRIPS = 32;     // strips decided per block (upper bound; the launch passes the actual number)
 constexpr int SEL_CTX = 3;         // context strips staged on each side (upper bound, likewise)
 constexpr int SEL_NL = SEL_STRIPS + 2 * SEL_CTX;
-constexpr int SEL_CAP = 2560;      // candidates staged per block (40 KB)
+constexpr int SEL_CAP = 2560;      // most candidates a block can stage (40 KB); the launch sizes the buffer (scap)
 
-__global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restrict__ seq_off,
+__global__ void __launch_bounds__(SEL_THREADS, SEL_MINB) k_select(const uint64_t* __restrict__ seq_off,
                                                          const uint32_t* __restrict__ strip_off,
                                                          const uint32_t* __restrict__ strip_seq, SkParams P, CandView V,
                                                          uint8_t* __restrict__ sel, uint32_t* __restrict__ selcnt,
                                                          unsigned long long* __restrict__ selmask,
                                                          GapRec* __restrict__ gaps, uint32_t* __restrict__ gap_head,
-                                                         SketchStatus* __restrict__ st, uint32_t nsb, uint32_t nctx) {
+                                                         SketchStatus* __restrict__ st, uint32_t nsb, uint32_t nctx, uint32_t scap) {
     // nsb strips are decided per block with nctx strips of context on each side: chosen by the host so that the
     // expected number of staged candidates fits SEL_CAP and the context covers w - 1 positions (select_shape)
-    __shared__ uint4 sh_c[SEL_CAP];               // staged candidate: {h0.lo, h0.hi, valid-k-mer index, staged strip}
+    // staged candidates {h0.lo, h0.hi, valid-k-mer index, staged strip}: scap entries of dynamic shared memory, sized by
+    // the host from the expected candidate density so that as many blocks as possible are resident (the kernel waits on
+    // global loads while staging; more resident blocks hide that)
+    extern __shared__ uint4 sh_c[];
     __shared__ uint32_t sh_off[SEL_NL + 1];       // compact offset of every staged strip
     __shared__ uint32_t sh_cnt[SEL_NL];
     __shared__ uint32_t sh_q[SEL_NL], sh_fs[SEL_NL], sh_es[SEL_NL], sh_idx0[SEL_NL], sh_n[SEL_NL], sh_np[SEL_NL];
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
     }
     __syncthreads();
     const uint32_t total = sh_off[nl];
-    const bool staged = (sh_bad == 0) && (total <= SEL_CAP);
+    const bool staged = (sh_bad == 0) && (total <= scap);
     __syncthreads();
 
     if (staged) {
@@ -210,10 +216,14 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const uint64_t* __restri
 }
 
 // strips per block / context strips for a given expected number of candidates per strip
-inline void select_shape(double mu, uint32_t S, uint32_t w, uint32_t& nsb, uint32_t& nctx) {
+inline void select_shape(double mu, uint32_t S, uint32_t w, uint32_t& nsb, uint32_t& nctx, uint32_t& scap) {
     nctx = std::min<uint32_t>(SEL_CTX, std::max<uint32_t>(1, (w - 1 + S - 1) / S));
     const double fit = 0.85 * SEL_CAP / std::max(1.0, mu) - 2.0 * nctx;
     nsb = (uint32_t)std::min<double>(SEL_STRIPS, std::max(1.0, fit));
+    // room for the expected number of staged candidates + 6 sigma (Poisson) + slack; blocks that exceed it fall back
+    const double staged = (nsb + 2.0 * nctx) * mu;
+    scap = (uint32_t)std::min<double>(SEL_CAP, staged + 6.0 * std::sqrt(staged) + 64.0);
+    scap = (scap + 63u) & ~63u;
 }
 
 }  // namespace

@@ -602,11 +602,11 @@ retry:
     CandView V;
     V.cands = W.slots.as<Cand>(); V.cnt = W.cnt.as<uint32_t>(); V.ovf_off = W.ovf_off.as<uint32_t>();
     V.vbase = W.vbase.as<uint32_t>(); V.cap = cap; V.pool_base = P.pool_base;
-    uint32_t nsb, nctx;
-    select_shape(mu, S, w, nsb, nctx);
-    k_select<<<div_up(nstrips_max, nsb), SEL_THREADS, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
+    uint32_t nsb, nctx, scap;
+    select_shape(mu, S, w, nsb, nctx, scap);
+    k_select<<<div_up(nstrips_max, nsb), SEL_THREADS, (size_t)scap * sizeof(uint4), c->stream>>>(d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P, V, W.sel.as<uint8_t>(),
                                                              W.selcnt.as<uint32_t>(), W.selmask.as<unsigned long long>(), W.gaps.as<GapRec>(),
-                                                             W.gap_head.as<uint32_t>(), st, nsb, nctx);
+                                                             W.gap_head.as<uint32_t>(), st, nsb, nctx, scap);
     k_seq_gaps<<<div_up(nseq, 128), 128, 0, c->stream>>>(d_off, W.strip_off.as<uint32_t>(), P, V, W.has_cand.as<uint8_t>(),
                                                         W.gaps.as<GapRec>(), W.gap_head.as<uint32_t>(), st);
     c->launches += 2;
