@@ -38,6 +38,8 @@ GENOME_BP = 5_000_000
 COVERAGE = 30
 K, W, Z = 32, 100, 1000
 SEED = 20240502
+WORKLOAD = ("configs[1]: synthetic 5 Mbp genome, 1-200 kbp contigs, 30x ONT-like reads (4% sub, 3% ins, 3% del), "
+            "k=32 w=100 z=1000")
 
 
 def make_inputs(rank, world):
@@ -157,10 +159,11 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "long_read_gbp_per_s_sketched_mapped", "value": val, "unit": "Gbp/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic 5 Mbp genome, 1-200 kbp contigs, 30x ONT-like reads, k=32 w=100",
-                       "k": K, "w": W, "z": Z},
+            "config": {"workload": WORKLOAD, "read_bases_per_gpu": int(reads.offsets[-1]), "reads_per_gpu": len(reads),
+                       "contigs": len(contigs), "k": K, "w": W, "z": Z,
+                       "step": "target sketch + index build + read sketch + lookup + chain + events + tally (CPU port of the reference path)"},
             "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": threads, "kind": "port",
-                             "sample": f"first {n_reads} reads ({bases // args.steps} bp) against the full 5 Mbp target; "
+                             "sample": f"{min(n_reads, len(reads))} of {len(reads)} reads ({bases // args.steps} bp) per step against the full 5 Mbp target; "
                                        "C oracle sketcher on all threads + single-threaded Python mapper (the reference's "
                                        "ntlink_pair.py has no -t)"},
             "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -198,9 +201,8 @@ def build_index_distributed(ctx, contigs, rank, world, dist, torch):
 _gather_buf = {}
 
 
-def gather_events(ctx, rank, world, dist, torch):
-    """pair events of every rank -> rank 0's device event log, in rank order = global read order: the library writes
-    {count, events} into a fixed-capacity device buffer, ONE NCCL all_gather moves them, rank 0 imports the result."""
+def gather_events_sync(ctx, rank, world, dist, torch):
+    "the same exchange with the synchronising entry points (ntl_events_export / ntl_events_import_gathered); NTL_GATHER_SYNC=1"
     import ctypes as C
     dev = torch.device("cuda", torch.cuda.current_device())
     while True:
@@ -211,12 +213,47 @@ def gather_events(ctx, rank, world, dist, torch):
         n = C.c_uint64()
         ctx._check(ctx.lib.ntl_events_export(ctx.h, _gather_buf["send"].data_ptr(), cap, C.byref(n)), "ntl_events_export")
         dist.all_gather_into_tensor(_gather_buf["recv"], _gather_buf["send"])
-        counts = _gather_buf["recv"].view(world, -1)[:, 0].tolist()      # every rank sees every count: same decision
+        counts = _gather_buf["recv"].view(world, -1)[:, 0].tolist()
         if max(counts) <= cap:
             if rank == 0:
                 ovf = C.c_int(0)
                 ctx._check(ctx.lib.ntl_events_import_gathered(ctx.h, _gather_buf["recv"].data_ptr(), world, cap, C.byref(ovf)),
                            "ntl_events_import_gathered")
+            return
+        _gather_buf["cap"] = int(max(counts)) * 2
+        _gather_buf["send"] = None
+
+
+def gather_events(ctx, rank, world, dist, torch):
+    """pair events of every rank -> rank 0's device event log, in rank order = global read order: the library writes
+    {count, events} into a fixed-capacity device buffer, ONE NCCL all_gather moves them, rank 0 imports the result.
+    One host synchronisation per step (reading the gathered counts, which every rank needs to agree on a retry); the
+    library's stream and the collective's stream are ordered with events, not with the host."""
+    import ctypes as C
+    if os.environ.get("NTL_GATHER_SYNC"):
+        return gather_events_sync(ctx, rank, world, dist, torch)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if "stream" not in _gather_buf:
+        sp = C.c_void_p()
+        ctx._check(ctx.lib.ntl_stream(ctx.h, C.byref(sp)), "ntl_stream")
+        _gather_buf["stream"] = torch.cuda.ExternalStream(sp.value, device=dev)
+    lib_stream = _gather_buf["stream"]
+    while True:
+        cap = _gather_buf.get("cap", 8192)
+        if _gather_buf.get("send") is None or _gather_buf["send"].shape[0] != (cap + 1) * 6:
+            _gather_buf["send"] = torch.zeros((cap + 1) * 6, device=dev, dtype=torch.int32)
+            _gather_buf["recv"] = torch.zeros(world * (cap + 1) * 6, device=dev, dtype=torch.int32)
+            torch.cuda.synchronize()
+        n = C.c_uint64()
+        ctx._check(ctx.lib.ntl_events_export_async(ctx.h, _gather_buf["send"].data_ptr(), cap, C.byref(n)), "ntl_events_export_async")
+        torch.cuda.current_stream().wait_stream(lib_stream)
+        dist.all_gather_into_tensor(_gather_buf["recv"], _gather_buf["send"])
+        counts = _gather_buf["recv"].view(world, -1)[:, 0].tolist()      # every rank sees every count: same decision
+        if max(counts) <= cap:
+            if rank == 0:
+                cnt = np.array(counts, np.uint32)
+                ctx._check(ctx.lib.ntl_events_import_counts(ctx.h, _gather_buf["recv"].data_ptr(), world, cap, cnt.ctypes.data),
+                           "ntl_events_import_counts")
             return
         _gather_buf["cap"] = int(max(counts)) * 2
         _gather_buf["send"] = None
@@ -342,8 +379,7 @@ def run_gpu(args, rank, world, local_rank):
         line = {"metric": "long_read_gbp_per_s_sketched_mapped", "value": value, "unit": "Gbp/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": "configs[1]: synthetic 5 Mbp genome, 1-200 kbp contigs, 30x ONT-like reads "
-                                       "(4% sub, 3% ins, 3% del), k=32 w=100 z=1000",
+                "config": {"workload": WORKLOAD,
                            "read_bases_per_gpu": read_bases, "reads_per_gpu": len(reads), "contigs": len(contigs),
                            "k": K, "w": W, "z": Z, "l2": "inputs larger than L2 (150 MB ASCII reads per step)",
                            "step": "target sketch + index build + read sketch + lookup + chain + events + tally",
@@ -371,7 +407,7 @@ def run_gpu(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             dt, nb, _ = cpu_pipeline(contigs, reads, args.cpu_reads, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": nb / dt / 1e9, "unit": "Gbp/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"first {min(args.cpu_reads, len(reads))} reads ({nb} bp) against the full target, "
+                                    "sample": f"{min(args.cpu_reads, len(reads))} of {len(reads)} reads ({nb} bp) against the full target, "
                                               f"{dt:.1f} s; C oracle sketcher on all threads + single-threaded Python mapper"}
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -385,7 +421,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ntlink_b200", choices=["ntlink_b200", "reference"])
-    ap.add_argument("--cpu-reads", type=int, default=1500, help="reads in the bounded CPU sample")
+    ap.add_argument("--cpu-reads", type=int, default=1000000, help="reads in the bounded CPU sample (default: the whole 150 Mbp workload, ~2 s of CPU)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--shard-target", default="auto", choices=["auto", "always", "never"],
                     help="N>1: sketch the target in contig shards + NCCL all-gather (auto: targets >= 256 Mbp)")

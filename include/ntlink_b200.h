@@ -205,6 +205,12 @@ int ntl_events_append_device(ntl_ctx* ctx, const void* d_events, uint64_t n);
  * cap_events events (nothing is imported then: grow the buffers and repeat). */
 int ntl_events_export(ntl_ctx* ctx, void* d_dst, uint64_t cap_events, uint64_t* n_out);
 int ntl_events_import_gathered(ntl_ctx* ctx, const void* d_src, uint32_t world, uint64_t cap_events, int* overflow);
+/* The same exchange without host synchronisation inside the library: ntl_events_export_async only enqueues on the
+ * context's stream (ntl_stream; make the collective's stream wait for it), ntl_events_import_counts takes the per-rank
+ * counts the caller already read from the gathered headers and only enqueues the copies. */
+int ntl_stream(ntl_ctx* ctx, void** cuda_stream_out);
+int ntl_events_export_async(ntl_ctx* ctx, void* d_dst, uint64_t cap_events, uint64_t* n_out);
+int ntl_events_import_counts(ntl_ctx* ctx, const void* d_src, uint32_t world, uint64_t cap_events, const uint32_t* counts);
 int ntl_pairs_finish(ntl_ctx* ctx, ntl_pairs_out* out);
 
 /* ---- host text emitters (byte-identical to the reference's files) -------------------------------

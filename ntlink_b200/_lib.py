@@ -79,6 +79,9 @@ SIGNATURES = {
     "ntl_map_sketch": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_uint32, C.c_uint64, C.POINTER(Params), C.POINTER(MapOut)]),
     "ntl_tally_mappings": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_uint32, C.c_uint64, C.POINTER(Params), _U64P]),
     "ntl_liftover_mappings": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_uint32, _VP, C.c_uint32, C.c_int, C.POINTER(MapOut)]),
+    "ntl_stream": (C.c_int, [_VP, C.POINTER(C.c_void_p)]),
+    "ntl_events_export_async": (C.c_int, [_VP, _VP, C.c_uint64, _U64P]),
+    "ntl_events_import_counts": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, _VP]),
     "ntl_events_reset": (C.c_int, [_VP]),
     "ntl_events_append": (C.c_int, [_VP, _VP, C.c_uint64]),
     "ntl_events_count": (C.c_int, [_VP, _U64P]),

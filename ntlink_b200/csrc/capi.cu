@@ -68,6 +68,7 @@ struct Results {
 
 using namespace ntl;
 
+static __global__ void k_export_header(uint32_t* dst, uint32_t n) { if (threadIdx.x < 6) dst[threadIdx.x] = threadIdx.x == 0 ? n : 0u; }
 static double host_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static Results* res_of(ntl_ctx* c) { return static_cast<Results*>(c->res); }
 
@@ -779,6 +780,47 @@ int ntl_events_export(ntl_ctx* c, void* d_dst, uint64_t cap_events, uint64_t* n_
     if (m) NTL_CUDA(c, cudaMemcpyAsync((char*)d_dst + 24, c->tl_events.p, m * sizeof(Event), cudaMemcpyDeviceToDevice, c->stream));
     NTL_CUDA(c, cudaStreamSynchronize(c->stream));
     if (n_out) *n_out = n;
+    return NTL_OK;
+}
+
+int ntl_stream(ntl_ctx* c, void** stream_out) {
+    if (!c || !stream_out) return NTL_ERR_ARG;
+    *stream_out = (void*)c->stream;
+    return NTL_OK;
+}
+
+int ntl_events_export_async(ntl_ctx* c, void* d_dst, uint64_t cap_events, uint64_t* n_out) {
+    if (!c || !d_dst) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    const uint64_t n = c->tl_n_events, m = std::min(n, cap_events);
+    // header row through a kernel argument (no pinned scratch that a later call could overwrite while in flight)
+    k_export_header<<<1, 32, 0, c->stream>>>((uint32_t*)d_dst, (uint32_t)n);
+    c->launches++;
+    if (m) NTL_CUDA(c, cudaMemcpyAsync((char*)d_dst + 24, c->tl_events.p, m * sizeof(Event), cudaMemcpyDeviceToDevice, c->stream));
+    NTL_CUDA(c, cudaGetLastError());
+    if (n_out) *n_out = n;
+    return NTL_OK;
+}
+
+int ntl_events_import_counts(ntl_ctx* c, const void* d_src, uint32_t world, uint64_t cap_events, const uint32_t* counts) {
+    if (!c || !d_src || !world || !counts) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    const size_t stride = (cap_events + 1) * sizeof(Event);
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        if (counts[r] > cap_events) { c->err = "ntl_events_import_counts: a rank sent more events than the buffer holds"; return NTL_ERR_ARG; }
+        total += counts[r];
+    }
+    c->tl_n_events = 0;
+    const size_t need = (total + 1) * sizeof(Event);
+    if (need > c->tl_events.cap) NTL_CUDA(c, c->tl_events.ensure(need));
+    uint64_t o = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        if (counts[r]) NTL_CUDA(c, cudaMemcpyAsync(c->tl_events.as<Event>() + o, (const char*)d_src + r * stride + sizeof(Event),
+                                                  (size_t)counts[r] * sizeof(Event), cudaMemcpyDeviceToDevice, c->stream));
+        o += counts[r];
+    }
+    c->tl_n_events = total;
     return NTL_OK;
 }
 

@@ -196,21 +196,28 @@ __global__ void __launch_bounds__(128) k_results_host(const uint32_t* __restrict
                                                       const uint32_t* __restrict__ ev_cnt, const uint32_t* __restrict__ ev_pref,
                                                       const Event* __restrict__ log, uint32_t rb, uint32_t nreads,
                                                       HostResults H, CallState* __restrict__ call) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per read: the lanes move the read's runs, hits and events word by word (coalesced writes over PCIe)
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r > nreads) return;
     const uint32_t hits_total = call->hits_total, ev_total = call->ev_total;
     const uint32_t o = hit_off[r], ep = ev_pref[r];
-    H.hit_off[rb + r] = hits_total + o;
-    H.ev_off[rb + r] = ev_total + ep;
+    if (lane == 0) { H.hit_off[rb + r] = hits_total + o; H.ev_off[rb + r] = ev_total + ep; }
     if (r == nreads) return;
     const uint32_t nr = nruns[r], nh = hit_off[r + 1] - o, ne = ev_cnt[r];
-    H.nruns[rb + r] = nr;
-    H.ev_cnt[rb + r] = ne;
-    if ((uint64_t)hits_total + o + nh > H.hits_cap || (uint64_t)ev_total + ep + ne > H.ev_cap) { atomicOr(&call->err, CALLERR_RESULTS); return; }
-    for (uint32_t i = 0; i < nr; i++) H.runs[hits_total + o + i] = runs[o + i];
-    for (uint32_t i = 0; i < nh; i++) H.hits[hits_total + o + i] = hits[o + i];
-    const Event* src = log + call->log_n + ep;
-    for (uint32_t i = 0; i < ne; i++) H.events[ev_total + ep + i] = src[i];
+    if (lane == 0) { H.nruns[rb + r] = nr; H.ev_cnt[rb + r] = ne; }
+    if ((uint64_t)hits_total + o + nh > H.hits_cap || (uint64_t)ev_total + ep + ne > H.ev_cap) {
+        if (lane == 0) atomicOr(&call->err, CALLERR_RESULTS);
+        return;
+    }
+    const uint32_t* rs = reinterpret_cast<const uint32_t*>(runs + o);
+    uint32_t* rd = reinterpret_cast<uint32_t*>(H.runs + hits_total + o);
+    for (uint32_t i = lane; i < nr * 3; i += 32) rd[i] = rs[i];
+    const uint32_t* hs = reinterpret_cast<const uint32_t*>(hits + o);
+    uint32_t* hd = reinterpret_cast<uint32_t*>(H.hits + hits_total + o);
+    for (uint32_t i = lane; i < nh * 3; i += 32) hd[i] = hs[i];
+    const uint32_t* es = reinterpret_cast<const uint32_t*>(log + call->log_n + ep);
+    uint32_t* ed = reinterpret_cast<uint32_t*>(H.events + ev_total + ep);
+    for (uint32_t i = lane; i < ne * 6; i += 32) ed[i] = es[i];
 }
 __global__ void k_chunk_finish(const MapStatus* __restrict__ st, const uint32_t* __restrict__ n_mx, CallState* __restrict__ call) {
     if (st->err) atomicOr(&call->err, CALLERR_MAP | (st->err << 8));
@@ -662,7 +669,7 @@ int call_chunk_finish(ntl_ctx* c, CallState* call, uint32_t rb, uint32_t nreads,
     const uint32_t* ev_cnt = evmax + 2 * ((size_t)nreads + 2);
     const uint32_t* ev_pref = evmax + 3 * ((size_t)nreads + 2);
     if (H) {
-        k_results_host<<<div_up((uint64_t)nreads + 1, 128), 128, 0, c->stream>>>(M.hit_off.as<uint32_t>(), M.nruns.as<uint32_t>(), M.runs.as<Run>(),
+        k_results_host<<<div_up(((uint64_t)nreads + 1) * 32, 128), 128, 0, c->stream>>>(M.hit_off.as<uint32_t>(), M.nruns.as<uint32_t>(), M.runs.as<Run>(),
                                                                                M.hits.as<Hit>(), ev_cnt, ev_pref, c->tl_events.as<Event>(), rb,
                                                                                nreads, *H, call);
         c->launches++;

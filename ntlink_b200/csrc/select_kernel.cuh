@@ -84,12 +84,36 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_MINB) k_select(const uint64_t
     __syncthreads();
 
     if (staged) {
-        // one warp per staged strip: lanes copy the strip's candidates (coalesced 16-byte loads, no searching)
-        for (uint32_t t = tid >> 5; t < nl; t += SEL_THREADS / 32) {
-            const uint32_t s = l0 + t, c = sh_cnt[t], o = sh_off[t], vb = V.vbase[s];
-            for (uint32_t j = tid & 31; j < c; j += 32) {
-                const Cand cd = V.cands[(uint64_t)s * V.cap + j];
-                sh_c[o + j] = make_uint4((uint32_t)cd.h0, (uint32_t)(cd.h0 >> 32), vb + cd.lord, t);
+        // one warp per staged strip, lanes copy the strip's candidates (coalesced 16-byte loads, no searching). A warp
+        // owns up to SEL_ROUNDS strips; the loads of all of them are issued before the first one is consumed, so the
+        // block waits for ONE global-memory latency here, not for one per strip.
+        constexpr int SEL_ROUNDS = (SEL_NL + SEL_THREADS / 32 - 1) / (SEL_THREADS / 32);
+        const uint32_t lane = tid & 31, wrp = tid >> 5;
+        Cand cd[SEL_ROUNDS];
+        uint32_t vb[SEL_ROUNDS];
+#pragma unroll
+        for (int u = 0; u < SEL_ROUNDS; u++) {
+            const uint32_t t = wrp + u * (SEL_THREADS / 32);
+            cd[u].h0 = 0; cd[u].posf = 0; cd[u].lord = 0; vb[u] = 0;
+            if (t < nl) {
+                vb[u] = V.vbase[l0 + t];
+                if (lane < sh_cnt[t]) cd[u] = V.cands[(uint64_t)(l0 + t) * V.cap + lane];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SEL_ROUNDS; u++) {
+            const uint32_t t = wrp + u * (SEL_THREADS / 32);
+            if (t < nl && lane < sh_cnt[t])
+                sh_c[sh_off[t] + lane] = make_uint4((uint32_t)cd[u].h0, (uint32_t)(cd[u].h0 >> 32), vb[u] + cd[u].lord, t);
+        }
+        // strips with more than 32 candidates (small w): the rest, 32 at a time
+        for (uint32_t t = wrp; t < nl; t += SEL_THREADS / 32) {
+            const uint32_t c = sh_cnt[t];
+            if (c <= 32) continue;
+            const uint32_t s = l0 + t, o = sh_off[t], vbs = V.vbase[s];
+            for (uint32_t j = 32 + lane; j < c; j += 32) {
+                const Cand x = V.cands[(uint64_t)s * V.cap + j];
+                sh_c[o + j] = make_uint4((uint32_t)x.h0, (uint32_t)(x.h0 >> 32), vbs + x.lord, t);
             }
         }
     }
