@@ -397,7 +397,7 @@ def run_gpu(args, rank, world, local_rank):
                              "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                              "ms_per_launch": dense_ms, "launches": int(tm["big_dense_launches"]),
                              "algorithmic_bytes_per_launch": alg_bytes,
-                             "note": "integer-ALU bound kernel (rolling ntHash: ncu alu pipe 83 %, DRAM 11 %, "
+                             "note": "integer-ALU bound kernel (rolling ntHash: ncu alu pipe 80 %, issue slots 73 %, DRAM 11 %, "
                                      "profiles/r1_k_dense_ncu_full.txt); HBM fraction reported as the metric asks; traffic = "
                                      "dram read+write bytes of the same launch from ncu --set full (profiles/r1_traffic.json)"},
                 "stage_ms_per_step": {k: tm[k] / args.steps for k in ("pack", "dense", "select", "gap", "emit", "lookup",
