@@ -69,31 +69,112 @@ class SeqBatch:
         return self._name_blob
 
 
-def read_sequences(path, max_bases=0):
-    """FASTA/FASTQ (plain or gzip, multi-line) -> SeqBatch; id = header up to the first whitespace
-    (bin/read_fasta.py). Host-side I/O through the library's reader."""
-    lib = _lib.load()
-    h = C.c_void_p()
-    if lib.ntl_seqfile_open(path.encode(), C.byref(h)) != 0:
-        raise OSError(f"cannot open {path}")
-    try:
+class _CBuffer:
+    """Owner of a malloc'ed buffer returned by the library, exposed through __array_interface__: numpy keeps this object
+    as the base of every array (and view) made from it, and the buffer is freed when the last of them is gone."""
+
+    def __init__(self, lib, ptr, n, typestr):
+        self.lib, self.ptr = lib, ptr
+        self.__array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        if self.ptr:
+            self.lib.ntl_free(self.ptr)
+            self.ptr = None
+
+
+def _np_view(lib, ptr, n, dtype):
+    "numpy array over a library buffer WITHOUT copying"
+    if n == 0 or not ptr:
+        if ptr:
+            lib.ntl_free(ptr)
+        return np.empty(0, dtype)
+    return np.asarray(_CBuffer(lib, ptr, n, np.dtype(dtype).str))
+
+
+class SeqFile:
+    """Streaming FASTA/FASTQ reader (plain or gzip, multi-line; id = header up to the first whitespace,
+    bin/read_fasta.py:6-46) over the library's block reader. `read(max_bases)` returns the next SeqBatch of about
+    max_bases bases (whole records), None at the end of the file; the arrays are views of the library's buffers."""
+
+    def __init__(self, path):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        if self.lib.ntl_seqfile_open(path.encode(), C.byref(self.h)) != 0:
+            raise OSError(f"cannot open {path}")
+
+    def read(self, max_bases=0):
+        if not self.h:
+            return None
         seq, off, names, noff = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         n = C.c_uint32()
-        rc = lib.ntl_seqfile_read(h, max_bases, C.byref(seq), C.byref(off), C.byref(names), C.byref(noff), C.byref(n))
+        rc = self.lib.ntl_seqfile_read(self.h, max_bases, C.byref(seq), C.byref(off), C.byref(names), C.byref(noff), C.byref(n))
         if rc != 0:
             raise NtlError(rc, "ntl_seqfile_read failed")
         nseq = n.value
         offsets = _np_from(off, nseq + 1, np.uint64)
         name_off = _np_from(noff, nseq + 1, np.uint64)
         total = int(offsets[-1]) if nseq else 0
-        s = _np_from(seq, total, np.uint8)
-        nb = _np_from(names, int(name_off[-1]) if nseq else 0, np.uint8).tobytes()
-        nm = [nb[int(name_off[i]):int(name_off[i + 1])].decode() for i in range(nseq)]
-        for p in (seq, off, names, noff):
-            lib.ntl_free(p)
+        nb = C.string_at(names, int(name_off[-1])) if nseq else b""
+        for p in (off, names, noff):
+            self.lib.ntl_free(p)
+        if nseq == 0:
+            self.lib.ntl_free(seq)
+            return None
+        s = _np_view(self.lib, seq.value, total, np.uint8)
+        no = name_off.tolist()
+        nm = [nb[no[i]:no[i + 1]].decode() for i in range(nseq)]
         return SeqBatch(s, offsets, nm)
-    finally:
-        lib.ntl_seqfile_close(h)
+
+    def close(self):
+        if self.h:
+            self.lib.ntl_seqfile_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def read_sequences(path, max_bases=0):
+    """FASTA/FASTQ (plain or gzip, multi-line) -> SeqBatch of the whole file (or of its first ~max_bases bases)."""
+    with SeqFile(path) as f:
+        batch = f.read(max_bases)
+    if batch is None:
+        return SeqBatch(np.empty(0, np.uint8), np.zeros(1, np.uint64), [])
+    return batch
+
+
+def prefetch_batches(paths, max_bases):
+    """Iterator over the SeqBatches of several files; the next batch is decoded by a background thread (the library call
+    releases the GIL) while the caller works on the current one."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=2)
+
+    def producer():
+        try:
+            for path in paths:
+                with SeqFile(path) as f:
+                    while True:
+                        b = f.read(max_bases)
+                        if b is None:
+                            break
+                        q.put(b)
+            q.put(None)
+        except BaseException as exc:      # hand the error to the consumer
+            q.put(exc)
+
+    threading.Thread(target=producer, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is None:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
 
 
 class Sketch:

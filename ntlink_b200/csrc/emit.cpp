@@ -10,6 +10,11 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -250,37 +255,91 @@ void ntl_free(void* p) { free(p); }
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------- reader
+// Block reader: the file is consumed in 8 MiB blocks (read(2) for plain files, gzread for gzip, chosen by the magic
+// bytes), lines are located with memchr inside the block and sequence lines are appended straight into the output
+// buffer (no per-line strings). A line that straddles two blocks is the only case that is assembled separately.
+namespace {
+
+struct GrowBuf {                 // malloc'ed, geometrically growing byte buffer that is handed to the caller
+    char* p = nullptr;
+    size_t n = 0, cap = 0;
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t c = cap ? cap : (1u << 20);
+        while (c < want) c += c / 2 + (1u << 20);
+        char* q = nullptr;
+        if (!p && c >= (8u << 20)) {
+            // first (hinted) allocation of a large batch: 2 MiB aligned + transparent huge pages, so that filling the
+            // buffer does not take one page fault per 4 KiB
+            void* a = nullptr;
+            if (posix_memalign(&a, 2u << 20, c) == 0) {
+#ifdef MADV_HUGEPAGE
+                madvise(a, c, MADV_HUGEPAGE);
+#endif
+                q = (char*)a;
+            }
+        }
+        if (!q) q = (char*)realloc(p, c);
+        if (!q) return false;
+        p = q; cap = c;
+        return true;
+    }
+    bool append(const char* src, size_t len) {
+        if (!reserve(n + len + 64)) return false;
+        memcpy(p + n, src, len);
+        n += len;
+        return true;
+    }
+};
+
+}  // namespace
+
 struct ntl_seqfile {
-    gzFile f = nullptr;
+    gzFile gz = nullptr;         // gzip input (or stdin)
+    int fd = -1;                 // plain file
     std::vector<char> buf;
     size_t pos = 0, len = 0;
     bool eof = false;
-    std::string pending;     // header line read ahead
+    std::string carry;           // assembled line that straddled two blocks
+    std::string pending;         // header line read ahead
     bool have_pending = false;
 
     bool fill() {
         if (eof) return false;
-        if (buf.empty()) buf.resize(4u << 20);
-        int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (buf.empty()) buf.resize(8u << 20);
+        long n;
+        if (fd >= 0) {
+            do { n = (long)::read(fd, buf.data(), buf.size()); } while (n < 0 && errno == EINTR);
+        } else {
+            n = gzread(gz, buf.data(), (unsigned)buf.size());
+        }
         if (n <= 0) { eof = true; pos = len = 0; return false; }
         pos = 0; len = (size_t)n;
         return true;
     }
-    // next line without its terminator; false at end of file
-    bool getline(std::string& line) {
-        line.clear();
-        bool got = false;
-        for (;;) {
-            if (pos >= len && !fill()) break;
-            got = true;
-            const char* p = buf.data() + pos;
-            const char* nl = (const char*)memchr(p, '\n', len - pos);
-            if (nl) { line.append(p, (size_t)(nl - p)); pos = (size_t)(nl - buf.data()) + 1; break; }
-            line.append(p, len - pos);
+    // next line without its terminator, as a view (valid until the next call); false at end of file
+    bool getline(const char*& lp, size_t& ll) {
+        if (pos >= len && !fill()) return false;
+        const char* p = buf.data() + pos;
+        const char* nl = (const char*)memchr(p, '\n', len - pos);
+        if (nl) {
+            lp = p; ll = (size_t)(nl - p);
+            pos = (size_t)(nl - buf.data()) + 1;
+        } else {                                   // the line continues in the next block(s)
+            carry.assign(p, len - pos);
             pos = len;
+            for (;;) {
+                if (!fill()) break;
+                const char* q = buf.data();
+                const char* e = (const char*)memchr(q, '\n', len);
+                if (e) { carry.append(q, (size_t)(e - q)); pos = (size_t)(e - q) + 1; break; }
+                carry.append(q, len);
+                pos = len;
+            }
+            lp = carry.data(); ll = carry.size();
         }
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        return got;
+        if (ll && lp[ll - 1] == '\r') ll--;
+        return true;
     }
 };
 
@@ -289,9 +348,25 @@ extern "C" {
 int ntl_seqfile_open(const char* path, ntl_seqfile** out) {
     if (!path || !out) return NTL_ERR_ARG;
     ntl_seqfile* f = new ntl_seqfile();
-    f->f = strcmp(path, "-") ? gzopen(path, "rb") : gzdopen(0, "rb");
-    if (!f->f) { delete f; return NTL_ERR_ARG; }
-    gzbuffer(f->f, 1u << 20);
+    if (strcmp(path, "-") == 0) {
+        f->gz = gzdopen(0, "rb");                  // zlib passes plain data through
+    } else {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) { delete f; return NTL_ERR_ARG; }
+        unsigned char magic[2] = {0, 0};
+        const long got = (long)::pread(fd, magic, 2, 0);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            ::close(fd);
+            f->gz = gzopen(path, "rb");
+        } else {
+            f->fd = fd;
+#ifdef POSIX_FADV_SEQUENTIAL
+            posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+        }
+    }
+    if (!f->gz && f->fd < 0) { delete f; return NTL_ERR_ARG; }
+    if (f->gz) gzbuffer(f->gz, 1u << 20);
     *out = f;
     return NTL_OK;
 }
@@ -299,57 +374,68 @@ int ntl_seqfile_open(const char* path, ntl_seqfile** out) {
 int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_t** offsets_out, char** names_out,
                      uint64_t** name_off_out, uint32_t* nseq_out) {
     if (!f || !seq_out || !offsets_out || !names_out || !name_off_out || !nseq_out) return NTL_ERR_ARG;
-    std::string seq, names, line;
+    GrowBuf seq, names;
     std::vector<uint64_t> offs(1, 0), noffs(1, 0);
-    for (;;) {
-        if (max_bases && seq.size() >= max_bases) break;
+    const char* lp = nullptr;
+    size_t ll = 0;
+    // plain files: what is left of the file bounds the batch, so the buffer never has to grow
+    size_t hint = 1u << 20;
+    if (f->fd >= 0) {
+        struct stat sb;
+        const off_t at = lseek(f->fd, 0, SEEK_CUR);
+        if (fstat(f->fd, &sb) == 0 && at >= 0 && sb.st_size > at) hint = (size_t)(sb.st_size - at) + (f->len - f->pos) + 4096;
+        if (max_bases && hint > max_bases + (64u << 20)) hint = (size_t)max_bases + (64u << 20);
+    }
+    bool ok = seq.reserve(hint) && names.reserve(1u << 12);
+    while (ok) {
+        if (max_bases && seq.n >= max_bases) break;
         // find the next header (bin/read_fasta.py:10-16)
         if (!f->have_pending) {
             bool found = false;
-            while (f->getline(line)) {
-                if (!line.empty() && (line[0] == '>' || line[0] == '@')) { found = true; break; }
+            while (f->getline(lp, ll)) {
+                if (ll && (lp[0] == '>' || lp[0] == '@')) { found = true; break; }
             }
             if (!found) break;
-            f->pending = line;
+            f->pending.assign(lp, ll);
         }
         f->have_pending = false;
         const std::string& hdr = f->pending;
         size_t e = 1;
         while (e < hdr.size() && hdr[e] != ' ' && hdr[e] != '\t' && hdr[e] != '\v' && hdr[e] != '\f' && hdr[e] != '\r') e++;
-        names.append(hdr, 1, e - 1);
-        noffs.push_back(names.size());
-        const size_t start = seq.size();
+        ok = names.append(hdr.data() + 1, e - 1);
+        noffs.push_back(names.n);
+        const size_t start = seq.n;
         bool plus = false;
-        while (f->getline(line)) {
-            if (!line.empty() && (line[0] == '>' || line[0] == '@')) { f->pending = line; f->have_pending = true; break; }
-            if (!line.empty() && line[0] == '+') { plus = true; break; }
-            seq.append(line);
+        while (ok && f->getline(lp, ll)) {
+            if (ll && (lp[0] == '>' || lp[0] == '@')) { f->pending.assign(lp, ll); f->have_pending = true; break; }
+            if (ll && lp[0] == '+') { plus = true; break; }
+            ok = seq.append(lp, ll);
         }
         if (plus) {                           // FASTQ: as many quality characters as bases (read_fasta.py:36-43)
             size_t q = 0;
-            const size_t need = seq.size() - start;
-            while (q < need && f->getline(line)) q += line.size();
+            const size_t need = seq.n - start;
+            while (q < need && f->getline(lp, ll)) q += ll;
         }
-        offs.push_back(seq.size());
+        offs.push_back(seq.n);
     }
     const uint32_t nseq = (uint32_t)(offs.size() - 1);
-    char* s = (char*)malloc(seq.size() + 64);
     uint64_t* o = (uint64_t*)malloc(offs.size() * 8);
-    char* nm = (char*)malloc(names.size() + 1);
     uint64_t* no = (uint64_t*)malloc(noffs.size() * 8);
-    if (!s || !o || !nm || !no) { free(s); free(o); free(nm); free(no); return NTL_ERR_ARG; }
-    memcpy(s, seq.data(), seq.size());
-    memset(s + seq.size(), 'N', 64);
+    if (!ok || !o || !no || !seq.reserve(seq.n + 64) || !names.reserve(names.n + 1)) {
+        free(seq.p); free(names.p); free(o); free(no);
+        return NTL_ERR_ARG;
+    }
+    memset(seq.p + seq.n, 'N', 64);
     memcpy(o, offs.data(), offs.size() * 8);
-    memcpy(nm, names.data(), names.size());
     memcpy(no, noffs.data(), noffs.size() * 8);
-    *seq_out = s; *offsets_out = o; *names_out = nm; *name_off_out = no; *nseq_out = nseq;
+    *seq_out = seq.p; *offsets_out = o; *names_out = names.p; *name_off_out = no; *nseq_out = nseq;
     return NTL_OK;
 }
 
 void ntl_seqfile_close(ntl_seqfile* f) {
     if (!f) return;
-    if (f->f) gzclose(f->f);
+    if (f->gz) gzclose(f->gz);
+    if (f->fd >= 0) ::close(f->fd);
     delete f;
 }
 

@@ -31,35 +31,16 @@ def parse_arguments(argv=None):
 
 def main(argv=None):
     a = parse_arguments(argv)
-    lib = _lib.load()
     ctx = api.Context(a.device)
-    h = C.c_void_p()
-    if lib.ntl_seqfile_open(a.FILE.encode(), C.byref(h)) != 0:
-        sys.exit(f"indexlr: cannot open {a.FILE}")
     out = sys.stdout.buffer
     try:
-        while True:
-            seq, off, names, noff = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-            n = C.c_uint32()
-            if lib.ntl_seqfile_read(h, int(a.chunk_bases), C.byref(seq), C.byref(off), C.byref(names), C.byref(noff), C.byref(n)) != 0:
-                sys.exit("indexlr: read error")
-            nseq = n.value
-            if nseq == 0:
-                for p in (seq, off, names, noff):
-                    lib.ntl_free(p)
-                break
-            offsets = api._np_from(off, nseq + 1, np.uint64)
-            name_off = api._np_from(noff, nseq + 1, np.uint64)
-            s = api._np_from(seq, int(offsets[-1]), np.uint8)
-            nb = api._np_from(names, int(name_off[-1]), np.uint8).tobytes()
-            nm = [nb[int(name_off[i]):int(name_off[i + 1])].decode() for i in range(nseq)]
-            for p in (seq, off, names, noff):
-                lib.ntl_free(p)
-            batch = api.SeqBatch(s, offsets, nm)
+        # streamed in chunks; the next chunk is read / decompressed while this one is sketched and printed
+        for batch in api.prefetch_batches([a.FILE], int(a.chunk_bases)):
             sk = ctx.sketch(batch, a.k, a.w)
             out.write(sk.to_tsv(batch, with_len=a.len, with_pos=a.pos, with_strand=a.strand, threads=a.t))
+    except OSError as exc:
+        sys.exit(f"indexlr: {exc}")
     finally:
-        lib.ntl_seqfile_close(h)
         ctx.close()
 
 

@@ -204,6 +204,7 @@ def parse_arguments(argv=None):
     p.add_argument("--sketch-target", action="store_true", help="Sketch the target (-s) on the GPU instead of reading -m")
     p.add_argument("--write-target-tsv", help="Also write the target sketch TSV here", default=None)
     p.add_argument("--device", type=int, default=0)
+    p.add_argument("--batch-bases", type=float, default=1e9, help="bases per streamed read batch with --reads-fasta [1e9]")
     p.add_argument("-t", type=int, default=4, help="host threads for text output")
     return p.parse_args(argv)
 
@@ -253,8 +254,9 @@ class NtLink:
             if a.reads_fasta:
                 if a.w is None:
                     raise NtlinkPairError("-w is required with --reads-fasta")
-                for path in a.reads_fasta:
-                    reads = api.read_sequences(path)
+                # streamed: batches of ~batch_bases, the next one is decoded by a background thread while this one is
+                # on the GPU (a 60x human read set does not fit in host memory, and gzip decoding is the slowest stage)
+                for reads in api.prefetch_batches(a.reads_fasta, int(a.batch_bases)):
                     res = self.ctx.map_reads(reads, prm, ordinal)
                     self._emit(res, reads, reads.lengths.astype(np.uint32), vf, pf)
                     ordinal += len(reads)

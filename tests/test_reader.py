@@ -1,0 +1,106 @@
+"""Host-side input path (ntl_seqfile_*, api.SeqFile / prefetch_batches): FASTA/FASTQ, plain and gzip, multi-line records,
+CRLF, ids cut at the first whitespace (bin/read_fasta.py:6-46), batching at record boundaries, lines that straddle the
+reader's 8 MiB blocks, buffer ownership of the zero-copy arrays. No GPU involved."""
+import gc
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import util
+from ntlink_b200 import api
+
+
+def reference_parse(text):
+    "plain-Python restatement of bin/read_fasta.py:6-46 (readfq): [(id, seq)]"
+    out, lines, i = [], text.split("\n"), 0
+    while i < len(lines):
+        if not lines[i] or lines[i][0] not in ">@":
+            i += 1
+            continue
+        name = lines[i][1:].split()[0] if lines[i][1:].split() else ""
+        i += 1
+        seq = []
+        while i < len(lines) and (not lines[i] or lines[i][0] not in ">@+"):
+            seq.append(lines[i].rstrip("\r"))
+            i += 1
+        s = "".join(seq)
+        if i < len(lines) and lines[i] and lines[i][0] == "+":
+            i += 1
+            q = 0
+            while i < len(lines) and q < len(s):
+                q += len(lines[i].rstrip("\r"))
+                i += 1
+        out.append((name, s))
+    return out
+
+
+def make_text(rng, n, fastq, width):
+    recs = []
+    for r in range(n):
+        L = int(rng.integers(0, 700))
+        s = "".join("ACGTN"[int(x)] for x in rng.integers(0, 5, L))
+        hdr = f"rec{r} some description\tmore"
+        if fastq:
+            recs.append(f"@{hdr}\n{s}\n+\n{'I' * L}\n")
+        else:
+            body = "\n".join(s[i:i + width] for i in range(0, L, width)) if width else s
+            recs.append(f">{hdr}\n{body}\n" if L else f">{hdr}\n")
+    return "".join(recs)
+
+
+@pytest.mark.parametrize("fastq,width,gz,crlf", [(False, 60, False, False), (False, 0, True, False), (True, 0, False, False),
+                                                  (True, 0, True, False), (False, 70, False, True)])
+def test_reader_matches_readfq(tmp_path, fastq, width, gz, crlf):
+    rng = np.random.default_rng(11 + width + 2 * gz + fastq)
+    text = make_text(rng, 300, fastq, width)
+    if crlf:
+        text = text.replace("\n", "\r\n")
+    path = os.path.join(str(tmp_path), "x.fq" if fastq else "x.fa") + (".gz" if gz else "")
+    with (gzip.open(path, "wt", newline="") if gz else open(path, "w", newline="")) as fout:
+        fout.write(text)
+    want = reference_parse(text.replace("\r\n", "\n"))
+    whole = api.read_sequences(path)
+    got = [(n, whole.seq[int(a):int(b)].tobytes().decode()) for n, a, b in zip(whole.names, whole.offsets, whole.offsets[1:])]
+    assert got == want
+    # streamed in small batches: same records, cut at record boundaries
+    streamed = []
+    for batch in api.prefetch_batches([path], 5000):
+        assert int(batch.offsets[-1]) < 5000 + 700
+        streamed += [(n, batch.seq[int(a):int(b)].tobytes().decode()) for n, a, b in zip(batch.names, batch.offsets, batch.offsets[1:])]
+    assert streamed == want
+
+
+def test_lines_longer_than_a_block_and_fixture_files(tmp_path):
+    rng = np.random.default_rng(3)
+    long_seq = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, 20_000_000))      # one 20 Mbp line: spans three 8 MiB blocks
+    path = os.path.join(str(tmp_path), "long.fa")
+    with open(path, "w") as fout:
+        fout.write(f">a\n{long_seq}\n>b x\nACGT\nAC\n")
+    b = api.read_sequences(path)
+    assert b.names == ["a", "b"] and b.offsets.tolist() == [0, 20_000_000, 20_000_006]
+    assert b.seq[:20_000_000].tobytes().decode() == long_seq and b.seq[20_000_000:].tobytes() == b"ACGTAC"
+    # the reference's fixtures against the test-suite's own FASTA loader
+    for name in ("scaffolds_3.fa", "long_reads_2.fq"):
+        f = util.fixture_file(tmp_path, name)
+        names, seq, offs = util.load_fasta_batch(f)
+        got = api.read_sequences(f)
+        assert got.names == names and np.array_equal(got.offsets, offs) and np.array_equal(got.seq, seq)
+
+
+def test_zero_copy_arrays_keep_their_buffer_alive(tmp_path):
+    path = os.path.join(str(tmp_path), "y.fa")
+    with open(path, "w") as fout:
+        fout.write(">s\n" + "ACGT" * 5000 + "\n")
+    batch = api.read_sequences(path)
+    part = batch.seq[100:108]
+    del batch
+    gc.collect()
+    assert part.tobytes() == b"ACGTACGT"
+    assert api.read_sequences(os.path.join(str(tmp_path), "y.fa"), max_bases=1).offsets.tolist() == [0, 20000]
+    with pytest.raises(OSError):
+        api.read_sequences(os.path.join(str(tmp_path), "missing.fa"))
+    empty = os.path.join(str(tmp_path), "empty.fa")
+    open(empty, "w").close()
+    assert len(api.read_sequences(empty)) == 0
