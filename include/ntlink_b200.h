@@ -45,7 +45,8 @@ int ntl_version(void);
  * expected candidates per window), "batch_bases" (bases per device batch), "pipeline_min_bases" (4x the chunk size of
  * the pipelined ntl_map_reads), "async" (1: ntl_map_reads / ntl_map_resident enqueue the whole call without waiting for
  * the device and synchronise once; 0: the step-by-step path the sync-free one falls back to), "graph" (1: each chunk of
- * a sync-free call is launched as one CUDA graph) */
+ * a sync-free call is launched as one CUDA graph), "copy_threads" (host threads that move pageable caller memory into
+ * pinned bounce buffers; -1 auto, 0 leaves the staging to the driver) */
 int ntl_set_option(ntl_ctx* ctx, const char* name, double value);
 
 /* ---- sketch -------------------------------------------------------------------------------------

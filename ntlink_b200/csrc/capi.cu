@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <thread>
 
 #include "common.cuh"
 #include "lift_logic.cuh"
@@ -59,6 +60,7 @@ struct Results {
     PinnedBuf st_hoff[2];
     // sync-free path: staging slot free again (its chunk's kernels are done), rebased offsets of every chunk of the call
     cudaEvent_t comp_done[2] = {nullptr, nullptr};
+    PinnedBuf pin_slot[2];                     // bounce buffers for callers that pass pageable memory
     std::vector<cudaGraphExec_t> chunk_execs;
     cudaGraphExec_t resident_exec = nullptr;
     PinnedBuf call_hoff;
@@ -69,6 +71,19 @@ struct Results {
 using namespace ntl;
 
 static __global__ void k_export_header(uint32_t* dst, uint32_t n) { if (threadIdx.x < 6) dst[threadIdx.x] = threadIdx.x == 0 ? n : 0u; }
+// copy with a few threads: one core moves ~10 GB/s, the PCIe link takes 55
+static void parallel_memcpy(char* dst, const char* src, size_t n, int threads) {
+    if (threads <= 1 || n < (4u << 20)) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((n + threads - 1) / threads + 4095) & ~(size_t)4095;
+    for (int t = 1; t < threads; t++) {
+        const size_t b = (size_t)t * per;
+        if (b >= n) break;
+        th.emplace_back([=]() { memcpy(dst + b, src + b, std::min(per, n - b)); });
+    }
+    memcpy(dst, src, std::min(per, n));
+    for (auto& x : th) x.join();
+}
 static double host_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static Results* res_of(ntl_ctx* c) { return static_cast<Results*>(c->res); }
 
@@ -182,6 +197,7 @@ void ntl_destroy(ntl_ctx* c) {
     R->h_off.release();
     for (int i = 0; i < 2; i++) { R->st_seq[i].release(); R->st_off[i].release(); R->st_hoff[i].release(); cudaEventDestroy(R->h2d_done[i]); cudaEventDestroy(R->comp_done[i]); }
     R->call_hoff.release();
+    R->pin_slot[0].release(); R->pin_slot[1].release();
     for (cudaGraphExec_t e : R->chunk_execs) if (e) cudaGraphExecDestroy(e);
     R->chunk_execs.clear();
     if (R->resident_exec) cudaGraphExecDestroy(R->resident_exec);
@@ -208,6 +224,8 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
         c->cand_c = value;
     } else if (!strcmp(name, "async")) {
         c->async_mode = value != 0.0;
+    } else if (!strcmp(name, "copy_threads")) {
+        c->copy_threads = (int)value;
     } else if (!strcmp(name, "graph")) {
         c->graph_mode = value != 0.0;
     } else if (!strcmp(name, "pipeline_min_bases")) {
@@ -458,12 +476,29 @@ static int map_reads_async(ntl_ctx* c, const char* seq, const uint64_t* offsets,
             for (uint32_t r = bounds[i]; r <= bounds[i + 1]; r++) ho_all[at++] = offsets[r] - base;
         }
     }
+    // Pageable caller memory (numpy arrays from the file reader): the driver's own staging of such copies runs at
+    // ~3 GB/s, so the chunk is moved into a pinned bounce buffer by a few host threads and sent from there.
+    bool pageable = true;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, seq) == cudaSuccess) pageable = (attr.type == cudaMemoryTypeUnregistered);
+        else cudaGetLastError();
+    }
+    const int copy_threads = c->copy_threads >= 0 ? c->copy_threads : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    if (copy_threads == 0) pageable = false;                   // option "copy_threads" = 0: leave the staging to the driver
+    if (pageable) for (int sl = 0; sl < 2 && (size_t)sl < nch; sl++) NTL_CUDA(c, R->pin_slot[sl].ensure(max_nb + 256));
     auto enqueue_copy = [&](size_t i) -> int {
         const int sl = (int)(i & 1);
         const uint64_t base = offsets[bounds[i]], nb = offsets[bounds[i + 1]] - base;
         const uint32_t ns = bounds[i + 1] - bounds[i];
+        const char* src = seq + base;
+        if (pageable && nb) {
+            if (i >= 2) NTL_CUDA(c, cudaEventSynchronize(R->h2d_done[sl]));                   // the bounce buffer's previous chunk has left
+            parallel_memcpy(R->pin_slot[sl].as<char>(), src, nb, copy_threads);
+            src = R->pin_slot[sl].as<char>();
+        }
         if (i >= 2) NTL_CUDA(c, cudaStreamWaitEvent(R->copy_stream, R->comp_done[sl], 0));   // slot's previous chunk is done with it
-        if (nb) NTL_CUDA(c, cudaMemcpyAsync(R->st_seq[sl].p, seq + base, nb, cudaMemcpyHostToDevice, R->copy_stream));
+        if (nb) NTL_CUDA(c, cudaMemcpyAsync(R->st_seq[sl].p, src, nb, cudaMemcpyHostToDevice, R->copy_stream));
         NTL_CUDA(c, cudaMemcpyAsync(R->st_off[sl].p, ho_all + ho_at[i], ((size_t)ns + 1) * 8, cudaMemcpyHostToDevice, R->copy_stream));
         NTL_CUDA(c, cudaEventRecord(R->h2d_done[sl], R->copy_stream));
         return NTL_OK;
@@ -492,7 +527,9 @@ static int map_reads_async(ntl_ctx* c, const char* seq, const uint64_t* offsets,
         const int sl = (int)(i & 1);
         const uint32_t b = bounds[i], ns = bounds[i + 1] - b;
         const uint64_t nb = offsets[bounds[i + 1]] - offsets[b];
-        if (i + 1 < nch) { NTL_TRY(enqueue_copy(i + 1)); if (trace) cudaEventRecord(tr_copy[i + 1], R->copy_stream); }
+        // pinned source: queue the next copy first (it is asynchronous); pageable source: the host-side bounce copy of
+        // the next chunk would delay this chunk's launch, so it comes after it
+        if (!pageable && i + 1 < nch) { NTL_TRY(enqueue_copy(i + 1)); if (trace) cudaEventRecord(tr_copy[i + 1], R->copy_stream); }
         if (use_graph) {
             // The ~60 launches of a chunk go into ONE CUDA graph: while a host->device copy is in flight every single
             // kernel launch costs several microseconds more (its launch data is fetched over the same PCIe link), a
@@ -543,6 +580,7 @@ static int map_reads_async(ntl_ctx* c, const char* seq, const uint64_t* offsets,
         }
         NTL_CUDA(c, cudaEventRecord(R->comp_done[sl], c->stream));
         if (trace) cudaEventRecord(tr_comp[i], c->stream);
+        if (pageable && i + 1 < nch) { NTL_TRY(enqueue_copy(i + 1)); if (trace) cudaEventRecord(tr_copy[i + 1], R->copy_stream); }
     }
     tock(c, T_TOTAL);
     CallState hs;
