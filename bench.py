@@ -291,20 +291,28 @@ def run_gpu(args, rank, world, local_rank):
     stats = {}
 
     def step_resident():
+        t_a = time.perf_counter()
         ctx.events_reset()
         if world == 1 or not shard_target:
             ctx.index_build_resident(K, W)
         else:
             build_index_distributed(ctx, contigs, rank, world, dist, torch)
         st = ctx.map_resident(prm, first_ordinal=rank * len(reads))
+        t_b = time.perf_counter()
         if world > 1:
             gather_events(ctx, rank, world, dist, torch)
+        t_c = time.perf_counter()
         if rank == 0:
             stats["pairs"] = len(ctx.pairs_raw()[0])
+        t_d = time.perf_counter()
+        for key, dt in (("t_map", t_b - t_a), ("t_gather", t_c - t_b), ("t_pairs", t_d - t_c)):
+            stats[key] = stats.get(key, 0.0) + dt
         stats.update(st)
 
     for _ in range(args.warmup):
         step_resident()
+    for key in ("t_map", "t_gather", "t_pairs"):
+        stats[key] = 0.0
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -402,6 +410,9 @@ def run_gpu(args, rank, world, local_rank):
                                      "dram read+write bytes of the same launch from ncu --set full (profiles/r1_traffic.json)"},
                 "stage_ms_per_step": {k: tm[k] / args.steps for k in ("pack", "dense", "select", "gap", "emit", "lookup",
                                                                       "chain", "tally", "index")},
+                "host_ms_per_step_rank0": {"index+map_resident": round(1e3 * stats["t_map"] / args.steps, 3),
+                                           "event_exchange": round(1e3 * stats["t_gather"] / args.steps, 3),
+                                           "tally+pairs": round(1e3 * stats["t_pairs"] / args.steps, 3)},
                 "counts": {"read_minimizers": int(n_mx), "hits": int(stats["hits"]), "runs": int(stats["runs"]),
                            "events": int(stats["events"]), "pairs": int(stats.get("pairs", 0))}}
         if world == 1 and not args.no_cpu:
