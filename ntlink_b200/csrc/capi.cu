@@ -16,6 +16,7 @@ int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, u
                CallState* call = nullptr);
 int call_begin(ntl_ctx* c, CallState** call_out);
 int call_reserve_events(ntl_ctx* c, uint32_t nreads);
+int call_note_mx(ntl_ctx* c, const uint32_t* n_dev, CallState* call);
 int call_chunk_finish(ntl_ctx* c, CallState* call, uint32_t rb, uint32_t nreads, const HostResults* H);
 int call_end(ntl_ctx* c, CallState* call, CallState* host_out);
 int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const Run* runs, const Hit* hits, uint32_t nreads,
@@ -62,7 +63,8 @@ struct Results {
     cudaEvent_t comp_done[2] = {nullptr, nullptr};
     PinnedBuf pin_slot[2];                     // bounce buffers for callers that pass pageable memory
     std::vector<cudaGraphExec_t> chunk_execs;
-    cudaGraphExec_t resident_exec = nullptr;
+    cudaGraphExec_t resident_exec = nullptr, index_exec = nullptr;
+    PinnedBuf idx_meta;                        // contig lengths + name ranks of the index being built (stable for the graph)
     PinnedBuf call_hoff;
     uint64_t last_call_hits = 0, last_call_bases = 0;
 };
@@ -201,6 +203,8 @@ void ntl_destroy(ntl_ctx* c) {
     for (cudaGraphExec_t e : R->chunk_execs) if (e) cudaGraphExecDestroy(e);
     R->chunk_execs.clear();
     if (R->resident_exec) cudaGraphExecDestroy(R->resident_exec);
+    if (R->index_exec) cudaGraphExecDestroy(R->index_exec);
+    R->idx_meta.release();
     cudaStreamSynchronize(R->copy_stream);
     cudaStreamDestroy(R->copy_stream);
     c->h_status.release();
@@ -239,6 +243,67 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
 }
 
 // ------------------------------------------------------------------------------------------- sketch
+// Sync-free index build from sequences that are already on the device: deferred sketch, contig ids, table insert and
+// finalize as ONE graph, one synchronisation. *ok = false (nothing built) when the sketch outgrew its bound: the caller
+// then takes the synchronous path.
+static int index_build_async(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t nbases, int k, int w,
+                             const uint32_t* h_len, const uint32_t* h_rank, DevBuf& ctg_ids, bool* ok) {
+    Results* R = res_of(c);
+    *ok = false;
+    if (nseq == 0 || nbases == 0 || nbases >= (1ull << 32) - 4096) return NTL_OK;
+    NTL_CUDA(c, R->idx_meta.ensure((size_t)nseq * 8 + 64));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));          // the previous build may still be reading idx_meta
+    uint32_t* meta = R->idx_meta.as<uint32_t>();
+    memcpy(meta, h_len, (size_t)nseq * 4);
+    memcpy(meta + nseq, h_rank, (size_t)nseq * 4);
+    NTL_TRY(sketch_prepare(c, (uint32_t)k));
+    CallState* call = nullptr;
+    NTL_TRY(call_begin(c, &call));
+    auto enqueue = [&]() -> int {
+        NTL_TRY(sketch_device(c, d_seq, d_off, nseq, nbases, (uint32_t)k, (uint32_t)w, c->dsk, call));
+        NTL_TRY(expand_contig_ids(c, c->dsk, ctg_ids));
+        NTL_TRY(index_build_device(c, c->dsk.hash.as<uint64_t>(), ctg_ids.as<uint32_t>(), c->dsk.posf.as<uint32_t>(), c->dsk.n_mx, meta,
+                                   meta + nseq, nseq, c->dsk.n_dev, false));
+        NTL_TRY(call_note_mx(c, c->dsk.n_dev, call));
+        return NTL_OK;
+    };
+    if (c->graph_mode) {
+        cudaGraph_t graph = nullptr;
+        NTL_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        c->capturing = true;
+        const int rc = enqueue();
+        c->capturing = false;
+        const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != NTL_OK) { if (graph) cudaGraphDestroy(graph); c->index.built = false; return rc; }
+        if (ce != cudaSuccess) { c->index.built = false; c->err = std::string("graph capture: ") + cudaGetErrorString(ce); return NTL_ERR_CUDA; }
+        if (R->index_exec) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(R->index_exec, graph, &info) != cudaSuccess) {
+                cudaGetLastError();
+                cudaGraphExecDestroy(R->index_exec);
+                R->index_exec = nullptr;
+            }
+        }
+        if (!R->index_exec) {
+            const cudaError_t ie = cudaGraphInstantiate(&R->index_exec, graph, 0);
+            if (ie != cudaSuccess) { cudaGraphDestroy(graph); R->index_exec = nullptr; c->index.built = false; c->err = std::string("graph instantiate: ") + cudaGetErrorString(ie); return NTL_ERR_CUDA; }
+        }
+        cudaGraphDestroy(graph);
+        NTL_CUDA(c, cudaGraphLaunch(R->index_exec, c->stream));
+        c->n_graph_launches++;
+    } else {
+        NTL_TRY(enqueue());
+    }
+    CallState hs;
+    NTL_TRY(call_end(c, call, &hs));
+    collect_timing(c);
+    if (hs.err) { c->index.built = false; return NTL_OK; }
+    c->index.n_inserted = hs.mx_total;
+    c->dsk.n_mx = hs.mx_total;
+    *ok = true;
+    return NTL_OK;
+}
+
 static int sketch_to_host(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t nseq, int k, int w,
                           ntl_sketch_out* out, bool build_index, const uint32_t* name_rank) {
     Results* R = res_of(c);
@@ -256,6 +321,16 @@ static int sketch_to_host(ntl_ctx* c, const char* seq, const uint64_t* offsets, 
     if (build_index && bounds.size() > 2) {
         c->err = "target does not fit one device batch: raise the batch_bases option (max 3.9e9)";
         return NTL_ERR_ARG;
+    }
+    if (build_index && !out && bounds.size() == 2 && c->async_mode) {
+        // index only (no sketch wanted back): copy, deferred sketch, contig ids and table build as one graph, one sync
+        uint64_t nb = 0;
+        NTL_TRY(stage_batch(c, seq, offsets, 0, nseq, &nb));
+        std::vector<uint32_t> len(nseq);
+        for (uint32_t i = 0; i < nseq; i++) len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+        bool ok = false;
+        NTL_TRY(index_build_async(c, c->d_seq.as<uint8_t>(), c->d_off.as<uint64_t>(), nseq, nb, k, w, len.data(), name_rank, R->ctg_ids, &ok));
+        if (ok) return NTL_OK;
     }
     for (size_t bi = 0; bi + 1 < bounds.size(); bi++) {
         const uint32_t b = bounds[bi], e = bounds[bi + 1];
@@ -1019,6 +1094,12 @@ int ntl_index_build_resident(ntl_ctx* c, int k, int w) {
     Results* R = res_of(c);
     cudaSetDevice(c->device);
     if (!R->t_ncontig) { c->err = "ntl_index_build_resident: no resident target"; return NTL_ERR_STATE; }
+    if (c->async_mode) {
+        bool ok = false;
+        NTL_TRY(index_build_async(c, R->t_seq.as<uint8_t>(), R->t_off.as<uint64_t>(), R->t_ncontig, R->t_bases, k, w, R->t_len.data(),
+                                  R->t_rank.data(), R->t_ctg, &ok));
+        if (ok) return NTL_OK;
+    }
     NTL_TRY(sketch_device(c, R->t_seq.as<uint8_t>(), R->t_off.as<uint64_t>(), R->t_ncontig, R->t_bases, (uint32_t)k, (uint32_t)w, c->dsk));
     NTL_TRY(expand_contig_ids(c, c->dsk, R->t_ctg));
     NTL_TRY(index_build_device(c, c->dsk.hash.as<uint64_t>(), R->t_ctg.as<uint32_t>(), c->dsk.posf.as<uint32_t>(), c->dsk.n_mx,

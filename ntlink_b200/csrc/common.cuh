@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -202,7 +203,12 @@ int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint3
 int sketch_prepare(ntl_ctx* c, uint32_t k);
 // implemented in map.cu
 int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg, const uint32_t* d_posf, uint64_t n,
-                       const uint32_t* h_ctg_len, const uint32_t* h_name_rank, uint32_t ncontig);
+                       const uint32_t* h_ctg_len, const uint32_t* h_name_rank, uint32_t ncontig, const uint32_t* n_dev = nullptr,
+                       bool sync = true);
+// upper bound of the number of minimizers a deferred sketch pass reserves room for
+inline uint32_t sketch_out_bound(uint64_t total_bases, uint32_t nseq, uint32_t w) {
+    return (uint32_t)std::min<uint64_t>(total_bases, (uint64_t)(2.6 * (double)total_bases / ((double)w + 1.0)) + 8ull * nseq + 4096);
+}
 // scan utility (scan.cu): exclusive prefix sum of in[0..n) into out[0..n], out[n] = total; n read from the device
 int exclusive_scan_u32(ntl_ctx* c, const uint32_t* in, uint32_t* out, const uint32_t* n_dev, uint32_t n_max,
                        DevBuf& blocksums);

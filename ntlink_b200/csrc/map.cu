@@ -24,9 +24,11 @@ inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) /
 
 // ------------------------------------------------------------------------------------------- index
 __global__ void k_index_insert(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ ctg,
-                               const uint32_t* __restrict__ posf, uint64_t n, IdxEntry* __restrict__ table,
-                               uint64_t mask, uint8_t* __restrict__ dupflag, IdxSpecial* __restrict__ special) {
+                               const uint32_t* __restrict__ posf, uint64_t n, const uint32_t* __restrict__ n_src,
+                               IdxEntry* __restrict__ table, uint64_t mask, uint8_t* __restrict__ dupflag,
+                               IdxSpecial* __restrict__ special) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_src && *n_src < n) n = *n_src;          // n is an upper bound after a deferred sketch; the exact count is on the device
     if (i >= n) return;
     const uint64_t key = hash[i];
     if (key == NTL_EMPTY_KEY) {
@@ -396,8 +398,10 @@ static int grow_preserve(ntl_ctx* c, DevBuf& b, size_t keep, size_t need) {
 }
 
 // Build the replicated target index from device-resident minimizer triples.
+// n_dev != null: n is an upper bound, the exact count is read on the device. sync = false: nothing is waited for (the
+// caller guarantees that h_ctg_len / h_name_rank stay valid until the stream has consumed them, e.g. pinned buffers it owns).
 int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg, const uint32_t* d_posf, uint64_t n,
-                       const uint32_t* h_ctg_len, const uint32_t* h_name_rank, uint32_t ncontig) {
+                       const uint32_t* h_ctg_len, const uint32_t* h_name_rank, uint32_t ncontig, const uint32_t* n_dev, bool sync) {
     TargetIndex& X = c->index;
     uint64_t slots = 1024;
     while (slots < 2 * n) slots <<= 1;
@@ -419,7 +423,7 @@ int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg
     NTL_CUDA(c, cudaMemcpyAsync(X.ctg_len.p, h_ctg_len, (size_t)ncontig * 4, cudaMemcpyHostToDevice, c->stream));
     NTL_CUDA(c, cudaMemcpyAsync(X.name_rank.p, h_name_rank, (size_t)ncontig * 4, cudaMemcpyHostToDevice, c->stream));
     if (n) {
-        k_index_insert<<<div_up(n, 256), 256, 0, c->stream>>>(d_hash, d_ctg, d_posf, n, X.table.as<IdxEntry>(), slots - 1,
+        k_index_insert<<<div_up(n, 256), 256, 0, c->stream>>>(d_hash, d_ctg, d_posf, n, n_dev, X.table.as<IdxEntry>(), slots - 1,
                                                              X.dupflag.as<uint8_t>(), X.special.as<IdxSpecial>());
         c->launches++;
     }
@@ -428,8 +432,16 @@ int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg
     c->launches++;
     tock(c, T_INDEX);
     NTL_CUDA(c, cudaGetLastError());
-    NTL_CUDA(c, cudaStreamSynchronize(c->stream));   // h_ctg_len / h_name_rank are caller memory
+    if (sync) NTL_CUDA(c, cudaStreamSynchronize(c->stream));   // h_ctg_len / h_name_rank are caller memory
     X.built = true;
+    return NTL_OK;
+}
+// note the exact number of minimizers of a deferred index build in the call state
+__global__ void k_call_note_mx(const uint32_t* __restrict__ n_mx, CallState* __restrict__ call) { call->mx_total = *n_mx; }
+int call_note_mx(ntl_ctx* c, const uint32_t* n_dev, CallState* call) {
+    k_call_note_mx<<<1, 1, 0, c->stream>>>(n_dev, call);
+    c->launches++;
+    NTL_CUDA(c, cudaGetLastError());
     return NTL_OK;
 }
 

@@ -623,7 +623,7 @@ retry:
     if (call_state) {
         // deferred pass: the output is sized by an upper bound (random sequence has 2/(w+1) minimizers per position;
         // 30 % head room, never more than one per position) and nobody waits for the counters
-        out_cap = (uint32_t)std::min<uint64_t>(total_bases, (uint64_t)(2.6 * (double)total_bases / ((double)w + 1.0)) + 8ull * nseq + 4096);
+        out_cap = sketch_out_bound(total_bases, nseq, w);
         out.n_mx = out_cap;
         goto emit;
     }
