@@ -65,13 +65,16 @@ static unsigned char CODE[256];
 static const uint64_t SEED[5] = { SEED_A, SEED_C, SEED_G, SEED_T, 0 };
 static const uint64_t SEED_RC[5] = { SEED_T, SEED_G, SEED_C, SEED_A, 0 }; /* seed of the complement */
 
-static void init_tables(void) {
-    static int done = 0;
-    if (done) return;
+/* thread-safe: the first sketches of a process may run on several worker threads at once, and a second thread
+ * re-initialising the table (memset to "invalid") under a running sketch would make valid bases look like N */
+static void init_tables_once(void) {
     memset(CODE, 4, sizeof CODE);
     CODE['A'] = CODE['a'] = 0; CODE['C'] = CODE['c'] = 1;
     CODE['G'] = CODE['g'] = 2; CODE['T'] = CODE['t'] = 3;
-    done = 1;
+}
+static void init_tables(void) {
+    static pthread_once_t once = PTHREAD_ONCE_INIT;
+    pthread_once(&once, init_tables_once);
 }
 
 /* split rotate left by 1: low 33 bits and high 31 bits rotate separately (bit32->bit0, bit63->bit33) */

@@ -34,7 +34,12 @@ def main():
     batch = SeqBatch(seq, offs, [f"s{i}" for i in range(len(lens))])
     ns = min(len(lens), 200)
     ctx = Context(0)
-    for k, w in [(32, 100), (24, 250), (40, 100), (20, 10), (15, 5)]:
+    if os.environ.get("NTL_STRIP_LEN"):
+        ctx.set_option("strip_len", float(os.environ["NTL_STRIP_LEN"]))
+    configs = [(32, 100), (24, 250), (40, 100), (20, 10), (15, 5)]
+    if os.environ.get("SWEEP_KW"):
+        configs = [tuple(int(v) for v in kw.split(",")) for kw in os.environ["SWEEP_KW"].split()]
+    for k, w in configs:
         for _ in range(2):
             ctx.sketch(batch, k, w)
         ctx.timing_reset()
