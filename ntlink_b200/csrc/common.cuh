@@ -122,6 +122,7 @@ struct PreMappings {          // accepted runs/hits supplied by the host (checkp
 
 struct TallyWork {
     DevBuf keys, pn, panchor, pfirst, ev_slot, gap_off, cursor, gkey, gval, nonempty, ppref, out, ndev, bs, skey, sval;
+    PinnedBuf h_stage;        // pair table + gap lists on their way to the host
 };
 
 struct MapWork {

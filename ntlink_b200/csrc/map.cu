@@ -770,12 +770,20 @@ int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>&
                                                               (uint32_t)slots, (ntl_pair*)out.p);
     c->launches++;
     tock(c, T_TALLY);
-    pairs.resize(pair_cap); gaps.resize(n);
-    if (one_sync) TL_CUDA(cudaMemcpyAsync(&n_pairs, ppref.as<uint32_t>() + slots, 4, cudaMemcpyDeviceToHost, c->stream));
-    if (pair_cap) TL_CUDA(cudaMemcpyAsync(pairs.data(), out.p, pair_cap * sizeof(ntl_pair), cudaMemcpyDeviceToHost, c->stream));
-    TL_CUDA(cudaMemcpyAsync(gaps.data(), gval.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    // through a pinned staging buffer: a device->host copy into pageable memory is several times slower, and the copy
+    // is sized by the bound (pair_cap), not by the number of pairs
+    const size_t pair_bytes = pair_cap * sizeof(ntl_pair), gap_bytes = (size_t)n * 4;
+    const size_t cnt_at = (pair_bytes + gap_bytes + 15) & ~(size_t)15;
+    TL_CUDA(T.h_stage.ensure(cnt_at + 64));
+    char* hs = T.h_stage.as<char>();
+    if (one_sync) TL_CUDA(cudaMemcpyAsync(hs + cnt_at, ppref.as<uint32_t>() + slots, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (pair_cap) TL_CUDA(cudaMemcpyAsync(hs, out.p, pair_bytes, cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA(cudaMemcpyAsync(hs + pair_bytes, gval.p, gap_bytes, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA(cudaStreamSynchronize(c->stream));
-    pairs.resize(n_pairs);
+    if (one_sync) n_pairs = *reinterpret_cast<const uint32_t*>(hs + cnt_at);
+    pairs.resize(n_pairs); gaps.resize(n);
+    if (n_pairs) memcpy(pairs.data(), hs, (size_t)n_pairs * sizeof(ntl_pair));
+    memcpy(gaps.data(), hs + pair_bytes, gap_bytes);
 #undef TL_CUDA
     cleanup();
     std::sort(pairs.begin(), pairs.end(), [](const ntl_pair& a, const ntl_pair& b) { return a.first_key < b.first_key; });
