@@ -227,36 +227,46 @@ def gather_events_sync(ctx, rank, world, dist, torch):
 def gather_events(ctx, rank, world, dist, torch):
     """pair events of every rank -> rank 0's device event log, in rank order = global read order: the library writes
     {count, events} into a fixed-capacity device buffer, ONE NCCL all_gather moves them, rank 0 imports the result.
-    One host synchronisation per step (reading the gathered counts, which every rank needs to agree on a retry); the
-    library's stream and the collective's stream are ordered with events, not with the host."""
+    No host synchronisation at all: the library's stream and the collective's stream are ordered with events, the
+    per-rank counts are interpreted on the device (ntl_events_import_device) and rank 0 learns the exact total together
+    with the pair table. The capacity was agreed on by every rank during the warm-up steps (gather_events_sync reads
+    the counts and grows the buffers); an overflow in a later step makes ntl_pairs_finish fail loudly."""
     import ctypes as C
-    if os.environ.get("NTL_GATHER_SYNC"):
-        return gather_events_sync(ctx, rank, world, dist, torch)
+    if os.environ.get("NTL_GATHER_SYNC") or not _gather_buf.get("agreed"):
+        gather_events_sync(ctx, rank, world, dist, torch)
+        return
     dev = torch.device("cuda", torch.cuda.current_device())
     if "stream" not in _gather_buf:
         sp = C.c_void_p()
         ctx._check(ctx.lib.ntl_stream(ctx.h, C.byref(sp)), "ntl_stream")
         _gather_buf["stream"] = torch.cuda.ExternalStream(sp.value, device=dev)
     lib_stream = _gather_buf["stream"]
-    while True:
-        cap = _gather_buf.get("cap", 8192)
-        if _gather_buf.get("send") is None or _gather_buf["send"].shape[0] != (cap + 1) * 6:
-            _gather_buf["send"] = torch.zeros((cap + 1) * 6, device=dev, dtype=torch.int32)
-            _gather_buf["recv"] = torch.zeros(world * (cap + 1) * 6, device=dev, dtype=torch.int32)
-            torch.cuda.synchronize()
-        n = C.c_uint64()
-        ctx._check(ctx.lib.ntl_events_export_async(ctx.h, _gather_buf["send"].data_ptr(), cap, C.byref(n)), "ntl_events_export_async")
-        torch.cuda.current_stream().wait_stream(lib_stream)
-        dist.all_gather_into_tensor(_gather_buf["recv"], _gather_buf["send"])
-        counts = _gather_buf["recv"].view(world, -1)[:, 0].tolist()      # every rank sees every count: same decision
-        if max(counts) <= cap:
-            if rank == 0:
-                cnt = np.array(counts, np.uint32)
-                ctx._check(ctx.lib.ntl_events_import_counts(ctx.h, _gather_buf["recv"].data_ptr(), world, cap, cnt.ctypes.data),
-                           "ntl_events_import_counts")
-            return
-        _gather_buf["cap"] = int(max(counts)) * 2
-        _gather_buf["send"] = None
+    cap = _gather_buf["cap"]
+    n = C.c_uint64()
+    ctx._check(ctx.lib.ntl_events_export_async(ctx.h, _gather_buf["send"].data_ptr(), cap, C.byref(n)), "ntl_events_export_async")
+    if n.value > cap:
+        raise RuntimeError("event exchange buffer too small for this step; run more warm-up steps")
+    torch.cuda.current_stream().wait_stream(lib_stream)
+    dist.all_gather_into_tensor(_gather_buf["recv"], _gather_buf["send"])
+    lib_stream.wait_stream(torch.cuda.current_stream())
+    if rank == 0:
+        ctx._check(ctx.lib.ntl_events_import_device(ctx.h, _gather_buf["recv"].data_ptr(), world, cap), "ntl_events_import_device")
+
+
+def agree_on_gather_capacity(world, dist, torch):
+    "after the warm-up: every rank takes the same capacity (4x the largest count seen, at least 8192 events)"
+    if world == 1 or os.environ.get("NTL_GATHER_SYNC"):
+        return
+    dev = torch.device("cuda", torch.cuda.current_device())
+    seen = int(_gather_buf["recv"].view(world, -1)[:, 0].max().item()) if _gather_buf.get("recv") is not None else 0
+    t = torch.tensor([seen], device=dev, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cap = max(8192, 4 * int(t.item()))
+    _gather_buf["cap"] = cap
+    _gather_buf["send"] = torch.zeros((cap + 1) * 6, device=dev, dtype=torch.int32)
+    _gather_buf["recv"] = torch.zeros(world * (cap + 1) * 6, device=dev, dtype=torch.int32)
+    torch.cuda.synchronize()
+    _gather_buf["agreed"] = True
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -311,6 +321,8 @@ def run_gpu(args, rank, world, local_rank):
 
     for _ in range(args.warmup):
         step_resident()
+    agree_on_gather_capacity(world, dist, torch)
+    step_resident()                                    # one more untimed step on the final exchange path
     for key in ("t_map", "t_gather", "t_pairs"):
         stats[key] = 0.0
     barrier()

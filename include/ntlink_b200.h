@@ -212,6 +212,10 @@ int ntl_events_import_gathered(ntl_ctx* ctx, const void* d_src, uint32_t world, 
 int ntl_stream(ntl_ctx* ctx, void** cuda_stream_out);
 int ntl_events_export_async(ntl_ctx* ctx, void* d_dst, uint64_t cap_events, uint64_t* n_out);
 int ntl_events_import_counts(ntl_ctx* ctx, const void* d_src, uint32_t world, uint64_t cap_events, const uint32_t* counts);
+/* ... and without the host ever reading the counts: the gathered headers are interpreted on the device, the event log
+ * is sized by the bound world * cap_events until ntl_pairs_finish reads the exact count back together with the pair
+ * table; a rank that sent more than cap_events makes ntl_pairs_finish fail with NTL_ERR_WORKSPACE. */
+int ntl_events_import_device(ntl_ctx* ctx, const void* d_src, uint32_t world, uint64_t cap_events);
 int ntl_pairs_finish(ntl_ctx* ctx, ntl_pairs_out* out);
 
 /* ---- host text emitters (byte-identical to the reference's files) -------------------------------

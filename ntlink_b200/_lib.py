@@ -82,6 +82,7 @@ SIGNATURES = {
     "ntl_stream": (C.c_int, [_VP, C.POINTER(C.c_void_p)]),
     "ntl_events_export_async": (C.c_int, [_VP, _VP, C.c_uint64, _U64P]),
     "ntl_events_import_counts": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, _VP]),
+    "ntl_events_import_device": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64]),
     "ntl_events_reset": (C.c_int, [_VP]),
     "ntl_events_append": (C.c_int, [_VP, _VP, C.c_uint64]),
     "ntl_events_count": (C.c_int, [_VP, _U64P]),

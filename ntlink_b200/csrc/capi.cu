@@ -17,6 +17,8 @@ int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, u
 int call_begin(ntl_ctx* c, CallState** call_out);
 int call_reserve_events(ntl_ctx* c, uint32_t nreads);
 int call_note_mx(ntl_ctx* c, const uint32_t* n_dev, CallState* call);
+int events_import_device(ntl_ctx* c, const void* d_src, uint32_t world, uint64_t cap_events);
+int events_resolve_count(ntl_ctx* c);
 int call_chunk_finish(ntl_ctx* c, CallState* call, uint32_t rb, uint32_t nreads, const HostResults* H);
 int call_end(ntl_ctx* c, CallState* call, CallState* host_out);
 int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const Run* runs, const Hit* hits, uint32_t nreads,
@@ -847,10 +849,11 @@ int ntl_liftover_mappings(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* n
 }
 
 // ------------------------------------------------------------------------------------------- pairs
-int ntl_events_reset(ntl_ctx* c) { if (!c) return NTL_ERR_ARG; c->tl_n_events = 0; return NTL_OK; }
-int ntl_events_count(ntl_ctx* c, uint64_t* n) { if (!c || !n) return NTL_ERR_ARG; *n = c->tl_n_events; return NTL_OK; }
+int ntl_events_reset(ntl_ctx* c) { if (!c) return NTL_ERR_ARG; c->tl_n_events = 0; c->tl_count_on_device = false; return NTL_OK; }
+int ntl_events_count(ntl_ctx* c, uint64_t* n) { if (!c || !n) return NTL_ERR_ARG; NTL_TRY(events_resolve_count(c)); *n = c->tl_n_events; return NTL_OK; }
 int ntl_events_device(ntl_ctx* c, uint64_t* n, void** d_events) {
     if (!c) return NTL_ERR_ARG;
+    NTL_TRY(events_resolve_count(c));
     if (n) *n = c->tl_n_events;
     if (d_events) *d_events = c->tl_events.p;
     return NTL_OK;
@@ -859,6 +862,7 @@ int ntl_events_device(ntl_ctx* c, uint64_t* n, void** d_events) {
 static int events_append_impl(ntl_ctx* c, const void* src, uint64_t n, cudaMemcpyKind kind) {
     cudaSetDevice(c->device);
     if (!n) return NTL_OK;
+    NTL_TRY(events_resolve_count(c));
     const size_t keep = c->tl_n_events * sizeof(Event), need = (c->tl_n_events + n + 1) * sizeof(Event);
     if (need > c->tl_events.cap) {
         DevBuf nb;
@@ -885,6 +889,7 @@ int ntl_events_append_device(ntl_ctx* c, const void* d_events, uint64_t n) {
 int ntl_events_export(ntl_ctx* c, void* d_dst, uint64_t cap_events, uint64_t* n_out) {
     if (!c || !d_dst) return NTL_ERR_ARG;
     cudaSetDevice(c->device);
+    NTL_TRY(events_resolve_count(c));
     const uint64_t n = c->tl_n_events, m = std::min(n, cap_events);
     NTL_CUDA(c, c->h_status.ensure(256));
     uint32_t* hdr = c->h_status.as<uint32_t>() + 32;       // pinned scratch (second half of the status block)
@@ -905,6 +910,7 @@ int ntl_stream(ntl_ctx* c, void** stream_out) {
 int ntl_events_export_async(ntl_ctx* c, void* d_dst, uint64_t cap_events, uint64_t* n_out) {
     if (!c || !d_dst) return NTL_ERR_ARG;
     cudaSetDevice(c->device);
+    NTL_TRY(events_resolve_count(c));
     const uint64_t n = c->tl_n_events, m = std::min(n, cap_events);
     // header row through a kernel argument (no pinned scratch that a later call could overwrite while in flight)
     k_export_header<<<1, 32, 0, c->stream>>>((uint32_t*)d_dst, (uint32_t)n);
@@ -935,6 +941,12 @@ int ntl_events_import_counts(ntl_ctx* c, const void* d_src, uint32_t world, uint
     }
     c->tl_n_events = total;
     return NTL_OK;
+}
+
+int ntl_events_import_device(ntl_ctx* c, const void* d_src, uint32_t world, uint64_t cap_events) {
+    if (!c || !d_src || !world || !cap_events) return NTL_ERR_ARG;
+    cudaSetDevice(c->device);
+    return events_import_device(c, d_src, world, cap_events);
 }
 
 int ntl_events_import_gathered(ntl_ctx* c, const void* d_src, uint32_t world, uint64_t cap_events, int* overflow) {

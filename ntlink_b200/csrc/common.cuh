@@ -165,6 +165,8 @@ struct ntl_ctx {
     // tally state (pairs accumulated over calls)
     ntl::DevBuf tl_events;                 // all events appended so far
     uint64_t tl_n_events = 0;
+    ntl::DevBuf tl_count;                  // {exact number of events, overflow flag} after ntl_events_import_device
+    bool tl_count_on_device = false;       // tl_n_events is only an upper bound until the next tally
     // sync-free call state
     ntl::DevBuf call_state;                // ntl::CallState
     uint64_t tl_pending_bound = 0;         // events the chunks in flight may still append (capacity reserved for them)

@@ -244,10 +244,13 @@ __device__ __forceinline__ uint64_t pair_key(const Event& e) {
 }
 __device__ __forceinline__ uint64_t order_key(const Event& e) { return ((uint64_t)e.read << 24) | (e.ord & 0xFFFFFFu); }
 
-__global__ void k_tally_insert(const Event* __restrict__ ev, uint64_t n, unsigned long long* __restrict__ keys,
+// n is exact, or -- after an import whose counts stayed on the device -- an upper bound with the exact count in *n_src
+__global__ void k_tally_insert(const Event* __restrict__ ev, uint64_t n, const uint32_t* __restrict__ n_src,
+                               unsigned long long* __restrict__ keys,
                                uint64_t mask, uint32_t* __restrict__ pn, uint32_t* __restrict__ panchor,
                                unsigned long long* __restrict__ pfirst, uint32_t* __restrict__ ev_slot) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_src && *n_src < n) n = *n_src;
     if (i >= n) return;
     const Event e = ev[i];
     const uint64_t key = pair_key(e);
@@ -263,10 +266,12 @@ __global__ void k_tally_insert(const Event* __restrict__ ev, uint64_t n, unsigne
     ev_slot[i] = (uint32_t)s;
 }
 
-__global__ void k_tally_scatter(const Event* __restrict__ ev, uint64_t n, const uint32_t* __restrict__ ev_slot,
+__global__ void k_tally_scatter(const Event* __restrict__ ev, uint64_t n, const uint32_t* __restrict__ n_src,
+                                const uint32_t* __restrict__ ev_slot,
                                 const uint32_t* __restrict__ gap_off, uint32_t* __restrict__ cursor,
                                 unsigned long long* __restrict__ gkey, int32_t* __restrict__ gval) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_src && *n_src < n) n = *n_src;
     if (i >= n) return;
     const uint32_t s = ev_slot[i];
     const uint32_t p = gap_off[s] + atomicAdd(&cursor[s], 1u);
@@ -456,6 +461,7 @@ int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids) {
 }
 
 int call_reserve_events(ntl_ctx* c, uint32_t nreads);
+int events_resolve_count(ntl_ctx* c);
 
 // Liftover of host mappings (ntl_map_out layout) through the AGP table. The lifted runs/hits stay in c->mw (hit_off,
 // nruns, runs, hits) -- exactly where map_device(pre->resident) expects them -- and the counters are returned.
@@ -518,6 +524,7 @@ int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, 
 int map_device(ntl_ctx* c, const DeviceSketch& sk, const uint32_t* d_read_len, uint32_t nreads, uint64_t first_ordinal,
                const ntl_params* prm, MapStatus* counts_out, uint64_t* log_base_out, const PreMappings* pre, CallState* call) {
     if (!c->index.built) { c->err = "map: no target index (call ntl_index_build first)"; return NTL_ERR_STATE; }
+    if (!call) NTL_TRY(events_resolve_count(c));
     MapWork& M = c->mw;
     const uint32_t n = pre ? pre->n_hits : sk.n_mx;
     MapParams P;
@@ -663,6 +670,7 @@ int call_reserve_events(ntl_ctx* c, uint32_t nreads) {
     return grow_preserve(c, c->tl_events, (c->tl_n_events + c->tl_pending_bound) * sizeof(Event), need);
 }
 int call_begin(ntl_ctx* c, CallState** call_out) {
+    NTL_TRY(events_resolve_count(c));
     NTL_CUDA(c, c->call_state.ensure(sizeof(CallState)));
     NTL_CUDA(c, c->h_status.ensure(256));
     if (c->tl_n_events >= (1ull << 31)) { c->err = "event log too large"; return NTL_ERR_WORKSPACE; }
@@ -709,6 +717,54 @@ int call_end(ntl_ctx* c, CallState* call, CallState* host_out) {
     return NTL_OK;
 }
 
+// after ntl_events_import_device the host only knows a bound of the log size: fetch the exact count (one synchronisation)
+int events_resolve_count(ntl_ctx* c) {
+    if (!c->tl_count_on_device) return NTL_OK;
+    uint32_t cw[2] = {0, 0};
+    NTL_CUDA(c, cudaMemcpyAsync(cw, c->tl_count.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->tl_count_on_device = false;
+    if (cw[1]) { c->tl_n_events = 0; c->err = "a rank sent more events than the exchange buffer holds (ntl_events_import_device)"; return NTL_ERR_WORKSPACE; }
+    c->tl_n_events = cw[0];
+    return NTL_OK;
+}
+
+// Import of the gathered exchange buffers with the per-rank counts left on the device: rank r's events go behind those of
+// the ranks before it; *count = {total, overflow flag}.
+__global__ void k_import_gathered(const uint32_t* __restrict__ src, uint32_t world, uint32_t cap, Event* __restrict__ log,
+                                  uint32_t* __restrict__ count) {
+    const uint32_t r = blockIdx.y;
+    const size_t stride = ((size_t)cap + 1) * 6;                    // words per rank: header row + cap events
+    uint32_t before = 0, ovf = 0;
+    for (uint32_t q = 0; q < world; q++) {
+        const uint32_t cq = src[q * stride];
+        if (cq > cap) ovf = 1;
+        if (q < r) before += min(cq, cap);
+    }
+    const uint32_t mine = min(src[r * stride], cap);
+    if (r == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (uint32_t q = 0; q < world; q++) total += min(src[q * stride], cap);
+        count[0] = total; count[1] = ovf;
+    }
+    const uint32_t* ev = src + r * stride + 6;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(log + before);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < mine * 6; i += gridDim.x * blockDim.x) dst[i] = ev[i];
+}
+int events_import_device(ntl_ctx* c, const void* d_src, uint32_t world, uint64_t cap_events) {
+    const uint64_t bound = (uint64_t)world * cap_events;
+    if (bound >= (1ull << 31)) { c->err = "event exchange buffers too large"; return NTL_ERR_ARG; }
+    NTL_CUDA(c, c->tl_events.ensure((bound + 1) * sizeof(Event)));
+    NTL_CUDA(c, c->tl_count.ensure(16));
+    k_import_gathered<<<dim3(std::max<uint32_t>(1, std::min<uint32_t>(div_up(cap_events * 6, 256), 64)), world), 256, 0, c->stream>>>(
+        (const uint32_t*)d_src, world, (uint32_t)cap_events, c->tl_events.as<Event>(), c->tl_count.as<uint32_t>());
+    c->launches++;
+    NTL_CUDA(c, cudaGetLastError());
+    c->tl_n_events = bound;                  // upper bound until the tally has read the exact count back
+    c->tl_count_on_device = true;
+    return NTL_OK;
+}
+
 // Pair table over the whole device event log.
 int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>& gaps) {
     const uint64_t n = c->tl_n_events;
@@ -743,12 +799,13 @@ int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>&
     }
     const Event* ev = c->tl_events.as<Event>();
     k_set_u32<<<1, 1, 0, c->stream>>>(ndev.as<uint32_t>(), (uint32_t)slots);
-    k_tally_insert<<<div_up(n, 256), 256, 0, c->stream>>>(ev, n, keys.as<unsigned long long>(), slots - 1, pn.as<uint32_t>(),
+    const uint32_t* n_src = c->tl_count_on_device ? c->tl_count.as<uint32_t>() : nullptr;
+    k_tally_insert<<<div_up(n, 256), 256, 0, c->stream>>>(ev, n, n_src, keys.as<unsigned long long>(), slots - 1, pn.as<uint32_t>(),
                                                          panchor.as<uint32_t>(), pfirst.as<unsigned long long>(), ev_slot.as<uint32_t>());
     c->launches += 2;
     rc = exclusive_scan_u32(c, pn.as<uint32_t>(), gap_off.as<uint32_t>(), ndev.as<uint32_t>(), (uint32_t)slots, bs);
     if (rc != NTL_OK) { cleanup(); return rc; }
-    k_tally_scatter<<<div_up(n, 256), 256, 0, c->stream>>>(ev, n, ev_slot.as<uint32_t>(), gap_off.as<uint32_t>(), cursor.as<uint32_t>(),
+    k_tally_scatter<<<div_up(n, 256), 256, 0, c->stream>>>(ev, n, n_src, ev_slot.as<uint32_t>(), gap_off.as<uint32_t>(), cursor.as<uint32_t>(),
                                                           gkey.as<unsigned long long>(), gval.as<int32_t>());
     k_tally_sort<<<div_up(slots, SORT_WARPS), SORT_WARPS * 32, 0, c->stream>>>(pn.as<uint32_t>(), gap_off.as<uint32_t>(), (uint32_t)slots,
                                                            gkey.as<unsigned long long>(), gval.as<int32_t>(), nonempty.as<uint32_t>(),
@@ -773,17 +830,28 @@ int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>&
     // through a pinned staging buffer: a device->host copy into pageable memory is several times slower, and the copy
     // is sized by the bound (pair_cap), not by the number of pairs
     const size_t pair_bytes = pair_cap * sizeof(ntl_pair), gap_bytes = (size_t)n * 4;
+    size_t gap_bytes_copy = gap_bytes;
     const size_t cnt_at = (pair_bytes + gap_bytes + 15) & ~(size_t)15;
     TL_CUDA(T.h_stage.ensure(cnt_at + 64));
     char* hs = T.h_stage.as<char>();
     if (one_sync) TL_CUDA(cudaMemcpyAsync(hs + cnt_at, ppref.as<uint32_t>() + slots, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (n_src) TL_CUDA(cudaMemcpyAsync(hs + cnt_at + 8, n_src, 8, cudaMemcpyDeviceToHost, c->stream));   // {exact count, overflow flag}
     if (pair_cap) TL_CUDA(cudaMemcpyAsync(hs, out.p, pair_bytes, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA(cudaMemcpyAsync(hs + pair_bytes, gval.p, gap_bytes, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA(cudaStreamSynchronize(c->stream));
     if (one_sync) n_pairs = *reinterpret_cast<const uint32_t*>(hs + cnt_at);
-    pairs.resize(n_pairs); gaps.resize(n);
+    uint64_t n_exact = n;
+    if (n_src) {
+        const uint32_t* cw = reinterpret_cast<const uint32_t*>(hs + cnt_at + 8);
+        c->tl_count_on_device = false;
+        if (cw[1]) { c->tl_n_events = 0; c->err = "a rank sent more events than the exchange buffer holds (ntl_events_import_device)"; return NTL_ERR_WORKSPACE; }
+        n_exact = cw[0];
+        c->tl_n_events = n_exact;                                  // from here on the host knows the exact size again
+    }
+    pairs.resize(n_pairs); gaps.resize(n_exact);
+    if (n_exact < n) gap_bytes_copy = (size_t)n_exact * 4;
     if (n_pairs) memcpy(pairs.data(), hs, (size_t)n_pairs * sizeof(ntl_pair));
-    memcpy(gaps.data(), hs + pair_bytes, gap_bytes);
+    memcpy(gaps.data(), hs + pair_bytes, gap_bytes_copy);
 #undef TL_CUDA
     cleanup();
     std::sort(pairs.begin(), pairs.end(), [](const ntl_pair& a, const ntl_pair& b) { return a.first_key < b.first_key; });
