@@ -257,7 +257,8 @@ enum { NTL_T_PACK = 0, NTL_T_DENSE, NTL_T_SELECT, NTL_T_GAP, NTL_T_EMIT, NTL_T_L
        NTL_T_INDEX, NTL_T_TOTAL, NTL_T_NUM };
 int ntl_timing_reset(ntl_ctx* ctx);
 /* counters since ntl_init: "async_calls" (calls that took the sync-free path), "async_fallbacks" (of those, how many had
- * to be repeated on the synchronous path because a capacity bound was too small), "graph_launches" */
+ * to be repeated on the synchronous path because a capacity bound was too small), "graph_launches", "graph_failures" (a
+ * CUDA-graph step failed: graphs are then switched off for the context and plain launches are used) */
 int ntl_get_stat(ntl_ctx* ctx, const char* name, double* value);
 int ntl_timing(ntl_ctx* ctx, double* ms_accum /* [NTL_T_NUM] */, uint64_t* launches, uint64_t* dense_launches,
                uint64_t* dense_bases);

@@ -88,6 +88,20 @@ static void parallel_memcpy(char* dst, const char* src, size_t n, int threads) {
     memcpy(dst, src, std::min(per, n));
     for (auto& x : th) x.join();
 }
+// A CUDA-graph step failed (capture, instantiate or launch): graphs are switched off for this context and the caller
+// falls back to plain launches -- slower next to a host->device copy, never wrong.
+// tests only: NTL_TEST_GRAPH_FAIL=1 fails every graph step, =map only the second chunk of ntl_map_reads
+static bool inject_graph_failure(const char* site) {
+    static const char* v = getenv("NTL_TEST_GRAPH_FAIL");
+    return v && (!strcmp(v, "1") || !strcmp(v, site));
+}
+static void graph_failed(ntl_ctx* c, const char* what, cudaError_t e) {
+    c->graph_mode = 0;
+    c->capturing = false; c->no_stage_timing = false;
+    c->n_graph_failures++;
+    cudaGetLastError();
+    if (getenv("NTL_TRACE")) fprintf(stderr, "[ntl] %s failed (%s): CUDA graphs disabled for this context\n", what, cudaGetErrorString(e));
+}
 static double host_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static Results* res_of(ntl_ctx* c) { return static_cast<Results*>(c->res); }
 
@@ -275,9 +289,10 @@ static int index_build_async(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d
         c->capturing = true;
         const int rc = enqueue();
         c->capturing = false;
-        const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
         if (rc != NTL_OK) { if (graph) cudaGraphDestroy(graph); c->index.built = false; return rc; }
-        if (ce != cudaSuccess) { c->index.built = false; c->err = std::string("graph capture: ") + cudaGetErrorString(ce); return NTL_ERR_CUDA; }
+        if (ce == cudaSuccess && inject_graph_failure("index")) { cudaGraphDestroy(graph); graph = nullptr; ce = cudaErrorUnknown; }
+        if (ce != cudaSuccess) { c->index.built = false; graph_failed(c, "graph capture", ce); return NTL_OK; }
         if (R->index_exec) {
             cudaGraphExecUpdateResultInfo info;
             if (cudaGraphExecUpdate(R->index_exec, graph, &info) != cudaSuccess) {
@@ -288,7 +303,7 @@ static int index_build_async(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d
         }
         if (!R->index_exec) {
             const cudaError_t ie = cudaGraphInstantiate(&R->index_exec, graph, 0);
-            if (ie != cudaSuccess) { cudaGraphDestroy(graph); R->index_exec = nullptr; c->index.built = false; c->err = std::string("graph instantiate: ") + cudaGetErrorString(ie); return NTL_ERR_CUDA; }
+            if (ie != cudaSuccess) { cudaGraphDestroy(graph); R->index_exec = nullptr; c->index.built = false; graph_failed(c, "graph instantiate", ie); return NTL_OK; }
         }
         cudaGraphDestroy(graph);
         NTL_CUDA(c, cudaGraphLaunch(R->index_exec, c->stream));
@@ -622,10 +637,11 @@ static int map_reads_async(ntl_ctx* c, const char* seq, const uint64_t* offsets,
             if (rc == NTL_OK) rc = map_device(c, c->dsk, R->read_len.as<uint32_t>(), ns, first_read_ordinal + b, prm, nullptr, nullptr, nullptr, call);
             if (rc == NTL_OK) rc = call_chunk_finish(c, call, b, ns, &H);
             c->capturing = false; c->no_stage_timing = false;
-            const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
             const double h1 = trace ? host_now_us() : 0;
             if (rc != NTL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (ce != cudaSuccess) { c->err = std::string("graph capture: ") + cudaGetErrorString(ce); return NTL_ERR_CUDA; }
+            if (ce == cudaSuccess && inject_graph_failure("map") && i == 1) { cudaGraphDestroy(graph); graph = nullptr; ce = cudaErrorUnknown; }
+            if (ce != cudaSuccess) { graph_failed(c, "graph capture", ce); return NTL_OK; }      // *ok is false: synchronous path
             cudaGraphExec_t exec = i < execs.size() ? execs[i] : nullptr;
             if (exec) {
                 cudaGraphExecUpdateResultInfo info;
@@ -637,7 +653,7 @@ static int map_reads_async(ntl_ctx* c, const char* seq, const uint64_t* offsets,
             }
             if (!exec) {
                 const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-                if (ie != cudaSuccess) { cudaGraphDestroy(graph); if (i < execs.size()) execs[i] = nullptr; c->err = std::string("graph instantiate: ") + cudaGetErrorString(ie); return NTL_ERR_CUDA; }
+                if (ie != cudaSuccess) { cudaGraphDestroy(graph); if (i < execs.size()) execs[i] = nullptr; graph_failed(c, "graph instantiate", ie); return NTL_OK; }
             }
             cudaGraphDestroy(graph);
             if (i < execs.size()) execs[i] = exec; else execs.push_back(exec);
@@ -1022,6 +1038,7 @@ int ntl_map_resident(ntl_ctx* c, uint64_t first_read_ordinal, const ntl_params* 
             tock(c, T_TOTAL);
             return NTL_OK;
         };
+        bool launched = false;
         if (c->graph_mode) {
             NTL_TRY(sketch_prepare(c, (uint32_t)prm->k));
             NTL_TRY(call_reserve_events(c, R->r_nreads));
@@ -1030,10 +1047,10 @@ int ntl_map_resident(ntl_ctx* c, uint64_t first_read_ordinal, const ntl_params* 
             c->capturing = true;
             const int rc = enqueue();
             c->capturing = false;
-            const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            cudaError_t ge = cudaStreamEndCapture(c->stream, &graph);
             if (rc != NTL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (ce != cudaSuccess) { c->err = std::string("graph capture: ") + cudaGetErrorString(ce); return NTL_ERR_CUDA; }
-            if (R->resident_exec) {
+            if (ge == cudaSuccess && inject_graph_failure("resident")) ge = cudaErrorUnknown;
+            if (ge == cudaSuccess && R->resident_exec) {
                 cudaGraphExecUpdateResultInfo info;
                 if (cudaGraphExecUpdate(R->resident_exec, graph, &info) != cudaSuccess) {
                     cudaGetLastError();
@@ -1041,16 +1058,16 @@ int ntl_map_resident(ntl_ctx* c, uint64_t first_read_ordinal, const ntl_params* 
                     R->resident_exec = nullptr;
                 }
             }
-            if (!R->resident_exec) {
-                const cudaError_t ie = cudaGraphInstantiate(&R->resident_exec, graph, 0);
-                if (ie != cudaSuccess) { cudaGraphDestroy(graph); R->resident_exec = nullptr; c->err = std::string("graph instantiate: ") + cudaGetErrorString(ie); return NTL_ERR_CUDA; }
+            if (ge == cudaSuccess && !R->resident_exec) {
+                ge = cudaGraphInstantiate(&R->resident_exec, graph, 0);
+                if (ge != cudaSuccess) R->resident_exec = nullptr;
             }
-            cudaGraphDestroy(graph);
-            NTL_CUDA(c, cudaGraphLaunch(R->resident_exec, c->stream));
-            c->n_graph_launches++;
-        } else {
-            NTL_TRY(enqueue());
+            if (graph) cudaGraphDestroy(graph);
+            if (ge == cudaSuccess) ge = cudaGraphLaunch(R->resident_exec, c->stream);
+            if (ge == cudaSuccess) { c->n_graph_launches++; launched = true; }
+            else graph_failed(c, "graph step of ntl_map_resident", ge);        // plain launches below
         }
+        if (!launched) NTL_TRY(enqueue());
         CallState hs;
         NTL_TRY(call_end(c, call, &hs));
         collect_timing(c);
@@ -1146,6 +1163,7 @@ int ntl_get_stat(ntl_ctx* c, const char* name, double* value) {
     if (!strcmp(name, "async_calls")) *value = (double)c->n_async_calls;
     else if (!strcmp(name, "async_fallbacks")) *value = (double)c->n_async_fallbacks;
     else if (!strcmp(name, "graph_launches")) *value = (double)c->n_graph_launches;
+    else if (!strcmp(name, "graph_failures")) *value = (double)c->n_graph_failures;
     else { c->err = std::string("unknown stat ") + name; return NTL_ERR_ARG; }
     return NTL_OK;
 }

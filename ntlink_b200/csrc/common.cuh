@@ -172,7 +172,7 @@ struct ntl_ctx {
     uint64_t tl_pending_bound = 0;         // events the chunks in flight may still append (capacity reserved for them)
     uint32_t ev_cap_hint = 0;              // event buffer size that was enough so far
     int async_mode = 1;                    // 0: always take the synchronous path (option "async")
-    uint64_t n_async_calls = 0, n_async_fallbacks = 0, n_graph_launches = 0;   // ntl_get_stat
+    uint64_t n_async_calls = 0, n_async_fallbacks = 0, n_graph_launches = 0, n_graph_failures = 0;   // ntl_get_stat
     int copy_threads = -1;                 // host threads of the pageable->pinned bounce copy (-1 auto, 0 = off)
     int graph_mode = 1;                    // sync-free ntl_map_reads: one CUDA graph per chunk (option "graph")
     bool capturing = false;                // c->stream is being captured: no synchronisation, no allocation-by-copy
