@@ -18,6 +18,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -303,6 +304,11 @@ struct ntl_seqfile {
     std::string carry;           // assembled line that straddled two blocks
     std::string pending;         // header line read ahead
     bool have_pending = false;
+    // parallel mode (plain FASTA files): the reader works on byte ranges of the file, ppos = next unread record
+    bool parallel = false;
+    off_t ppos = 0, fsize = 0;
+    int threads = 1;
+    const char* map = nullptr;   // the whole file, mapped read-only
 
     bool fill() {
         if (eof) return false;
@@ -343,6 +349,178 @@ struct ntl_seqfile {
     }
 };
 
+namespace {
+
+struct ParRec { uint64_t byte_start; uint64_t name_at; uint32_t name_len; uint64_t seq_len; uint64_t body_start; };
+struct ParSeg {
+    GrowBuf names;
+    std::vector<ParRec> recs;
+    bool not_fasta = false, ok = true;
+    ParSeg() = default;
+    ParSeg(const ParSeg&) = delete;
+    ~ParSeg() { free(names.p); }
+};
+
+// pass 1: the records of raw[b, e) (b is a record start or the first byte of the range): names and sequence lengths
+void scan_segment(const char* raw, size_t b, size_t e, ParSeg& g) {
+    size_t p = b;
+    bool in_rec = false;
+    g.ok = g.names.reserve(1u << 12);
+    while (g.ok && p < e) {
+        const char* nl = (const char*)memchr(raw + p, '\n', e - p);
+        const size_t le = nl ? (size_t)(nl - raw) : e;          // end of the line (exclusive)
+        size_t ll = le - p;
+        if (ll && raw[p + ll - 1] == '\r') ll--;
+        const char c0 = ll ? raw[p] : 0;
+        if (c0 == '>') {
+            size_t t = 1;
+            while (t < ll && raw[p + t] != ' ' && raw[p + t] != '\t' && raw[p + t] != '\v' && raw[p + t] != '\f' && raw[p + t] != '\r') t++;
+            ParRec r; r.byte_start = p; r.name_at = g.names.n; r.name_len = (uint32_t)(t - 1); r.seq_len = 0; r.body_start = le + 1;
+            g.ok = g.names.append(raw + p + 1, t - 1);
+            g.recs.push_back(r);
+            in_rec = true;
+        } else if (c0 == '@' || c0 == '+') {
+            g.not_fasta = true;                                   // FASTQ-like content: the sequential reader decides
+            return;
+        } else if (in_rec) {
+            g.recs.back().seq_len += ll;
+        }
+        p = le + 1;
+    }
+}
+
+// pass 2: the sequence lines of one record (raw[body, end)) without their terminators -> dst
+void copy_body(const char* raw, size_t body, size_t end, char* dst) {
+    size_t p = body;
+    while (p < end) {
+        const char* nl = (const char*)memchr(raw + p, '\n', end - p);
+        const size_t le = nl ? (size_t)(nl - raw) : end;
+        size_t ll = le - p;
+        if (ll && raw[p + ll - 1] == '\r') ll--;
+        memcpy(dst, raw + p, ll);
+        dst += ll;
+        p = le + 1;
+    }
+}
+
+// next record start ("\n>" + 1) at or after position p, or e
+size_t next_record_start(const char* raw, size_t p, size_t e) {
+    if (p == 0) return 0;
+    while (p < e) {
+        const char* nl = (const char*)memchr(raw + p - 1, '\n', e - (p - 1));
+        if (!nl) return e;
+        const size_t q = (size_t)(nl - raw) + 1;
+        if (q >= e) return e;
+        if (raw[q] == '>') return q;
+        p = q + 1;
+    }
+    return e;
+}
+
+template <class F>
+void run_threads(size_t n, F&& body) {
+    std::vector<std::thread> th;
+    for (size_t g = 1; g < n; g++) th.emplace_back([&, g]() { body(g); });
+    if (n) body(0);
+    for (auto& x : th) x.join();
+}
+
+// Parallel FASTA batch straight from the mapped file: pass 1 finds the records of every segment, pass 2 copies the
+// sequence lines to their final place. Returns 1 = batch produced, 0 = not applicable (the caller uses the sequential
+// reader from f->ppos), -1 = out of memory.
+int read_parallel(ntl_seqfile* f, uint64_t max_bases, GrowBuf& seq, GrowBuf& names, std::vector<uint64_t>& offs,
+                  std::vector<uint64_t>& noffs) {
+    const off_t start = f->ppos;
+    if (start >= f->fsize) return 1;                               // end of file: empty batch
+    if (!f->map) {
+        void* m = mmap(nullptr, (size_t)f->fsize, PROT_READ, MAP_PRIVATE, f->fd, 0);
+        if (m == MAP_FAILED) { f->parallel = false; return 0; }
+        f->map = (const char*)m;
+        madvise(m, (size_t)f->fsize, MADV_SEQUENTIAL);
+    }
+    const char* raw = f->map + start;
+    uint64_t want = max_bases ? max_bases + max_bases / 16 + (16u << 20) : (uint64_t)(f->fsize - start);
+    size_t n = 0, cut = 0;
+    for (;;) {
+        n = (size_t)std::min<uint64_t>(want, (uint64_t)(f->fsize - start));
+        if (start + (off_t)n >= f->fsize) { cut = n; break; }       // the rest of the file: every record is complete
+        // cut at the last record start in the range; a range without one (a record larger than the range) grows
+        size_t q = n;
+        cut = 0;
+        while (q > 1) {
+            const char* gt = (const char*)memrchr(raw, '>', q);
+            if (!gt) break;
+            const size_t at = (size_t)(gt - raw);
+            if (at > 0 && raw[at - 1] == '\n') { cut = at; break; }
+            q = at;
+        }
+        if (cut > 0) break;
+        want *= 2;
+    }
+    // segments at record starts
+    std::vector<size_t> bounds;
+    bounds.push_back(0);
+    for (int t = 1; t < f->threads; t++) {
+        const size_t b = next_record_start(raw, (size_t)((uint64_t)cut * t / f->threads), cut);
+        if (b > bounds.back() && b < cut) bounds.push_back(b);
+    }
+    bounds.push_back(cut);
+    const size_t nseg = bounds.size() - 1;
+    std::unique_ptr<ParSeg[]> segs(new ParSeg[nseg]);
+    run_threads(nseg, [&](size_t g) { scan_segment(raw, bounds[g], bounds[g + 1], segs[g]); });
+    for (size_t g = 0; g < nseg; g++) {
+        if (!segs[g].ok) return -1;
+        if (segs[g].not_fasta) { f->parallel = false; return 0; }
+    }
+    // how many records make the batch (bin/read_fasta.py semantics: whole records until max_bases is reached)
+    uint64_t total = 0, names_total = 0;
+    off_t next_pos = start + (off_t)cut;
+    size_t last_seg = nseg, last_cnt = 0;
+    bool full = false;
+    for (size_t g = 0; g < nseg && !full; g++) {
+        for (size_t r = 0; r < segs[g].recs.size(); r++) {
+            if (max_bases && total >= max_bases) {
+                next_pos = start + (off_t)segs[g].recs[r].byte_start;
+                last_seg = g; last_cnt = r; full = true;
+                break;
+            }
+            total += segs[g].recs[r].seq_len; names_total += segs[g].recs[r].name_len;
+        }
+    }
+    if (!seq.reserve(total + 64) || !names.reserve(names_total + 1)) return -1;
+    // offsets and names, then the sequence bytes of every segment in parallel, straight to their final place
+    std::vector<uint64_t> seg_seq_at(nseg, 0);
+    std::vector<size_t> seg_cnt(nseg, 0);
+    uint64_t so = 0, no = 0;
+    for (size_t g = 0; g < nseg; g++) {
+        const size_t cnt = full ? (g < last_seg ? segs[g].recs.size() : g == last_seg ? last_cnt : 0) : segs[g].recs.size();
+        seg_seq_at[g] = so; seg_cnt[g] = cnt;
+        for (size_t r = 0; r < cnt; r++) {
+            const ParRec& rec = segs[g].recs[r];
+            memcpy(names.p + no, segs[g].names.p + rec.name_at, rec.name_len);
+            no += rec.name_len;
+            noffs.push_back(no);
+            so += rec.seq_len;
+            offs.push_back(so);
+        }
+    }
+    names.n = no;
+    run_threads(nseg, [&](size_t g) {
+        uint64_t at = seg_seq_at[g];
+        for (size_t r = 0; r < seg_cnt[g]; r++) {
+            const ParRec& rec = segs[g].recs[r];
+            const size_t end = r + 1 < segs[g].recs.size() ? (size_t)segs[g].recs[r + 1].byte_start : bounds[g + 1];
+            copy_body(raw, (size_t)rec.body_start, end, seq.p + at);
+            at += rec.seq_len;
+        }
+    });
+    seq.n = so;
+    f->ppos = next_pos;
+    return 1;
+}
+
+}  // namespace
+
 extern "C" {
 
 int ntl_seqfile_open(const char* path, ntl_seqfile** out) {
@@ -363,6 +541,15 @@ int ntl_seqfile_open(const char* path, ntl_seqfile** out) {
 #ifdef POSIX_FADV_SEQUENTIAL
             posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
 #endif
+            // a regular file that starts like FASTA is parsed by several threads (ntl_seqfile_read falls back to the
+            // sequential reader the moment it meets something that is not plain FASTA)
+            struct stat sb;
+            const char* env = getenv("NTL_READER_THREADS");
+            const unsigned hw = std::thread::hardware_concurrency();
+            f->threads = env ? atoi(env) : (int)std::max(1u, std::min(8u, hw / 2));
+            if (f->threads > 1 && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && got >= 1 && magic[0] == '>') {
+                f->parallel = true; f->fsize = sb.st_size; f->ppos = 0;
+            }
         }
     }
     if (!f->gz && f->fd < 0) { delete f; return NTL_ERR_ARG; }
@@ -378,6 +565,26 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_
     std::vector<uint64_t> offs(1, 0), noffs(1, 0);
     const char* lp = nullptr;
     size_t ll = 0;
+    if (f->parallel) {
+        const int pr = read_parallel(f, max_bases, seq, names, offs, noffs);
+        if (pr < 0) { free(seq.p); free(names.p); return NTL_ERR_ARG; }
+        if (pr == 1) {
+            const uint32_t nseq_p = (uint32_t)(offs.size() - 1);
+            uint64_t* o = (uint64_t*)malloc(offs.size() * 8);
+            uint64_t* no = (uint64_t*)malloc(noffs.size() * 8);
+            if (!o || !no || !seq.reserve(seq.n + 64) || !names.reserve(names.n + 1)) { free(seq.p); free(names.p); free(o); free(no); return NTL_ERR_ARG; }
+            memset(seq.p + seq.n, 'N', 64);
+            memcpy(o, offs.data(), offs.size() * 8);
+            memcpy(no, noffs.data(), noffs.size() * 8);
+            *seq_out = seq.p; *offsets_out = o; *names_out = names.p; *name_off_out = no; *nseq_out = nseq_p;
+            return NTL_OK;
+        }
+        // not plain FASTA after all: continue sequentially from the first unread record
+        free(seq.p); free(names.p); seq = GrowBuf(); names = GrowBuf();
+        offs.assign(1, 0); noffs.assign(1, 0);
+        lseek(f->fd, f->ppos, SEEK_SET);
+        f->pos = f->len = 0; f->eof = false; f->have_pending = false;
+    }
     // plain files: what is left of the file bounds the batch, so the buffer never has to grow
     size_t hint = 1u << 20;
     if (f->fd >= 0) {
@@ -435,6 +642,7 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_
 void ntl_seqfile_close(ntl_seqfile* f) {
     if (!f) return;
     if (f->gz) gzclose(f->gz);
+    if (f->map) munmap((void*)f->map, (size_t)f->fsize);
     if (f->fd >= 0) ::close(f->fd);
     delete f;
 }

@@ -104,3 +104,39 @@ def test_zero_copy_arrays_keep_their_buffer_alive(tmp_path):
     empty = os.path.join(str(tmp_path), "empty.fa")
     open(empty, "w").close()
     assert len(api.read_sequences(empty)) == 0
+
+
+def _records(path, max_bases, threads):
+    os.environ["NTL_READER_THREADS"] = str(threads)
+    try:
+        out, sizes = [], []
+        for batch in api.prefetch_batches([path], max_bases):
+            sizes.append(int(batch.offsets[-1]))
+            out += [(n, batch.seq[int(a):int(b)].tobytes()) for n, a, b in zip(batch.names, batch.offsets, batch.offsets[1:])]
+        return out, sizes
+    finally:
+        del os.environ["NTL_READER_THREADS"]
+
+
+@pytest.mark.parametrize("width,crlf,tail", [(60, False, ""), (0, False, ""), (71, True, ""), (60, False, "fastq"), (60, False, "junk")])
+def test_parallel_fasta_reader_equals_sequential(tmp_path, width, crlf, tail):
+    "plain FASTA files are parsed by several threads from the mapped file; same records and same batch cuts as one thread"
+    rng = np.random.default_rng(width + 5)
+    text = "leading line without a header\n" + make_text(rng, 4000, False, width)
+    if tail == "fastq":                       # FASTQ records after FASTA ones: the parallel reader must hand over
+        text += make_text(rng, 50, True, 0)
+    elif tail == "junk":
+        text += ">last no newline at the end\nACGTACGT"
+    if crlf:
+        text = text.replace("\n", "\r\n")
+    path = os.path.join(str(tmp_path), "p.fa")
+    with open(path, "w", newline="") as fout:
+        fout.write(text)
+    want = [(n, s.encode()) for n, s in reference_parse(text.replace("\r\n", "\n"))]
+    for max_bases in (0, 200_000, 3_000):
+        seq_recs, seq_sizes = _records(path, max_bases, 1)
+        for threads in (2, 5):
+            par_recs, par_sizes = _records(path, max_bases, threads)
+            assert par_recs == seq_recs == want
+            if tail != "fastq":               # after a hand-over the cuts may differ, the records may not
+                assert par_sizes == seq_sizes
