@@ -532,7 +532,7 @@ static int map_reads_async(ntl_ctx* c, const char* seq, const uint64_t* offsets,
         const uint64_t nb = offsets[bounds[i + 1]] - offsets[bounds[i]];
         if (nb >= (1ull << 32) - 4096) return NTL_OK;          // let the synchronous path report it
         max_nb = std::max(max_nb, nb); max_ns = std::max(max_ns, bounds[i + 1] - bounds[i]);
-        const uint64_t b = std::min<uint64_t>(nb, (uint64_t)(2.6 * (double)nb / ((double)prm->w + 1.0)) + 8ull * (bounds[i + 1] - bounds[i]) + 4096);
+        const uint64_t b = sketch_out_bound(nb, bounds[i + 1] - bounds[i], (uint32_t)prm->w, c->mx_density_factor);
         if ((uint64_t)mx_bound_total + b >= (1ull << 31)) return NTL_OK;
         mx_bound_total += (uint32_t)b;
     }
@@ -692,6 +692,7 @@ static int map_reads_async(ntl_ctx* c, const char* seq, const uint64_t* offsets,
     }
     if (hs.err) return NTL_OK;                                  // *ok stays false
     R->last_call_hits = hs.hits_total; R->last_call_bases = total_bases;
+    note_mx_density(c, hs.mx_total, total_bases, (uint32_t)prm->w);
     R->runs.used = (size_t)hs.hits_total * sizeof(ntl_run); R->hits.used = (size_t)hs.hits_total * sizeof(ntl_hit);
     R->events.used = (size_t)hs.ev_total * sizeof(ntl_event);
     fill_map_out(c, out, nreads, hs.mx_total, hs.hits_total, hs.runs_total, hs.ev_total);
@@ -754,6 +755,7 @@ int ntl_map_reads(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t
         mx_total += c->dsk.n_mx; runs_total += cs.n_runs;
     }
     fill_map_out(c, out, nreads, mx_total, hits_total, runs_total, ev_total);
+    R->last_call_hits = hits_total; R->last_call_bases = total_bases;      // what the sync-free path sizes its host arrays from
     return NTL_OK;
 }
 

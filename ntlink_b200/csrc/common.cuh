@@ -173,6 +173,7 @@ struct ntl_ctx {
     uint32_t ev_cap_hint = 0;              // event buffer size that was enough so far
     int async_mode = 1;                    // 0: always take the synchronous path (option "async")
     uint64_t n_async_calls = 0, n_async_fallbacks = 0, n_graph_launches = 0, n_graph_failures = 0;   // ntl_get_stat
+    double mx_density_factor = 2.6;        // minimizers per base * (w + 1), upper estimate (see sketch_out_bound)
     int copy_threads = -1;                 // host threads of the pageable->pinned bounce copy (-1 auto, 0 = off)
     int graph_mode = 1;                    // sync-free ntl_map_reads: one CUDA graph per chunk (option "graph")
     bool capturing = false;                // c->stream is being captured: no synchronisation, no allocation-by-copy
@@ -208,9 +209,11 @@ int sketch_prepare(ntl_ctx* c, uint32_t k);
 int index_build_device(ntl_ctx* c, const uint64_t* d_hash, const uint32_t* d_ctg, const uint32_t* d_posf, uint64_t n,
                        const uint32_t* h_ctg_len, const uint32_t* h_name_rank, uint32_t ncontig, const uint32_t* n_dev = nullptr,
                        bool sync = true);
-// upper bound of the number of minimizers a deferred sketch pass reserves room for
-inline uint32_t sketch_out_bound(uint64_t total_bases, uint32_t nseq, uint32_t w) {
-    return (uint32_t)std::min<uint64_t>(total_bases, (uint64_t)(2.6 * (double)total_bases / ((double)w + 1.0)) + 8ull * nseq + 4096);
+// Upper bound of the number of minimizers a deferred sketch pass reserves room for: random sequence has 2/(w+1) per
+// base; `factor` (ntl_ctx::mx_density_factor, >= 2.6) follows the densest input this context has seen, so that a run on
+// low-complexity data pays the fallback to the synchronous path once, not for every batch.
+inline uint32_t sketch_out_bound(uint64_t total_bases, uint32_t nseq, uint32_t w, double factor) {
+    return (uint32_t)std::min<uint64_t>(total_bases, (uint64_t)(factor * (double)total_bases / ((double)w + 1.0)) + 8ull * nseq + 4096);
 }
 // scan utility (scan.cu): exclusive prefix sum of in[0..n) into out[0..n], out[n] = total; n read from the device
 int exclusive_scan_u32(ntl_ctx* c, const uint32_t* in, uint32_t* out, const uint32_t* n_dev, uint32_t n_max,
@@ -228,6 +231,11 @@ static __global__ void k_fill_segs(FillSegs s) {
 }
 // inside a stream capture the records become event-record nodes of the graph (cudaEventRecordExternal), so the stage
 // times of a graph launch can be read like those of plain launches
+inline void note_mx_density(ntl_ctx* c, uint64_t n_mx, uint64_t bases, uint32_t w) {
+    if (bases < 100000) return;                                   // too small to say anything
+    const double seen = (double)n_mx * ((double)w + 1.0) / (double)bases;
+    if (1.3 * seen > c->mx_density_factor) c->mx_density_factor = 1.3 * seen;
+}
 inline void tick(ntl_ctx* c, int stage) {
     if (c->no_stage_timing) return;
     cudaEventRecordWithFlags(c->ev[2 * stage], c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);

@@ -623,7 +623,7 @@ retry:
     if (call_state) {
         // deferred pass: the output is sized by an upper bound (random sequence has 2/(w+1) minimizers per position;
         // 30 % head room, never more than one per position) and nobody waits for the counters
-        out_cap = sketch_out_bound(total_bases, nseq, w);
+        out_cap = sketch_out_bound(total_bases, nseq, w, c->mx_density_factor);
         out.n_mx = out_cap;
         goto emit;
     }
@@ -647,6 +647,7 @@ retry:
         const uint32_t total = *(uint32_t*)(c->h_status.as<char>() + 68);
         out_cap = total;
         out.n_mx = total;
+        note_mx_density(c, total, total_bases, w);
     }
 emit:
     NTL_CUDA(c, out.hash.ensure((size_t)out_cap * 8 + 8));
