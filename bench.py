@@ -391,11 +391,14 @@ def run_gpu(args, rank, world, local_rank):
         mx_per_base = n_mx / read_bases
         alg_bytes = bases_per_launch * (1.0 + 13.0 * mx_per_base)
         achieved = alg_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms > 0 else 0.0
-        traffic = None
+        traffic, ncu_pipes = None, None
         tp = os.path.join(REPO, "profiles", "r1_traffic.json")
         if os.path.exists(tp):
             with open(tp) as fin:
-                traffic = json.load(fin).get("k_dense_reads_launch_dram_bytes")
+                prof = json.load(fin)
+            traffic = prof.get("k_dense_reads_launch_dram_bytes")
+            ncu_pipes = {"alu_pipe_pct": prof.get("k_dense_alu_pipe_pct"), "issue_slots_pct": prof.get("k_dense_issue_slots_pct"),
+                         "dram_throughput_pct": prof.get("k_dense_dram_throughput_pct"), "source": "profiles/r1_k_dense_ncu_full.txt"}
         line = {"metric": "long_read_gbp_per_s_sketched_mapped", "value": value, "unit": "Gbp/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -415,7 +418,7 @@ def run_gpu(args, rank, world, local_rank):
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "k_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                             "ms_per_launch": dense_ms, "launches": int(tm["big_dense_launches"]),
+                             "ms_per_launch": dense_ms, "launches": int(tm["big_dense_launches"]), "ncu": ncu_pipes,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "integer-ALU bound kernel (rolling ntHash: ncu alu pipe 80 %, issue slots 73 %, DRAM 11 %, "
                                      "profiles/r1_k_dense_ncu_full.txt); HBM fraction reported as the metric asks; traffic = "
