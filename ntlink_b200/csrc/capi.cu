@@ -948,7 +948,7 @@ int ntl_events_import_counts(ntl_ctx* c, const void* d_src, uint32_t world, uint
         if (counts[r] > cap_events) { c->err = "ntl_events_import_counts: a rank sent more events than the buffer holds"; return NTL_ERR_ARG; }
         total += counts[r];
     }
-    c->tl_n_events = 0;
+    c->tl_n_events = 0; c->tl_count_on_device = false;
     const size_t need = (total + 1) * sizeof(Event);
     if (need > c->tl_events.cap) NTL_CUDA(c, c->tl_events.ensure(need));
     uint64_t o = 0;
@@ -958,6 +958,7 @@ int ntl_events_import_counts(ntl_ctx* c, const void* d_src, uint32_t world, uint
         o += counts[r];
     }
     c->tl_n_events = total;
+    c->tl_count_on_device = false;
     return NTL_OK;
 }
 
@@ -978,7 +979,7 @@ int ntl_events_import_gathered(ntl_ctx* c, const void* d_src, uint32_t world, ui
     *overflow = 0;
     for (uint32_t r = 0; r < world; r++) { if (cnt[r] > cap_events) *overflow = 1; total += cnt[r]; }
     if (*overflow) return NTL_OK;
-    c->tl_n_events = 0;
+    c->tl_n_events = 0; c->tl_count_on_device = false;
     const size_t need = (total + 1) * sizeof(Event);
     if (need > c->tl_events.cap) NTL_CUDA(c, c->tl_events.ensure(need));
     uint64_t o = 0;
@@ -988,6 +989,7 @@ int ntl_events_import_gathered(ntl_ctx* c, const void* d_src, uint32_t world, ui
         o += cnt[r];
     }
     c->tl_n_events = total;
+    c->tl_count_on_device = false;
     return NTL_OK;
 }
 
