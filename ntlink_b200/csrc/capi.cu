@@ -198,12 +198,14 @@ void ntl_destroy(ntl_ctx* c) {
     for (DevBuf* b : sb) b->release();
     MapWork& M = c->mw;
     DevBuf* mb[] = {&M.hit_tmp, &M.hit_flag, &M.hit_pref, &M.hits, &M.runs, &M.mark, &M.hit_off, &M.nruns, &M.events,
-                    &M.status, &M.read_len, &M.ev_cnt, &M.blocksums};
+                    &M.status, &M.read_len, &M.ev_cnt, &M.blocksums, &M.lift_runs, &M.lift_nruns, &M.lift_agp};
     for (DevBuf* b : mb) b->release();
     ntl::TallyWork& TW = c->tw;
     DevBuf* tb[] = {&TW.keys, &TW.pn, &TW.panchor, &TW.pfirst, &TW.ev_slot, &TW.gap_off, &TW.cursor, &TW.gkey, &TW.gval,
-                    &TW.nonempty, &TW.ppref, &TW.out, &TW.ndev, &TW.bs};
+                    &TW.nonempty, &TW.ppref, &TW.out, &TW.ndev, &TW.bs, &TW.skey, &TW.sval};
     for (DevBuf* b : tb) b->release();
+    TW.h_stage.release();
+    c->call_state.release(); c->tl_count.release();
     DevBuf* ib[] = {&c->index.table, &c->index.special, &c->index.ctg_len, &c->index.name_rank, &c->index.dupflag,
                     &c->d_seq, &c->d_off, &c->dsk.hash, &c->dsk.posf, &c->dsk.mx_off, &c->tl_events,
                     &R->r_seq, &R->r_off, &R->r_len, &R->t_seq, &R->t_off, &R->t_ctg, &R->stage_off, &R->ctg_ids,
