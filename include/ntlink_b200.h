@@ -157,6 +157,17 @@ int ntl_tally_mappings(ntl_ctx* ctx, const uint32_t* hit_off, const uint32_t* nr
                        const uint32_t* read_len, uint32_t nreads, uint64_t first_read_ordinal, const ntl_params* prm,
                        uint64_t* n_events_out);
 
+/* Grouped mapping for gap filling. Replaces, for ALL gaps at once, the per-gap body of map_long_reads
+ * (bin/ntlink_patch_gaps.py:412-442): read_btllib_minimizers (:397-410, a hash seen twice among the group's targets is
+ * dropped), the membership filter (:437-438) and ntlink_utils.get_accepted_anchor_contigs (bin/ntlink_utils.py:200-294).
+ * Group g = target sequences [group_t_off[g], group_t_off[g+1]) (the two scaffold ends around a gap) + read g. Sketches
+ * in the ntl_sketch_out layout (hash, pos|strand<<31, per-sequence offsets), t_len = the lengths the z filter uses (the
+ * full scaffolds, :206), r_len = read lengths. Output: ntl_map_out with one "read" per group, contig ids = target
+ * sequence indices, hit_off = the read's minimizer offsets (holey regions), no events. */
+int ntl_map_groups(ntl_ctx* ctx, const uint64_t* t_hash, const uint32_t* t_pos_strand, const uint64_t* t_mx_off, const uint32_t* t_len,
+                   uint32_t ntargets, const uint32_t* group_t_off, const uint64_t* r_hash, const uint32_t* r_pos_strand,
+                   const uint64_t* r_mx_off, const uint32_t* r_len, uint32_t ngroups, const ntl_params* prm, ntl_map_out* out);
+
 /* Mapping liftover between rounds. Replaces bin/ntlink_liftover_mappings.py (liftover_ctg_mappings :61-88 and
  * print_adjusted_mappings :90-124; called from ntLink_rounds:122-125): the accepted runs of every read are rewritten
  * from contig coordinates to the coordinates of the scaffolds they were joined into. One ntl_agp_row per contig id of

@@ -78,6 +78,7 @@ SIGNATURES = {
     "ntl_map_reads": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint64, C.POINTER(Params), C.POINTER(MapOut)]),
     "ntl_map_sketch": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_uint32, C.c_uint64, C.POINTER(Params), C.POINTER(MapOut)]),
     "ntl_tally_mappings": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_uint32, C.c_uint64, C.POINTER(Params), _U64P]),
+    "ntl_map_groups": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_uint32, _VP, _VP, _VP, _VP, _VP, C.c_uint32, C.POINTER(Params), C.POINTER(MapOut)]),
     "ntl_liftover_mappings": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_uint32, _VP, C.c_uint32, C.c_int, C.POINTER(MapOut)]),
     "ntl_stream": (C.c_int, [_VP, C.POINTER(C.c_void_p)]),
     "ntl_events_export_async": (C.c_int, [_VP, _VP, C.c_uint64, _U64P]),

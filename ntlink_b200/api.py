@@ -364,6 +364,26 @@ class Context:
                                             C.byref(prm), C.byref(mo)), "ntl_map_sketch")
         return MapResult(mo)
 
+    def map_groups(self, target_sketch, target_len, group_t_off, read_sketch, read_len, prm):
+        """Gap-filling style mapping of many small groups in one call (bin/ntlink_patch_gaps.py:412-442): group g = target
+        sequences [group_t_off[g], group_t_off[g+1]) of target_sketch + read g of read_sketch. Returns a MapResult with one
+        entry per group (accepted runs + hits, contig ids = target sequence indices)."""
+        th = np.ascontiguousarray(target_sketch.hash, np.uint64)
+        tp = np.ascontiguousarray(target_sketch.pos_strand, np.uint32)
+        to = np.ascontiguousarray(target_sketch.seq_off, np.uint64)
+        tl = np.ascontiguousarray(target_len, np.uint32)
+        go = np.ascontiguousarray(group_t_off, np.uint32)
+        rh = np.ascontiguousarray(read_sketch.hash, np.uint64)
+        rp = np.ascontiguousarray(read_sketch.pos_strand, np.uint32)
+        ro = np.ascontiguousarray(read_sketch.seq_off, np.uint64)
+        rl = np.ascontiguousarray(read_len, np.uint32)
+        if len(to) != len(tl) + 1 or len(ro) != len(rl) + 1 or len(go) != len(rl) + 1 or (len(go) and int(go[-1]) != len(tl)):
+            raise ValueError("map_groups: inconsistent array sizes")
+        mo = _lib.MapOut()
+        self._check(self.lib.ntl_map_groups(self.h, _ptr(th), _ptr(tp), _ptr(to), _ptr(tl), len(tl), _ptr(go), _ptr(rh), _ptr(rp), _ptr(ro),
+                                            _ptr(rl), len(rl), C.byref(prm), C.byref(mo)), "ntl_map_groups")
+        return MapResult(mo)
+
     def liftover_mappings(self, hit_off, nruns, runs, hits, agp_rows, k, want_result=True):
         """bin/ntlink_liftover_mappings.py:61-124 on the GPU. agp_rows: (ncontig, 5) uint32 {new_id, flags, scaf_start,
         ctg_start, ctg_end} (see liftover.agp_table). Returns a MapResult in the new contig namespace (or None); the

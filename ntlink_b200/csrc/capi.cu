@@ -19,6 +19,9 @@ int call_reserve_events(ntl_ctx* c, uint32_t nreads);
 int call_note_mx(ntl_ctx* c, const uint32_t* n_dev, CallState* call);
 int events_import_device(ntl_ctx* c, const void* d_src, uint32_t world, uint64_t cap_events);
 int events_resolve_count(ntl_ctx* c);
+int group_map_device(ntl_ctx* c, const uint64_t* t_hash, const uint32_t* t_posf, const uint64_t* t_mx_off, const uint32_t* t_len,
+                     uint32_t ntargets, const uint32_t* g_t_off, const uint64_t* r_hash, const uint32_t* r_posf,
+                     const uint64_t* r_mx_off, const uint32_t* r_len, uint32_t ngroups, const ntl_params* prm, MapStatus* counts_out);
 int call_chunk_finish(ntl_ctx* c, CallState* call, uint32_t rb, uint32_t nreads, const HostResults* H);
 int call_end(ntl_ctx* c, CallState* call, CallState* host_out);
 int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, const Run* runs, const Hit* hits, uint32_t nreads,
@@ -200,6 +203,7 @@ void ntl_destroy(ntl_ctx* c) {
     DevBuf* mb[] = {&M.hit_tmp, &M.hit_flag, &M.hit_pref, &M.hits, &M.runs, &M.mark, &M.hit_off, &M.nruns, &M.events,
                     &M.status, &M.read_len, &M.ev_cnt, &M.blocksums, &M.lift_runs, &M.lift_nruns, &M.lift_agp};
     for (DevBuf* b : mb) b->release();
+    for (DevBuf& b : M.gm) b.release();
     ntl::TallyWork& TW = c->tw;
     DevBuf* tb[] = {&TW.keys, &TW.pn, &TW.panchor, &TW.pfirst, &TW.ev_slot, &TW.gap_off, &TW.cursor, &TW.gkey, &TW.gval,
                     &TW.nonempty, &TW.ppref, &TW.out, &TW.ndev, &TW.bs, &TW.skey, &TW.sval};
@@ -833,6 +837,37 @@ int ntl_tally_mappings(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nrun
     NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), nreads, first_read_ordinal, prm, &cs, &log_base, &pre));
     NTL_TRY(finish_call(c));
     if (n_events_out) *n_events_out = cs.n_events;
+    return NTL_OK;
+}
+
+int ntl_map_groups(ntl_ctx* c, const uint64_t* t_hash, const uint32_t* t_pos_strand, const uint64_t* t_mx_off, const uint32_t* t_len,
+                   uint32_t ntargets, const uint32_t* group_t_off, const uint64_t* r_hash, const uint32_t* r_pos_strand,
+                   const uint64_t* r_mx_off, const uint32_t* r_len, uint32_t ngroups, const ntl_params* prm, ntl_map_out* out) {
+    if (!c || !t_mx_off || !group_t_off || !r_mx_off || !prm || !out || prm->k <= 0 || (ntargets && !t_len) || (ngroups && !r_len)) {
+        if (c) c->err = "ntl_map_groups: bad argument";
+        return NTL_ERR_ARG;
+    }
+    const uint64_t nt = ntargets ? t_mx_off[ntargets] - t_mx_off[0] : 0, nr = ngroups ? r_mx_off[ngroups] - r_mx_off[0] : 0;
+    if ((nt && (!t_hash || !t_pos_strand)) || (nr && (!r_hash || !r_pos_strand))) { c->err = "ntl_map_groups: bad argument"; return NTL_ERR_ARG; }
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    MapStatus cs;
+    NTL_TRY(group_map_device(c, t_hash, t_pos_strand, t_mx_off, t_len, ntargets, group_t_off, r_hash, r_pos_strand, r_mx_off, r_len, ngroups,
+                             prm, &cs));
+    MapWork& M = c->mw;
+    NTL_TRY(begin_map_results(c, ngroups));
+    if (R->runs.reserve(((size_t)nr + 1) * sizeof(ntl_run)) || R->hits.reserve(((size_t)nr + 1) * sizeof(ntl_hit))) { c->err = "pinned alloc failed"; return NTL_ERR_CUDA; }
+    memset(R->ev_off.at<uint32_t>(0), 0, ((size_t)ngroups + 1) * 4);
+    memset(R->ev_cnt.at<uint32_t>(0), 0, ((size_t)ngroups + 1) * 4);
+    NTL_CUDA(c, cudaMemcpyAsync(R->hit_off.at<uint32_t>(0), M.hit_off.p, ((size_t)ngroups + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (ngroups) NTL_CUDA(c, cudaMemcpyAsync(R->nruns.at<uint32_t>(0), M.nruns.p, (size_t)ngroups * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (nr) {
+        NTL_CUDA(c, cudaMemcpyAsync(R->runs.at<ntl_run>(0), M.runs.p, (size_t)nr * sizeof(ntl_run), cudaMemcpyDeviceToHost, c->stream));
+        NTL_CUDA(c, cudaMemcpyAsync(R->hits.at<ntl_hit>(0), M.hits.p, (size_t)nr * sizeof(ntl_hit), cudaMemcpyDeviceToHost, c->stream));
+    }
+    NTL_TRY(finish_call(c));
+    fill_map_out(c, out, ngroups, nr, nr, cs.n_runs, 0);
+    out->n_hits = cs.n_hits;
     return NTL_OK;
 }
 

@@ -128,6 +128,7 @@ struct TallyWork {
 struct MapWork {
     DevBuf hit_tmp, hit_flag, hit_pref, hits, runs, mark, hit_off, nruns, events, status, read_len, ev_cnt, blocksums;
     DevBuf lift_runs, lift_nruns, lift_agp;     // liftover inputs
+    DevBuf gm[15];                              // grouped mapping (ntl_map_groups): inputs, per-group plan, global tables
     bool lifted_valid = false;                  // hits/runs/nruns/hit_off hold the output of the last liftover
     uint32_t lifted_reads = 0, lifted_hits = 0;
 };

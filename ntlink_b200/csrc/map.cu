@@ -388,6 +388,117 @@ __global__ void k_publish_map(const MapStatus* __restrict__ st, const uint32_t* 
     __threadfence_system();
 }
 
+
+// ------------------------------------------------------------------------------------------- grouped mapping (gap filling)
+// Many small, independent mapping problems: group g = a few target sequences (the two scaffold ends around a gap) and
+// ONE read (bin/ntlink_patch_gaps.py:412-442: read_btllib_minimizers + get_accepted_anchor_contigs per gap). One block
+// per group: the group's unique-minimizer table is built in shared memory (global memory for the rare group whose
+// targets have more minimizers than fit), the read's minimizers are looked up and compacted in read order, and thread 0
+// chains the hits with the same chain_read as the main path.
+constexpr int GM_THREADS = 128;
+constexpr uint32_t GM_SLOTS = 8192;                       // shared-memory table: 64 KB keys + 32 KB values + 8 KB flags
+struct GroupTables { unsigned long long* keys; uint32_t* vals; uint8_t* dup; };
+
+__global__ void __launch_bounds__(GM_THREADS) k_group_map(const uint64_t* __restrict__ t_hash, const uint32_t* __restrict__ t_posf,
+                                                          const uint32_t* __restrict__ t_mx_off, const uint32_t* __restrict__ t_len,
+                                                          const uint32_t* __restrict__ g_t_off,
+                                                          const uint64_t* __restrict__ r_hash, const uint32_t* __restrict__ r_posf,
+                                                          const uint32_t* __restrict__ r_mx_off, const uint32_t* __restrict__ r_len,
+                                                          uint32_t ngroups, uint32_t g_base, MapParams P, const uint32_t* __restrict__ g_slots,
+                                                          const uint64_t* __restrict__ g_tab_off, GroupTables gtab,
+                                                          Hit* __restrict__ hits, Run* __restrict__ runs, uint8_t* __restrict__ mark,
+                                                          uint32_t* __restrict__ nruns, uint32_t* __restrict__ nhits,
+                                                          MapStatus* __restrict__ st) {
+    extern __shared__ unsigned long long gm_smem[];
+    __shared__ uint32_t s_warp[GM_THREADS / 32];
+    __shared__ uint32_t s_running, s_special_cnt, s_special_val;
+    const uint32_t g = g_base + blockIdx.x, tid = threadIdx.x;
+    if (g >= ngroups) return;
+    const uint32_t ts0 = g_t_off[g], ts1 = g_t_off[g + 1];            // target sequences of the group
+    const uint32_t t0 = t_mx_off[ts0], t1 = t_mx_off[ts1];            // their minimizers (contiguous)
+    const uint32_t slots = g_slots[g];
+    const uint64_t mask = slots - 1;
+    unsigned long long* keys;
+    uint32_t* vals;
+    uint8_t* dup;
+    if (g_tab_off[g] == ~0ull) {
+        keys = gm_smem; vals = reinterpret_cast<uint32_t*>(gm_smem + GM_SLOTS); dup = reinterpret_cast<uint8_t*>(vals + GM_SLOTS);
+    } else {
+        keys = gtab.keys + g_tab_off[g]; vals = gtab.vals + g_tab_off[g]; dup = gtab.dup + g_tab_off[g];
+    }
+    for (uint32_t i = tid; i < slots; i += GM_THREADS) { keys[i] = NTL_EMPTY_KEY; dup[i] = 0; }
+    if (tid == 0) { s_running = 0; s_special_cnt = 0; s_special_val = 0; }
+    // the table may live in global memory: its plain stores must have reached L2, where the atomics below operate,
+    // before any thread of the block starts inserting (a block-level barrier alone only orders what the block sees
+    // through its L1)
+    __threadfence();
+    __syncthreads();
+    // M1 within the group (patch:397-410): first occurrence keeps its place, any second occurrence removes the hash
+    for (uint32_t i = t0 + tid; i < t1; i += GM_THREADS) {
+        const unsigned long long key = t_hash[i];
+        if (key == NTL_EMPTY_KEY) { if (atomicAdd(&s_special_cnt, 1u) == 0) s_special_val = i - t0; continue; }
+        uint64_t s = idx_slot(key, mask);
+        for (;;) {
+            const unsigned long long prev = atomicCAS(&keys[s], (unsigned long long)NTL_EMPTY_KEY, key);
+            if (prev == NTL_EMPTY_KEY) { vals[s] = i - t0; break; }
+            if (prev == key) { dup[s] = 1; break; }
+            s = (s + 1) & mask;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    // Which occurrence "wins" a slot is a race, but only unique hashes are ever looked up successfully, so it does not matter.
+    const uint32_t r0 = r_mx_off[g], r1 = r_mx_off[g + 1];
+    for (uint32_t base = r0; base < r1; base += GM_THREADS) {
+        const uint32_t i = base + tid;
+        bool found = false;
+        Hit h; h.ctg = 0; h.cposf = 0; h.rposf = 0;
+        if (i < r1) {
+            const unsigned long long key = r_hash[i];
+            uint32_t v = 0xFFFFFFFFu;
+            if (key == NTL_EMPTY_KEY) { if (s_special_cnt == 1) v = s_special_val; }
+            else {
+                // volatile: read what the atomics / stores of the insert phase left in memory, not an L1 copy
+                const volatile unsigned long long* vkeys = keys;
+                const volatile uint32_t* vvals = vals;
+                const volatile uint8_t* vdup = dup;
+                uint64_t s = idx_slot(key, mask);
+                for (;;) {
+                    const unsigned long long kk = vkeys[s];
+                    if (kk == key) { if (!vdup[s]) v = vvals[s]; break; }
+                    if (kk == NTL_EMPTY_KEY) break;
+                    s = (s + 1) & mask;
+                }
+            }
+            if (v != 0xFFFFFFFFu) {
+                const uint32_t gi = t0 + v;
+                uint32_t ctg = ts0;
+                while (ctg + 1 < ts1 && t_mx_off[ctg + 1] <= gi) ctg++;           // a handful of targets per group
+                h.ctg = ctg; h.cposf = t_posf[gi]; h.rposf = r_posf[i];
+                found = true;
+            }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, found);
+        if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(b);
+        __syncthreads();
+        uint32_t before = s_running;
+        for (uint32_t q = 0; q < (tid >> 5); q++) before += s_warp[q];
+        if (found) hits[r0 + before + __popc(b & ((1u << (tid & 31)) - 1u))] = h;
+        __syncthreads();
+        if (tid == 0) { uint32_t tot = 0; for (int q = 0; q < GM_THREADS / 32; q++) tot += s_warp[q]; s_running += tot; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint32_t nh = s_running;
+        uint32_t nr = 0;
+        if (nh) nr = chain_read(hits + r0, nh, runs + r0, mark + r0, r_len[g], t_len, P);
+        nruns[g] = nr;
+        nhits[g] = nh;
+        if (nr) atomicAdd(&st->n_runs, nr);
+        if (nh) atomicAdd(&st->n_hits, nh);
+    }
+}
+
 }  // namespace
 
 // grow a device buffer keeping its first `keep` bytes
@@ -511,6 +622,86 @@ int liftover_device(ntl_ctx* c, const uint32_t* hit_off, const uint32_t* nruns, 
     if (hs.err & (LIFTERR_RANGE << 8)) { c->err = "liftover: a lifted position does not fit in 31 bits"; return NTL_ERR_ARG; }
     *counts_out = hs;
     M.lifted_reads = nreads; M.lifted_hits = n; M.lifted_valid = true;
+    return NTL_OK;
+}
+
+
+// Grouped mapping on host arrays (see k_group_map). Results: holey per-read regions at r_mx_off (a read cannot have more
+// hits than minimizers), contig ids = target sequence indices.
+int group_map_device(ntl_ctx* c, const uint64_t* t_hash, const uint32_t* t_posf, const uint64_t* t_mx_off, const uint32_t* t_len,
+                     uint32_t ntargets, const uint32_t* g_t_off, const uint64_t* r_hash, const uint32_t* r_posf,
+                     const uint64_t* r_mx_off, const uint32_t* r_len, uint32_t ngroups, const ntl_params* prm, MapStatus* counts_out) {
+    MapWork& M = c->mw;
+    const uint64_t nt = ntargets ? t_mx_off[ntargets] - t_mx_off[0] : 0, nr = ngroups ? r_mx_off[ngroups] - r_mx_off[0] : 0;
+    if (nt >= (1ull << 31) || nr >= (1ull << 31)) { c->err = "ntl_map_groups: too many minimizers in one call"; return NTL_ERR_ARG; }
+    MapParams P;
+    P.k = prm->k; P.z = prm->z; P.f = prm->f; P.x = prm->x; P.x_is_zero = (prm->x == 0.0);
+    P.sensitive = prm->sensitive; P.repeat_filter = prm->repeat_filter;
+    // host-side planning: 32-bit offsets, table size per group, global table room for the groups too big for shared memory
+    std::vector<uint32_t> t_off32((size_t)ntargets + 1), r_off32((size_t)ngroups + 1), slots(ngroups ? ngroups : 1);
+    std::vector<uint64_t> tab_off(ngroups ? ngroups : 1);
+    for (uint32_t i = 0; i <= ntargets; i++) t_off32[i] = (uint32_t)(t_mx_off[i] - t_mx_off[0]);
+    for (uint32_t i = 0; i <= ngroups; i++) r_off32[i] = (uint32_t)(r_mx_off[i] - r_mx_off[0]);
+    uint64_t gtab_total = 0;
+    for (uint32_t g = 0; g < ngroups; g++) {
+        if (g_t_off[g] > g_t_off[g + 1] || g_t_off[g + 1] > ntargets) { c->err = "ntl_map_groups: group_t_off must be non-decreasing and end at ntargets"; return NTL_ERR_ARG; }
+        const uint64_t n = (uint64_t)t_off32[g_t_off[g + 1]] - t_off32[g_t_off[g]];
+        uint64_t sl = 64;
+        while (sl < 2 * n) sl <<= 1;
+        slots[g] = (uint32_t)sl;
+        if (sl <= GM_SLOTS) tab_off[g] = ~0ull;
+        else { tab_off[g] = gtab_total; gtab_total += sl; }
+    }
+    DevBuf &d_th = M.gm[0], &d_tp = M.gm[1], &d_to = M.gm[2], &d_tl = M.gm[3], &d_go = M.gm[4], &d_rh = M.gm[5], &d_rp = M.gm[6], &d_ro = M.gm[7],
+           &d_rl = M.gm[8], &d_sl = M.gm[9], &d_tb = M.gm[10], &d_gk = M.gm[11], &d_gv = M.gm[12], &d_gd = M.gm[13], &d_nh = M.gm[14];
+    NTL_CUDA(c, d_th.ensure(nt * 8 + 8)); NTL_CUDA(c, d_tp.ensure(nt * 4 + 4)); NTL_CUDA(c, d_to.ensure(((size_t)ntargets + 1) * 4));
+    NTL_CUDA(c, d_tl.ensure((size_t)ntargets * 4 + 4)); NTL_CUDA(c, d_go.ensure(((size_t)ngroups + 1) * 4));
+    NTL_CUDA(c, d_rh.ensure(nr * 8 + 8)); NTL_CUDA(c, d_rp.ensure(nr * 4 + 4)); NTL_CUDA(c, d_ro.ensure(((size_t)ngroups + 1) * 4));
+    NTL_CUDA(c, d_rl.ensure((size_t)ngroups * 4 + 4)); NTL_CUDA(c, d_sl.ensure((size_t)ngroups * 4 + 4)); NTL_CUDA(c, d_tb.ensure((size_t)ngroups * 8 + 8));
+    NTL_CUDA(c, d_gk.ensure(gtab_total * 8 + 8)); NTL_CUDA(c, d_gv.ensure(gtab_total * 4 + 4)); NTL_CUDA(c, d_gd.ensure(gtab_total + 8));
+    NTL_CUDA(c, d_nh.ensure((size_t)ngroups * 4 + 4));
+    NTL_CUDA(c, M.hits.ensure((size_t)nr * sizeof(Hit) + 16)); NTL_CUDA(c, M.runs.ensure((size_t)nr * sizeof(Run) + 16));
+    NTL_CUDA(c, M.mark.ensure((size_t)nr + 16)); NTL_CUDA(c, M.nruns.ensure(((size_t)ngroups + 2) * 4));
+    NTL_CUDA(c, M.hit_off.ensure(((size_t)ngroups + 2) * 4));
+    NTL_CUDA(c, M.status.ensure(sizeof(MapStatus) + 64));
+    NTL_CUDA(c, c->h_status.ensure(256));
+    MapStatus* st = M.status.as<MapStatus>();
+    {
+        FillSegs fs{};
+        fs.p[0] = st; fs.n[0] = sizeof(MapStatus) + 64;
+        k_fill_segs<<<1, 256, 0, c->stream>>>(fs);
+        c->launches++;
+    }
+    auto up = [&](DevBuf& d, const void* src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+    };
+    NTL_CUDA(c, up(d_th, t_hash + t_mx_off[0], nt * 8)); NTL_CUDA(c, up(d_tp, t_posf + t_mx_off[0], nt * 4));
+    NTL_CUDA(c, up(d_to, t_off32.data(), ((size_t)ntargets + 1) * 4)); NTL_CUDA(c, up(d_tl, t_len, (size_t)ntargets * 4));
+    NTL_CUDA(c, up(d_go, g_t_off, ((size_t)ngroups + 1) * 4));
+    NTL_CUDA(c, up(d_rh, r_hash + r_mx_off[0], nr * 8)); NTL_CUDA(c, up(d_rp, r_posf + r_mx_off[0], nr * 4));
+    NTL_CUDA(c, up(d_ro, r_off32.data(), ((size_t)ngroups + 1) * 4)); NTL_CUDA(c, up(d_rl, r_len, (size_t)ngroups * 4));
+    NTL_CUDA(c, up(d_sl, slots.data(), (size_t)ngroups * 4)); NTL_CUDA(c, up(d_tb, tab_off.data(), (size_t)ngroups * 8));
+    NTL_CUDA(c, up(M.hit_off, r_off32.data(), ((size_t)ngroups + 1) * 4));
+    if (ngroups) {
+        static bool attr_set = false;
+        const size_t smem = (size_t)GM_SLOTS * (8 + 4 + 1);
+        if (!attr_set) { NTL_CUDA(c, cudaFuncSetAttribute(k_group_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+        tick(c, T_CHAIN);
+        GroupTables gt{d_gk.as<unsigned long long>(), d_gv.as<uint32_t>(), d_gd.as<uint8_t>()};
+        k_group_map<<<ngroups, GM_THREADS, smem, c->stream>>>(d_th.as<uint64_t>(), d_tp.as<uint32_t>(), d_to.as<uint32_t>(), d_tl.as<uint32_t>(),
+                                                             d_go.as<uint32_t>(), d_rh.as<uint64_t>(), d_rp.as<uint32_t>(), d_ro.as<uint32_t>(),
+                                                             d_rl.as<uint32_t>(), ngroups, 0u, P, d_sl.as<uint32_t>(), d_tb.as<uint64_t>(), gt,
+                                                             M.hits.as<Hit>(), M.runs.as<Run>(), M.mark.as<uint8_t>(), M.nruns.as<uint32_t>(),
+                                                             d_nh.as<uint32_t>(), st);
+        c->launches++;
+        tock(c, T_CHAIN);
+    }
+    k_publish_map<<<1, 32, 0, c->stream>>>(st, &st->n_hits, &st->n_runs, c->h_status.as<uint32_t>());
+    c->launches++;
+    NTL_CUDA(c, cudaGetLastError());
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));        // also: the host vectors above are done with
+    *counts_out = *c->h_status.as<MapStatus>();
+    c->mw.lifted_valid = false;
     return NTL_OK;
 }
 
