@@ -111,3 +111,65 @@ def test_grouped_mapping_edge_cases(ctx):
     assert [(int(h[1]) & 0x7FFFFFFF, int(h[2]) & 0x7FFFFFFF) for h in hits] == [(50, 1), (40, 3), (20, 4)]      # 5 is duplicated, 11 unknown
     with pytest.raises(ValueError):
         ctx.map_groups(t, np.array([1000], np.uint32), np.array([0, 2], np.uint32), r, np.array([100], np.uint32), prm)
+
+
+def test_gapfill_front_end_on_masked_files(ctx, tmp_path):
+    """ntlink_b200.gapfill.map_long_reads on files written the way print_masked_sequences does (patch:346-389): N-masked
+    full-length scaffolds and reads, `<read>__<src>__<tgt>` / `<src>_source` / `<tgt>_target` headers; checked per gap
+    against the oracle (index of the two ends with duplicates dropped + accepted_anchor_contigs)."""
+    from ntlink_b200 import gapfill
+    k, w = 20, 10
+    tnames, tseq, toff = util.load_fasta_batch(util.fixture_file(tmp_path, "scaffolds_3.fa"))
+    rnames, rseq, roff = util.load_fasta_batch(util.fixture_file(tmp_path, "long_reads_3.fa"))
+    rng = np.random.default_rng(99)
+    lengths = {n: int(toff[i + 1] - toff[i]) for i, n in enumerate(tnames)}
+    big = [i for i, n in enumerate(tnames) if lengths[n] > 4000]
+    # gaps where the read really joins the two contigs: taken from the reference-generated mapping of this fixture
+    tidx, ridx, joined, seen = {n: i for i, n in enumerate(tnames)}, {n: i for i, n in enumerate(rnames)}, [], {}
+    for line in util.golden_case("f3_default", "verbose_mapping.tsv").decode().splitlines():
+        rd, ctg = line.split("\t")[:2]
+        seen.setdefault(rd, []).append(ctg)
+    for rd, ctgs in seen.items():
+        if len(ctgs) >= 2 and all(lengths[c] > 4000 for c in ctgs[:2]):
+            joined.append((ridx[rd], tidx[ctgs[0]], tidx[ctgs[1]]))
+    assert len(joined) >= 5
+    spath, rpath = os.path.join(str(tmp_path), "o.scaffolds.masked_temp.fa"), os.path.join(str(tmp_path), "o.reads.masked_temp.fa")
+    gaps = []
+    with open(spath, "w") as fs, open(rpath, "w") as fr:
+        for g in range(40):
+            if g < len(joined):
+                r, a, b = joined[g]
+            else:
+                a, b = (int(v) for v in rng.choice(big, size=2, replace=False))
+                r = int(rng.integers(0, len(rnames)))
+            src, tgt = tnames[a] + "+-"[g % 2], tnames[b] + "-+"[g % 3 == 0]
+            sa, sb = tseq[int(toff[a]):int(toff[a + 1])].tobytes().decode(), tseq[int(toff[b]):int(toff[b + 1])].tobytes().decode()
+            cut_a, cut_b = int(rng.integers(500, len(sa) // 3)), int(rng.integers(500, len(sb) // 3))
+            fs.write(f">{src}_source\n{'N' * cut_a}{sa[cut_a:]}\n" if src[-1] == "+" else f">{src}_source\n{sa[:cut_a]}{'N' * (len(sa) - cut_a)}\n")
+            fs.write(f">{tgt}_target\n{sb[:cut_b]}{'N' * (len(sb) - cut_b)}\n" if tgt[-1] == "+" else f">{tgt}_target\n{'N' * cut_b}{sb[cut_b:]}\n")
+            rs = rseq[int(roff[r]):int(roff[r + 1])].tobytes().decode()
+            lo, hi = int(rng.integers(0, len(rs) // 8 + 1)), len(rs) - int(rng.integers(0, len(rs) // 8 + 1))
+            fr.write(f">{rnames[r]}__{src}__{tgt}\n{'N' * lo}{rs[lo:hi]}{'N' * (len(rs) - hi)}\n")
+            gaps.append((rnames[r], src, tgt))
+    got = gapfill.map_long_reads(ctx, spath, rpath, lengths, k=k, w=w, z=1000)
+    assert [(m.read, m.source, m.target) for m in got] == gaps
+    # oracle on the same files
+    _, sseq, soff = util.load_fasta_batch(spath)
+    _, mseq, moff = util.load_fasta_batch(rpath)
+    th, tp, ts, tmo = util.oracle_sketch_batch(sseq, soff, k, w)
+    rh, rp, rs_, rmo = util.oracle_sketch_batch(mseq, moff, k, w)
+    tpf = (tp | (ts.astype(np.uint32) << 31)).astype(np.uint32)
+    rpf = (rp | (rs_.astype(np.uint32) << 31)).astype(np.uint32)
+    prm = po.Params(k, 1000, 1, 10, 0.0, 1, False, False)
+    n_with = 0
+    for g, m in enumerate(got):
+        ids = [m.source.strip("+-"), m.target.strip("+-")]
+        tlen = [lengths[ids[0]], lengths[ids[1]]]
+        want = oracle_group(th, tpf, tmo, None, {2 * g: tlen[0], 2 * g + 1: tlen[1]}, [2 * g, 2 * g + 1], rh, rpf, int(rmo[g]), int(rmo[g + 1]),
+                            int(moff[g + 1] - moff[g]), prm)
+        assert [(r.contig, [(h.ctg_pos, h.ctg_strand, h.read_pos, h.read_strand) for h in r.hits]) for r in m.accepted] == \
+            [(ids[c - 2 * g], hs) for c, hs in want], g
+        n_with += bool(m.accepted)
+    assert n_with >= 3
+    with pytest.raises(ValueError):
+        gapfill.pair_up(["a+_source"], ["r__a+__b-"])
