@@ -253,6 +253,30 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq, uint64_t** 
 void ntl_seqfile_close(ntl_seqfile* f);
 void ntl_free(void* p);
 
+/* verbose_mapping.tsv (plain or gzip) -> the arrays ntl_tally_mappings / ntl_liftover_mappings take. Replaces the Python
+ * line loops of find_scaffold_pairs_checkpoints / parse_verbose_entries (bin/ntlink_pair.py:437-488) and liftover_mappings
+ * (bin/ntlink_liftover_mappings.py:128-147): reads = maximal blocks of consecutive lines with one read id, one run per
+ * line, read_len = the largest first/last read position of the read's runs (:487). With a contig table (names as in the
+ * target FASTA) unknown contigs are an error, without one ids are assigned in order of appearance; the table seen so far
+ * is returned with every batch. share_repeated = 1 keeps the reference's dict quirk of the checkpoint path (a contig
+ * listed twice in a read refers both times to its last listing, :470-472); the liftover passes 0. max_hits = 0 reads the
+ * whole file, otherwise whole read blocks until about that many hits. All arrays are malloc'ed: release with ntl_free. */
+typedef struct ntl_verbose_file ntl_verbose_file;
+typedef struct ntl_mappings_out {
+    uint32_t n_reads, n_slots, n_contigs, reserved;
+    uint32_t* hit_off;        /* [n_reads + 1] */
+    uint32_t* nruns;          /* [n_reads] */
+    uint32_t* read_len;       /* [n_reads] */
+    uint32_t* runs;           /* [n_slots * 3] {ctg, start, count} */
+    uint32_t* hits;           /* [n_slots * 3] {ctg, ctg_pos|strand<<31, read_pos|strand<<31} */
+    char* read_names;  uint64_t* read_name_off;     /* [n_reads + 1] */
+    char* ctg_names;   uint64_t* ctg_name_off;      /* [n_contigs + 1] */
+} ntl_mappings_out;
+int ntl_verbose_open(const char* path, const char* ctg_names, const uint64_t* ctg_name_off, uint32_t ncontig, ntl_verbose_file** out);
+int ntl_verbose_read(ntl_verbose_file* f, uint64_t max_hits, int share_repeated, ntl_mappings_out* out);
+const char* ntl_verbose_error(ntl_verbose_file* f);
+void ntl_verbose_close(ntl_verbose_file* f);
+
 /* ---- device-resident / timing interface (bench.py) ----------------------------------------------- */
 /* copy a read batch to the device once; ntl_map_resident then runs the whole hot path on it without touching
  * the host (results stay on the device; only the counters come back). */

@@ -51,6 +51,14 @@ class MapOut(C.Structure):
                 ("ev_off", C.POINTER(C.c_uint32)), ("ev_cnt", C.POINTER(C.c_uint32)), ("events", C.POINTER(Event))]
 
 
+class MappingsOut(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_slots", C.c_uint32), ("n_contigs", C.c_uint32), ("reserved", C.c_uint32),
+                ("hit_off", C.POINTER(C.c_uint32)), ("nruns", C.POINTER(C.c_uint32)), ("read_len", C.POINTER(C.c_uint32)),
+                ("runs", C.POINTER(C.c_uint32)), ("hits", C.POINTER(C.c_uint32)),
+                ("read_names", C.c_void_p), ("read_name_off", C.POINTER(C.c_uint64)),
+                ("ctg_names", C.c_void_p), ("ctg_name_off", C.POINTER(C.c_uint64))]
+
+
 class Pair(C.Structure):
     _fields_ = [("src", C.c_uint32), ("tgt", C.c_uint32), ("flags", C.c_uint32), ("n", C.c_uint32),
                 ("anchor", C.c_uint32), ("reserved", C.c_uint32), ("gap_off", C.c_uint64), ("first_key", C.c_uint64)]
@@ -84,6 +92,10 @@ SIGNATURES = {
     "ntl_events_export_async": (C.c_int, [_VP, _VP, C.c_uint64, _U64P]),
     "ntl_events_import_counts": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, _VP]),
     "ntl_events_import_device": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64]),
+    "ntl_verbose_open": (C.c_int, [C.c_char_p, _VP, _VP, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "ntl_verbose_read": (C.c_int, [_VP, C.c_uint64, C.c_int, C.POINTER(MappingsOut)]),
+    "ntl_verbose_error": (C.c_char_p, [_VP]),
+    "ntl_verbose_close": (None, [_VP]),
     "ntl_events_reset": (C.c_int, [_VP]),
     "ntl_events_append": (C.c_int, [_VP, _VP, C.c_uint64]),
     "ntl_events_count": (C.c_int, [_VP, _U64P]),

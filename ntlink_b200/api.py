@@ -138,6 +138,55 @@ class SeqFile:
         self.close()
 
 
+def read_verbose_mappings(path, contig_names=None, share_repeated=True, max_hits=0):
+    """verbose_mapping.tsv (plain or gzip) -> batches (hit_off, nruns, runs (n,3), hits (n,3), read_len, read_ids, contig_names)
+    through the library's native parser (ntl_verbose_*): the arrays of Context.tally_mappings / liftover_mappings. With
+    contig_names the ids follow that table and unknown contigs raise; without, ids are assigned in order of appearance and
+    the table grows from batch to batch. max_hits = 0: one batch for the whole file."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    if contig_names is not None:
+        enc = [n.encode() for n in contig_names]
+        off = np.zeros(len(enc) + 1, np.uint64)
+        if enc:
+            off[1:] = np.cumsum([len(e) for e in enc])
+        blob = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+        rc = lib.ntl_verbose_open(path.encode(), _ptr(blob), _ptr(off), len(enc), C.byref(h))
+    else:
+        rc = lib.ntl_verbose_open(path.encode(), None, None, 0, C.byref(h))
+    if rc != 0:
+        raise OSError(f"cannot open {path}")
+    try:
+        while True:
+            mo = _lib.MappingsOut()
+            rc = lib.ntl_verbose_read(h, max_hits, int(bool(share_repeated)), C.byref(mo))
+            if rc != 0:
+                raise ValueError((lib.ntl_verbose_error(h) or b"malformed mappings file").decode())
+            n, slots = mo.n_reads, mo.n_slots
+            hit_off = _np_from(mo.hit_off, n + 1, np.uint32)
+            nruns = _np_from(mo.nruns, n, np.uint32)
+            read_len = _np_from(mo.read_len, n, np.uint32)
+            runs = _np_from(mo.runs, slots * 3, np.uint32).reshape(-1, 3)
+            hits = _np_from(mo.hits, slots * 3, np.uint32).reshape(-1, 3)
+            rno = _np_from(mo.read_name_off, n + 1, np.uint64).tolist()
+            rnb = C.string_at(mo.read_names, rno[-1]) if n else b""
+            cno = _np_from(mo.ctg_name_off, mo.n_contigs + 1, np.uint64).tolist()
+            cnb = C.string_at(mo.ctg_names, cno[-1]) if mo.n_contigs else b""
+            for p in (mo.hit_off, mo.nruns, mo.read_len, mo.runs, mo.hits, mo.read_name_off, mo.ctg_name_off):
+                lib.ntl_free(C.cast(p, C.c_void_p))
+            lib.ntl_free(mo.read_names)
+            lib.ntl_free(mo.ctg_names)
+            if n == 0:
+                return
+            ids = [rnb[rno[i]:rno[i + 1]].decode() for i in range(n)]
+            names = [cnb[cno[i]:cno[i + 1]].decode() for i in range(mo.n_contigs)]
+            yield hit_off, nruns, runs, hits, read_len, ids, names
+            if max_hits == 0:
+                return
+    finally:
+        lib.ntl_verbose_close(h)
+
+
 def read_sequences(path, max_bases=0):
     """FASTA/FASTQ (plain or gzip, multi-line) -> SeqBatch of the whole file (or of its first ~max_bases bases)."""
     with SeqFile(path) as f:

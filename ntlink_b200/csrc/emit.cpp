@@ -648,3 +648,191 @@ void ntl_seqfile_close(ntl_seqfile* f) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------- verbose_mapping.tsv parser
+// The checkpoint path and the liftover both start from a verbose_mapping.tsv (bin/ntlink_pair.py:437-488,
+// bin/ntlink_liftover_mappings.py:128-147), which is gigabytes of text at genome scale; the reference splits it line by
+// line in Python. This is the same parse as ntlink_b200/pair.py::parse_verbose_mappings, natively.
+#include <unordered_map>
+
+struct ntl_verbose_file {
+    ntl_seqfile* src = nullptr;                       // reuses the block reader (plain or gzip)
+    std::unordered_map<std::string, uint32_t> ctg_id;
+    std::vector<std::string> ctg_names;
+    bool fixed_table = false;                         // ids come from the caller's table: unknown names are an error
+    std::string pend_line;                            // first line of the next read block
+    bool have_pend = false, done = false;
+    std::string err;
+};
+
+namespace {
+
+template <class T> T* vec_to_malloc(const std::vector<T>& v) {
+    T* p = (T*)malloc((v.size() + 1) * sizeof(T));
+    if (p && !v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+// one token "ctgpos:ctgstrand_readpos:readstrand" -> (cposf, rposf); false on malformed input
+bool parse_token(const char* p, const char* e, uint32_t& cposf, uint32_t& rposf) {
+    uint64_t a = 0, b = 0;
+    const char* q = p;
+    if (q >= e || *q < '0' || *q > '9') return false;
+    while (q < e && *q >= '0' && *q <= '9') a = a * 10 + (uint64_t)(*q++ - '0');
+    if (q + 3 >= e || q[0] != ':' || (q[1] != '+' && q[1] != '-') || q[2] != '_') return false;
+    const bool cs = q[1] == '+';
+    q += 3;
+    if (q >= e || *q < '0' || *q > '9') return false;
+    while (q < e && *q >= '0' && *q <= '9') b = b * 10 + (uint64_t)(*q++ - '0');
+    if (q + 2 != e || q[0] != ':' || (q[1] != '+' && q[1] != '-')) return false;
+    const bool rs = q[1] == '+';
+    if (a > 0x7FFFFFFFull || b > 0x7FFFFFFFull) return false;
+    cposf = (uint32_t)a | (cs ? 0x80000000u : 0u);
+    rposf = (uint32_t)b | (rs ? 0x80000000u : 0u);
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ntl_verbose_open(const char* path, const char* ctg_names, const uint64_t* ctg_name_off, uint32_t ncontig, ntl_verbose_file** out) {
+    if (!path || !out || (ncontig && (!ctg_names || !ctg_name_off))) return NTL_ERR_ARG;
+    ntl_verbose_file* f = new ntl_verbose_file();
+    if (ntl_seqfile_open(path, &f->src) != NTL_OK) { delete f; return NTL_ERR_ARG; }
+    f->src->parallel = false;                         // line-oriented use of the block reader
+    if (f->src->fd >= 0) lseek(f->src->fd, 0, SEEK_SET);
+    if (ncontig) {
+        f->fixed_table = true;
+        for (uint32_t i = 0; i < ncontig; i++) {
+            std::string n(ctg_names + ctg_name_off[i], (size_t)(ctg_name_off[i + 1] - ctg_name_off[i]));
+            f->ctg_id[n] = i;                         // a repeated name: the last one wins, like a dict built from a FASTA
+            f->ctg_names.push_back(n);
+        }
+    }
+    *out = f;
+    return NTL_OK;
+}
+
+const char* ntl_verbose_error(ntl_verbose_file* f) { return f ? f->err.c_str() : ""; }
+
+// Reads whole read blocks until about max_hits hits are collected (0 = to the end of the file).
+int ntl_verbose_read(ntl_verbose_file* f, uint64_t max_hits, int share_repeated, ntl_mappings_out* out) {
+    if (!f || !out) return NTL_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    std::vector<uint32_t> hit_off(1, 0), nruns, read_len, runs, hits;           // runs/hits: 3 words per entry
+    std::vector<uint64_t> rname_off(1, 0);
+    std::string rnames;
+    struct Line { uint32_t ctg; uint32_t start, count; };
+    std::vector<Line> block;                                                   // lines of the current read
+    std::string cur_read;
+    bool have_read = false;
+    uint32_t base = 0;
+
+    auto flush = [&]() {
+        if (!have_read) return;
+        // share_repeated (pair:470-472): a contig listed twice refers both times to its LAST listing
+        std::vector<Line> eff = block;
+        if (share_repeated) {
+            std::unordered_map<uint32_t, size_t> last;
+            for (size_t i = 0; i < block.size(); i++) last[block[i].ctg] = i;
+            for (size_t i = 0; i < block.size(); i++) eff[i] = block[last[block[i].ctg]];
+        }
+        uint32_t maxpos = 0;
+        for (const Line& l : eff) {
+            runs.push_back(l.ctg); runs.push_back(l.start); runs.push_back(l.count);
+            const uint32_t first = hits[3 * (size_t)(base + l.start) + 2] & 0x7FFFFFFFu;
+            const uint32_t last = hits[3 * (size_t)(base + l.start + l.count - 1) + 2] & 0x7FFFFFFFu;
+            maxpos = std::max(maxpos, std::max(first, last));
+        }
+        const uint32_t nh = (uint32_t)(hits.size() / 3) - base, nr = (uint32_t)block.size();
+        const uint32_t width = std::max(nh, nr);                               // holey layout: both arrays get `width` slots
+        hits.resize(3 * (size_t)(base + width), 0);
+        runs.resize(3 * (size_t)(base + width), 0);
+        nruns.push_back(nr);
+        read_len.push_back(maxpos);
+        hit_off.push_back(base + width);
+        rnames += cur_read;
+        rname_off.push_back(rnames.size());
+        base += width;
+        block.clear();
+        have_read = false;
+    };
+
+    const char* lp = nullptr;
+    size_t ll = 0;
+    std::string line;
+    while (!f->done) {
+        if (f->have_pend) { line.swap(f->pend_line); f->have_pend = false; }
+        else if (f->src->getline(lp, ll)) line.assign(lp, ll);
+        else { f->done = true; break; }
+        // line.strip().split('\t') -> exactly 4 fields (pair:449)
+        size_t b = 0, e = line.size();
+        while (b < e && (unsigned char)line[b] <= ' ') b++;
+        while (e > b && (unsigned char)line[e - 1] <= ' ') e--;
+        if (b == e) { f->err = "empty line in the mappings file"; return NTL_ERR_ARG; }
+        const char* s = line.data();
+        const char* t1 = (const char*)memchr(s + b, '\t', e - b);
+        const char* t2 = t1 ? (const char*)memchr(t1 + 1, '\t', (size_t)(s + e - (t1 + 1))) : nullptr;
+        const char* t3 = t2 ? (const char*)memchr(t2 + 1, '\t', (size_t)(s + e - (t2 + 1))) : nullptr;
+        if (!t3 || memchr(t3 + 1, '\t', (size_t)(s + e - (t3 + 1)))) { f->err = "a mappings line must have 4 tab-separated fields"; return NTL_ERR_ARG; }
+        const size_t rl = (size_t)(t1 - (s + b));
+        const bool same = have_read && cur_read.size() == rl && memcmp(cur_read.data(), s + b, rl) == 0;
+        if (!same) {
+            if (have_read && max_hits && hits.size() / 3 >= max_hits) {        // batch is full: this line starts the next call
+                f->pend_line = line; f->have_pend = true;
+                break;
+            }
+            flush();
+            cur_read.assign(s + b, rl);
+            have_read = true;
+        }
+        std::string cname(t1 + 1, (size_t)(t2 - (t1 + 1)));
+        uint32_t cid;
+        auto it = f->ctg_id.find(cname);
+        if (it != f->ctg_id.end()) cid = it->second;
+        else if (f->fixed_table) { f->err = "contig " + cname + " of the mappings file is not in the target"; return NTL_ERR_ARG; }
+        else { cid = (uint32_t)f->ctg_names.size(); f->ctg_id.emplace(cname, cid); f->ctg_names.push_back(cname); }
+        Line l; l.ctg = cid; l.start = (uint32_t)(hits.size() / 3) - base; l.count = 0;
+        const char* p = t3 + 1;
+        const char* end = s + e;
+        while (p < end) {
+            const char* sp = (const char*)memchr(p, ' ', (size_t)(end - p));
+            const char* te = sp ? sp : end;
+            uint32_t cposf, rposf;
+            if (!parse_token(p, te, cposf, rposf)) { f->err = "malformed minimizer position in the mappings file: " + std::string(p, (size_t)(te - p)); return NTL_ERR_ARG; }
+            hits.push_back(cid); hits.push_back(cposf); hits.push_back(rposf);
+            l.count++;
+            p = te + 1;
+        }
+        if (l.count == 0) { f->err = "a mappings line without minimizer positions"; return NTL_ERR_ARG; }
+        block.push_back(l);
+    }
+    flush();
+    out->n_reads = (uint32_t)nruns.size();
+    out->n_slots = hit_off.back();
+    out->hit_off = vec_to_malloc(hit_off); out->nruns = vec_to_malloc(nruns); out->read_len = vec_to_malloc(read_len);
+    out->runs = vec_to_malloc(runs); out->hits = vec_to_malloc(hits);
+    out->read_names = (char*)malloc(rnames.size() + 1);
+    if (out->read_names) memcpy(out->read_names, rnames.data(), rnames.size());
+    out->read_name_off = vec_to_malloc(rname_off);
+    // the contig table seen so far (all of it: ids are stable across calls)
+    std::string cn;
+    std::vector<uint64_t> co(1, 0);
+    for (const std::string& n : f->ctg_names) { cn += n; co.push_back(cn.size()); }
+    out->n_contigs = (uint32_t)f->ctg_names.size();
+    out->ctg_names = (char*)malloc(cn.size() + 1);
+    if (out->ctg_names) memcpy(out->ctg_names, cn.data(), cn.size());
+    out->ctg_name_off = vec_to_malloc(co);
+    if (!out->hit_off || !out->nruns || !out->read_len || !out->runs || !out->hits || !out->read_names || !out->read_name_off ||
+        !out->ctg_names || !out->ctg_name_off) { f->err = "out of memory"; return NTL_ERR_ARG; }
+    return NTL_OK;
+}
+
+void ntl_verbose_close(ntl_verbose_file* f) {
+    if (!f) return;
+    ntl_seqfile_close(f->src);
+    delete f;
+}
+
+}  // extern "C"

@@ -12,6 +12,7 @@ ntl_liftover_mappings; the host parses the two text files and prints the result 
 there (ntl_tally_mappings with resident inputs), i.e. rounds >= 2 of ntLink_rounds without the text round trip.
 """
 import argparse
+import os
 import sys
 
 import numpy as np
@@ -60,9 +61,17 @@ def agp_table(old_names, agp):
     return rows, new_names
 
 
-def load_mappings(mapping_lines):
-    "verbose_mapping.tsv -> (old contig names, arrays, read ids); contig ids are assigned in order of appearance"
-    mapping_lines = list(mapping_lines)
+def load_mappings(mappings):
+    """verbose_mapping.tsv -> (old contig names, arrays, read ids); contig ids are assigned in order of appearance.
+    `mappings` is a path (parsed natively by the library) or an iterable of lines (parsed in Python)."""
+    if isinstance(mappings, (str, bytes, os.PathLike)):
+        batches = list(api.read_verbose_mappings(os.fspath(mappings), None, share_repeated=False))
+        if not batches:
+            empty = np.zeros((0, 3), np.uint32)
+            return [], (np.zeros(1, np.uint32), np.zeros(0, np.uint32), empty, empty), []
+        hit_off, nruns, runs, hits, _, ids, names = batches[0]
+        return names, (hit_off, nruns, runs, hits), ids
+    mapping_lines = list(mappings)
     old_index = {}
     for line in mapping_lines:
         old_index.setdefault(line.split("\t", 2)[1], len(old_index))
@@ -111,8 +120,7 @@ def main(argv=None):
     try:
         with open(args.agp, encoding="utf-8") as fin:
             agp_lines = fin.readlines()
-        with open(args.mappings, encoding="utf-8") as fin:
-            data = liftover(ctx, fin, agp_lines, args.kmer, threads=args.t)
+        data = liftover(ctx, args.mappings, agp_lines, args.kmer, threads=args.t)
         with open(args.output, "wb") as fout:
             fout.write(data)
     finally:

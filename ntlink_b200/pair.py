@@ -275,7 +275,7 @@ class NtLink:
                 pf.close()
         return pairs_dict(self.ctx.pairs(), self.contigs.names)
 
-    def find_scaffold_pairs_checkpoints(self, chunk_lines=2_000_000):
+    def find_scaffold_pairs_checkpoints(self, chunk_hits=50_000_000):
         """replaces pair:437-464: re-tally the pairs from the checkpoint verbose_mapping.tsv; the accepted runs go to
         the GPU in chunks cut at read boundaries and only the pair events are computed there"""
         a = self.args
@@ -285,28 +285,17 @@ class NtLink:
         # lengths and name ranks only: the checkpoint path never touches the target minimizers (pair:571-575)
         none = np.empty(0, np.uint32)
         self.ctx.build_index(np.empty(0, np.uint64), none, none, self.contigs.lengths.astype(np.uint32), self.contigs.names)
-        idx = {n: i for i, n in enumerate(self.contigs.names)}
         prm = self.ctx.params(a.k, a.w or 1, a.z, a.f, a.x, a.sensitive, a.repeat_filter)
         self.ctx.events_reset()
         ordinal = 0
-
-        def submit(lines):
-            nonlocal ordinal
-            if lines:
-                arrays = parse_verbose_mappings(lines, idx)
-                self.ctx.tally_mappings(*arrays, prm, ordinal)
-                ordinal += len(arrays[1])
-
-        with open(a.checkpoint) as fin:
-            pending, last_id = [], None
-            for line in fin:
-                read_id = line.split("\t", 1)[0]
-                if len(pending) >= chunk_lines and read_id != last_id:
-                    submit(pending)
-                    pending = []
-                pending.append(line)
-                last_id = read_id
-            submit(pending)
+        # the file is parsed natively (ntl_verbose_*), in batches cut at read boundaries
+        try:
+            for hit_off, nruns, runs, hits, read_len, _, _ in api.read_verbose_mappings(a.checkpoint, self.contigs.names, share_repeated=True,
+                                                                                        max_hits=chunk_hits):
+                self.ctx.tally_mappings(hit_off, nruns, runs, hits, read_len, prm, ordinal)
+                ordinal += len(nruns)
+        except ValueError as exc:
+            raise NtlinkPairError(str(exc)) from exc
         return pairs_dict(self.ctx.pairs(), self.contigs.names)
 
     def _emit(self, res, reads, read_len, vf, pf):
