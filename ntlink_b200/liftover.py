@@ -89,6 +89,21 @@ def liftover(ctx, mapping_lines, agp_lines, k, threads=4):
     return res.verbose_bytes(reads, contigs, threads=threads)
 
 
+def liftover_file(ctx, mappings_path, agp_lines, k, out_path, threads=4, batch_hits=50_000_000):
+    """Streaming form for genome-scale files: the mappings are parsed natively in batches of ~batch_hits hits (cut at read
+    boundaries), every batch is lifted on the GPU and its text appended to out_path. Contig ids are assigned in order of
+    appearance and stay stable across batches; the AGP table is extended as new contigs show up."""
+    agp = read_agp(agp_lines)
+    with open(out_path, "wb") as fout:
+        for hit_off, nruns, runs, hits, _, ids, old_names in api.read_verbose_mappings(os.fspath(mappings_path), None, share_repeated=False,
+                                                                                     max_hits=batch_hits):
+            rows, new_names = agp_table(old_names, agp)
+            res = ctx.liftover_mappings(hit_off, nruns, runs, hits, rows, k)
+            reads = api.SeqBatch(np.empty(0, np.uint8), np.zeros(len(ids) + 1, np.uint64), ids)
+            contigs = api.SeqBatch(np.empty(0, np.uint8), np.zeros(len(new_names) + 1, np.uint64), new_names)
+            fout.write(res.verbose_bytes(reads, contigs, threads=threads))
+
+
 def liftover_and_tally(ctx, mapping_lines, agp_lines, k, scaffold_lengths, prm):
     """Round N+1 without text in between: liftover, then the checkpoint tally (pair:437-488) of the lifted mappings, both
     on the device. scaffold_lengths: name -> length of the round-N scaffolds. Returns pair.pairs_dict-style raw pairs
@@ -114,15 +129,14 @@ def main(argv=None):
     p.add_argument("-k", "--kmer", help="Kmer size", required=True, type=int)
     p.add_argument("-v", "--version", action="version", version="ntLink v1.3.11 (ntlink_b200 GPU path)")
     p.add_argument("--device", type=int, default=0)
+    p.add_argument("--batch-hits", type=float, default=5e7, help="hits per streamed batch [5e7]")
     p.add_argument("-t", type=int, default=4, help="host threads for text output")
     args = p.parse_args(argv)
     ctx = api.Context(args.device)
     try:
         with open(args.agp, encoding="utf-8") as fin:
             agp_lines = fin.readlines()
-        data = liftover(ctx, args.mappings, agp_lines, args.kmer, threads=args.t)
-        with open(args.output, "wb") as fout:
-            fout.write(data)
+        liftover_file(ctx, args.mappings, agp_lines, args.kmer, args.output, threads=args.t, batch_hits=int(args.batch_hits))
     finally:
         ctx.close()
 

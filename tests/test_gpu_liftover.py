@@ -36,6 +36,8 @@ def test_liftover_cli_against_reference(tmp_path, case):
     out = os.path.join(str(tmp_path), "lifted.tsv")
     liftover.main(["-m", m, "-a", a, "-o", out, "-k", str(MAN[case]["k"])])
     assert open(out, "rb").read() == util.lift_golden(case, "lifted.verbose_mapping.tsv")
+    liftover.main(["-m", m, "-a", a, "-o", out, "-k", str(MAN[case]["k"]), "--batch-hits", "300"])      # streamed in many batches
+    assert open(out, "rb").read() == util.lift_golden(case, "lifted.verbose_mapping.tsv")
 
 
 def round2_lengths(case):
