@@ -19,11 +19,17 @@
 
 #include <algorithm>
 #include <memory>
+#include <mutex>
+#include <unordered_map>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/ntlink_b200.h"
+
+// Big sequence buffers are recycled: a fresh 1 GB buffer costs hundreds of milliseconds of page faults, more than parsing
+// the batch that goes into it. ntl_free() parks up to two of them, the next batch takes one over.
+bool ntl_pool_release(void* p);
 
 namespace {
 
@@ -251,7 +257,7 @@ int64_t ntl_format_paf(const ntl_map_out* m, const char* read_names, const uint6
 }
 
 void ntl_buf_free(char* buf) { free(buf); }
-void ntl_free(void* p) { free(p); }
+void ntl_free(void* p) { if (!ntl_pool_release(p)) free(p); }
 
 }  // extern "C"
 
@@ -260,6 +266,34 @@ void ntl_free(void* p) { free(p); }
 // bytes), lines are located with memchr inside the block and sequence lines are appended straight into the output
 // buffer (no per-line strings). A line that straddles two blocks is the only case that is assembled separately.
 namespace {
+
+struct BigPool {
+    std::mutex mu;
+    std::unordered_map<void*, size_t> live;          // big buffers handed out (ptr -> capacity)
+    std::vector<std::pair<void*, size_t>> parked;    // released, ready for reuse
+    static constexpr size_t MAX_PARKED = 2, MAX_PARKED_BYTES = (size_t)6 << 30;
+};
+BigPool& big_pool() { static BigPool* p = new BigPool(); return *p; }     // never destroyed: buffers may outlive static teardown
+
+void* pool_take(size_t want, size_t& cap_out) {
+    BigPool& P = big_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    for (size_t i = 0; i < P.parked.size(); i++) {
+        if (P.parked[i].second >= want && P.parked[i].second <= want * 2 + (64u << 20)) {
+            void* p = P.parked[i].first;
+            cap_out = P.parked[i].second;
+            P.parked.erase(P.parked.begin() + (long)i);
+            P.live[p] = cap_out;
+            return p;
+        }
+    }
+    return nullptr;
+}
+void pool_register(void* p, size_t cap) {
+    BigPool& P = big_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.live[p] = cap;
+}
 
 struct GrowBuf {                 // malloc'ed, geometrically growing byte buffer that is handed to the caller
     char* p = nullptr;
@@ -270,17 +304,25 @@ struct GrowBuf {                 // malloc'ed, geometrically growing byte buffer
         while (c < want) c += c / 2 + (1u << 20);
         char* q = nullptr;
         if (!p && c >= (8u << 20)) {
-            // first (hinted) allocation of a large batch: 2 MiB aligned + transparent huge pages, so that filling the
-            // buffer does not take one page fault per 4 KiB
-            void* a = nullptr;
-            if (posix_memalign(&a, 2u << 20, c) == 0) {
+            // first (hinted) allocation of a large batch: a recycled buffer if one is parked, else 2 MiB aligned memory
+            // with transparent huge pages, so that filling it does not take one page fault per 4 KiB
+            size_t pc = 0;
+            void* a = pool_take(c, pc);
+            if (a) { q = (char*)a; c = pc; }
+            else if (posix_memalign(&a, 2u << 20, c) == 0) {
 #ifdef MADV_HUGEPAGE
                 madvise(a, c, MADV_HUGEPAGE);
 #endif
+                pool_register(a, c);
                 q = (char*)a;
             }
         }
-        if (!q) q = (char*)realloc(p, c);
+        if (!q) {
+            bool pooled = false;
+            if (p) { BigPool& P = big_pool(); std::lock_guard<std::mutex> lk(P.mu); pooled = P.live.erase(p) > 0; }
+            (void)pooled;                                    // a pooled buffer that has to grow simply leaves the pool
+            q = (char*)realloc(p, c);
+        }
         if (!q) return false;
         p = q; cap = c;
         return true;
@@ -295,6 +337,21 @@ struct GrowBuf {                 // malloc'ed, geometrically growing byte buffer
 
 }  // namespace
 
+bool ntl_pool_release(void* p) {
+    if (!p) return false;
+    BigPool& P = big_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) return false;
+    const size_t cap = it->second;
+    P.live.erase(it);
+    size_t bytes = cap;
+    for (auto& b : P.parked) bytes += b.second;
+    if (P.parked.size() < BigPool::MAX_PARKED && bytes <= BigPool::MAX_PARKED_BYTES) { P.parked.emplace_back(p, cap); return true; }
+    free(p);
+    return true;
+}
+
 struct ntl_seqfile {
     gzFile gz = nullptr;         // gzip input (or stdin)
     int fd = -1;                 // plain file
@@ -308,6 +365,7 @@ struct ntl_seqfile {
     bool parallel = false;
     off_t ppos = 0, fsize = 0;
     int threads = 1;
+    bool fastq = false;          // parallel mode on a file of 4-line FASTQ records
     const char* map = nullptr;   // the whole file, mapped read-only
 
     bool fill() {
@@ -351,14 +409,14 @@ struct ntl_seqfile {
 
 namespace {
 
-struct ParRec { uint64_t byte_start; uint64_t name_at; uint32_t name_len; uint64_t seq_len; uint64_t body_start; };
+struct ParRec { uint64_t byte_start; uint64_t name_at; uint32_t name_len; uint64_t seq_len; uint64_t body_start; uint64_t body_end; };
 struct ParSeg {
     GrowBuf names;
     std::vector<ParRec> recs;
     bool not_fasta = false, ok = true;
     ParSeg() = default;
     ParSeg(const ParSeg&) = delete;
-    ~ParSeg() { free(names.p); }
+    ~ParSeg() { ntl_free(names.p); }
 };
 
 // pass 1: the records of raw[b, e) (b is a record start or the first byte of the range): names and sequence lengths
@@ -375,7 +433,7 @@ void scan_segment(const char* raw, size_t b, size_t e, ParSeg& g) {
         if (c0 == '>') {
             size_t t = 1;
             while (t < ll && raw[p + t] != ' ' && raw[p + t] != '\t' && raw[p + t] != '\v' && raw[p + t] != '\f' && raw[p + t] != '\r') t++;
-            ParRec r; r.byte_start = p; r.name_at = g.names.n; r.name_len = (uint32_t)(t - 1); r.seq_len = 0; r.body_start = le + 1;
+            ParRec r; r.byte_start = p; r.name_at = g.names.n; r.name_len = (uint32_t)(t - 1); r.seq_len = 0; r.body_start = le + 1; r.body_end = 0;
             g.ok = g.names.append(raw + p + 1, t - 1);
             g.recs.push_back(r);
             in_rec = true;
@@ -417,6 +475,78 @@ size_t next_record_start(const char* raw, size_t p, size_t e) {
     return e;
 }
 
+
+// ---- FASTQ (4 lines per record) -------------------------------------------------------------------------------------
+// line [p, le) of raw[.., e): le = index of its '\n' (or e); returns the length without a trailing '\r'
+inline size_t line_at(const char* raw, size_t p, size_t e, size_t& le) {
+    const char* nl = (const char*)memchr(raw + p, '\n', e - p);
+    le = nl ? (size_t)(nl - raw) : e;
+    size_t ll = le - p;
+    if (ll && raw[p + ll - 1] == '\r') ll--;
+    return ll;
+}
+
+// Is the line starting at q the header of a well-formed 4-line record ('@', sequence, '+', as many quality characters)?
+// A quality line may start with '@' too, so the structure is what identifies a header. Fills the record on success.
+bool fastq_record_at(const char* raw, size_t q, size_t e, ParRec& r, size_t& next) {
+    if (q >= e || raw[q] != '@') return false;
+    size_t l1e, l2e, l3e, l4e;
+    const size_t l1 = line_at(raw, q, e, l1e);
+    if (l1e >= e) return false;
+    const size_t l2 = line_at(raw, l1e + 1, e, l2e);
+    if (l2e >= e) return false;
+    const size_t l3 = line_at(raw, l2e + 1, e, l3e);
+    if (l3 == 0 || raw[l2e + 1] != '+' || l3e >= e) return false;
+    const size_t l4 = line_at(raw, l3e + 1, e, l4e);
+    if (l4 != l2) return false;
+    if (l2 && (raw[l1e + 1] == '@' || raw[l1e + 1] == '+' || raw[l1e + 1] == '>')) return false;   // the sequential reader would see a header / separator
+    size_t t = 1;
+    while (t < l1 && raw[q + t] != ' ' && raw[q + t] != '\t' && raw[q + t] != '\v' && raw[q + t] != '\f' && raw[q + t] != '\r') t++;
+    r.byte_start = q; r.name_at = 0; r.name_len = (uint32_t)(t - 1); r.seq_len = l2; r.body_start = l1e + 1; r.body_end = l2e + 1;
+    next = l4e < e ? l4e + 1 : e;
+    return true;
+}
+
+// first record header at a line start >= p
+size_t next_fastq_start(const char* raw, size_t p, size_t e) {
+    size_t q = p;
+    if (q > 0 && raw[q - 1] != '\n') {                               // move to the next line start
+        const char* nl = (const char*)memchr(raw + q, '\n', e - q);
+        if (!nl) return e;
+        q = (size_t)(nl - raw) + 1;
+    }
+    ParRec r;
+    size_t next;
+    while (q < e) {
+        if (fastq_record_at(raw, q, e, r, next)) return q;
+        const char* nl = (const char*)memchr(raw + q, '\n', e - q);
+        if (!nl) return e;
+        q = (size_t)(nl - raw) + 1;
+    }
+    return e;
+}
+
+// pass 1 for FASTQ: strictly 4-line records from b to e; anything else hands the file over to the sequential reader
+void scan_segment_fastq(const char* raw, size_t b, size_t e, size_t file_end, ParSeg& g) {
+    g.ok = g.names.reserve(1u << 12);
+    size_t p = b;
+    while (g.ok && p < e) {
+        ParRec r;
+        size_t next;
+        if (!fastq_record_at(raw, p, file_end, r, next)) {
+            // blank lines between records are fine (the sequential reader skips them); anything else is not
+            size_t le;
+            if (line_at(raw, p, e, le) == 0) { p = le + 1; continue; }
+            g.not_fasta = true;
+            return;
+        }
+        r.name_at = g.names.n;
+        g.ok = g.names.append(raw + p + 1, r.name_len);
+        g.recs.push_back(r);
+        p = next;
+    }
+}
+
 template <class F>
 void run_threads(size_t n, F&& body) {
     std::vector<std::thread> th;
@@ -447,6 +577,24 @@ int read_parallel(ntl_seqfile* f, uint64_t max_bases, GrowBuf& seq, GrowBuf& nam
         // cut at the last record start in the range; a range without one (a record larger than the range) grows
         size_t q = n;
         cut = 0;
+        if (f->fastq) {
+            const size_t total = (size_t)(f->fsize - start);
+            for (size_t window = 4u << 20; cut == 0; window *= 4) {
+                size_t p = n > window ? n - window : 0;
+                p = next_fastq_start(raw, p, total);
+                while (p < n) {                                       // walk the records of the window; keep the last start below n
+                    ParRec r;
+                    size_t next;
+                    if (!fastq_record_at(raw, p, total, r, next)) { p = next_fastq_start(raw, p + 1, total); continue; }
+                    if (p > 0) cut = p;
+                    p = next;
+                }
+                if (n <= window) break;
+            }
+            if (cut > 0) break;
+            want *= 2;
+            continue;
+        }
         while (q > 1) {
             const char* gt = (const char*)memrchr(raw, '>', q);
             if (!gt) break;
@@ -460,14 +608,19 @@ int read_parallel(ntl_seqfile* f, uint64_t max_bases, GrowBuf& seq, GrowBuf& nam
     // segments at record starts
     std::vector<size_t> bounds;
     bounds.push_back(0);
+    const size_t file_end = (size_t)(f->fsize - start);
     for (int t = 1; t < f->threads; t++) {
-        const size_t b = next_record_start(raw, (size_t)((uint64_t)cut * t / f->threads), cut);
+        const size_t at = (size_t)((uint64_t)cut * t / f->threads);
+        const size_t b = f->fastq ? next_fastq_start(raw, at, cut) : next_record_start(raw, at, cut);
         if (b > bounds.back() && b < cut) bounds.push_back(b);
     }
     bounds.push_back(cut);
     const size_t nseg = bounds.size() - 1;
     std::unique_ptr<ParSeg[]> segs(new ParSeg[nseg]);
-    run_threads(nseg, [&](size_t g) { scan_segment(raw, bounds[g], bounds[g + 1], segs[g]); });
+    run_threads(nseg, [&](size_t g) {
+        if (f->fastq) scan_segment_fastq(raw, bounds[g], bounds[g + 1], file_end, segs[g]);
+        else scan_segment(raw, bounds[g], bounds[g + 1], segs[g]);
+    });
     for (size_t g = 0; g < nseg; g++) {
         if (!segs[g].ok) return -1;
         if (segs[g].not_fasta) { f->parallel = false; return 0; }
@@ -509,7 +662,8 @@ int read_parallel(ntl_seqfile* f, uint64_t max_bases, GrowBuf& seq, GrowBuf& nam
         uint64_t at = seg_seq_at[g];
         for (size_t r = 0; r < seg_cnt[g]; r++) {
             const ParRec& rec = segs[g].recs[r];
-            const size_t end = r + 1 < segs[g].recs.size() ? (size_t)segs[g].recs[r + 1].byte_start : bounds[g + 1];
+            const size_t end = rec.body_end ? (size_t)rec.body_end
+                                            : r + 1 < segs[g].recs.size() ? (size_t)segs[g].recs[r + 1].byte_start : bounds[g + 1];
             copy_body(raw, (size_t)rec.body_start, end, seq.p + at);
             at += rec.seq_len;
         }
@@ -547,8 +701,8 @@ int ntl_seqfile_open(const char* path, ntl_seqfile** out) {
             const char* env = getenv("NTL_READER_THREADS");
             const unsigned hw = std::thread::hardware_concurrency();
             f->threads = env ? atoi(env) : (int)std::max(1u, std::min(8u, hw / 2));
-            if (f->threads > 1 && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && got >= 1 && magic[0] == '>') {
-                f->parallel = true; f->fsize = sb.st_size; f->ppos = 0;
+            if (f->threads > 1 && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && got >= 1 && (magic[0] == '>' || magic[0] == '@')) {
+                f->parallel = true; f->fsize = sb.st_size; f->ppos = 0; f->fastq = magic[0] == '@';
             }
         }
     }
@@ -567,12 +721,12 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_
     size_t ll = 0;
     if (f->parallel) {
         const int pr = read_parallel(f, max_bases, seq, names, offs, noffs);
-        if (pr < 0) { free(seq.p); free(names.p); return NTL_ERR_ARG; }
+        if (pr < 0) { ntl_free(seq.p); ntl_free(names.p); return NTL_ERR_ARG; }
         if (pr == 1) {
             const uint32_t nseq_p = (uint32_t)(offs.size() - 1);
             uint64_t* o = (uint64_t*)malloc(offs.size() * 8);
             uint64_t* no = (uint64_t*)malloc(noffs.size() * 8);
-            if (!o || !no || !seq.reserve(seq.n + 64) || !names.reserve(names.n + 1)) { free(seq.p); free(names.p); free(o); free(no); return NTL_ERR_ARG; }
+            if (!o || !no || !seq.reserve(seq.n + 64) || !names.reserve(names.n + 1)) { ntl_free(seq.p); ntl_free(names.p); free(o); free(no); return NTL_ERR_ARG; }
             memset(seq.p + seq.n, 'N', 64);
             memcpy(o, offs.data(), offs.size() * 8);
             memcpy(no, noffs.data(), noffs.size() * 8);
@@ -580,7 +734,7 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_
             return NTL_OK;
         }
         // not plain FASTA after all: continue sequentially from the first unread record
-        free(seq.p); free(names.p); seq = GrowBuf(); names = GrowBuf();
+        ntl_free(seq.p); ntl_free(names.p); seq = GrowBuf(); names = GrowBuf();
         offs.assign(1, 0); noffs.assign(1, 0);
         lseek(f->fd, f->ppos, SEEK_SET);
         f->pos = f->len = 0; f->eof = false; f->have_pending = false;
@@ -629,7 +783,7 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_
     uint64_t* o = (uint64_t*)malloc(offs.size() * 8);
     uint64_t* no = (uint64_t*)malloc(noffs.size() * 8);
     if (!ok || !o || !no || !seq.reserve(seq.n + 64) || !names.reserve(names.n + 1)) {
-        free(seq.p); free(names.p); free(o); free(no);
+        ntl_free(seq.p); ntl_free(names.p); free(o); free(no);
         return NTL_ERR_ARG;
     }
     memset(seq.p + seq.n, 'N', 64);

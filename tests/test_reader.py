@@ -140,3 +140,44 @@ def test_parallel_fasta_reader_equals_sequential(tmp_path, width, crlf, tail):
             assert par_recs == seq_recs == want
             if tail != "fastq":               # after a hand-over the cuts may differ, the records may not
                 assert par_sizes == seq_sizes
+
+
+def fastq_text(rng, n, adversarial=True, multiline=False):
+    recs = []
+    for r in range(n):
+        L = int(rng.integers(0, 500))
+        s = "".join("ACGTN"[int(x)] for x in rng.integers(0, 5, L))
+        q = "".join("@+>I5#"[int(x)] for x in rng.integers(0, 6, L)) if adversarial else "I" * L     # quality lines may start with @ + >
+        if multiline and L > 60:
+            s = s[:60] + "\n" + s[60:]
+            q = q[:60] + "\n" + q[60:]
+        recs.append(f"@rec{r} desc\t{r}\n{s}\n+{'rec%d' % r if r % 3 == 0 else ''}\n{q}\n")
+    return "".join(recs)
+
+
+@pytest.mark.parametrize("variant", ["plain", "crlf", "multiline", "no_final_newline", "blank_lines", "fasta_tail"])
+def test_parallel_fastq_reader_equals_sequential(tmp_path, variant):
+    """4-line FASTQ is parsed in parallel too; record starts are recognised by structure (a quality line may start with
+    '@'), and anything that is not strictly 4-line FASTQ is handed to the sequential reader"""
+    rng = np.random.default_rng(len(variant))
+    text = fastq_text(rng, 3000, multiline=(variant == "multiline"))
+    if variant == "crlf":
+        text = text.replace("\n", "\r\n")
+    elif variant == "no_final_newline":
+        text = text[:-1]
+    elif variant == "blank_lines":
+        text = text.replace("\n@rec7 ", "\n\n\n@rec7 ").replace("\n@rec1500 ", "\n\n@rec1500 ")
+    elif variant == "fasta_tail":
+        text += make_text(rng, 40, False, 60)
+    path = os.path.join(str(tmp_path), "p.fq")
+    with open(path, "w", newline="") as fout:
+        fout.write(text)
+    want = [(n, q.encode()) for n, q in reference_parse(text.replace("\r\n", "\n"))]
+    for max_bases in (0, 100_000, 2_000):
+        seq_recs, seq_sizes = _records(path, max_bases, 1)
+        assert len(seq_recs) >= 3000 and seq_recs == want
+        for threads in (2, 7):
+            par_recs, par_sizes = _records(path, max_bases, threads)
+            assert par_recs == seq_recs
+            if variant in ("plain", "crlf", "no_final_newline", "blank_lines"):
+                assert par_sizes == seq_sizes
