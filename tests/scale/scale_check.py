@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Large-scale parity + throughput check (not part of the default test-suite: takes minutes).
 
-    python tools/scale_check.py --genome 100e6 --coverage 10 -k 24 -w 250 --sensitive
+    python tests/scale/scale_check.py --genome 100e6 --coverage 10 -k 24 -w 250 --sensitive
 
 Generates a synthetic assembly + ONT-like reads (ntlink_b200/synth.py), runs the whole GPU path through the C ABI,
 and compares against the CPU oracle: sketch checksums of ALL reads (multi-threaded C oracle) and byte-equality of
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 sys.path.insert(0, os.path.join(REPO, "oracle"))

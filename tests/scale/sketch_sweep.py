@@ -2,7 +2,7 @@
 """Sketch-only kernel time over (k, w) settings the reference uses (ntLink defaults, the overlap stage's k15/w5 and the
 gap-fill stage's k20/w10), with a checksum comparison against the C oracle on a sample of the sequences.
 
-    python tools/sketch_sweep.py [--bases 100e6]"""
+    python tests/scale/sketch_sweep.py [--bases 100e6]"""
 import argparse
 import json
 import os
@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
