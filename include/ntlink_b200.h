@@ -45,7 +45,7 @@ int ntl_version(void);
  * expected candidates per window), "batch_bases" (bases per device batch), "pipeline_min_bases" (4x the chunk size of
  * the pipelined ntl_map_reads), "async" (1: ntl_map_reads / ntl_map_resident enqueue the whole call without waiting for
  * the device and synchronise once; 0: the step-by-step path the sync-free one falls back to), "graph" (1: each chunk of
- * a sync-free call is launched as one CUDA graph), "copy_threads" (host threads that move pageable caller memory into
+ * a sync-free call is launched as one CUDA graph), "resident_chunk_bases" (bases per device batch of ntl_map_resident), "copy_threads" (host threads that move pageable caller memory into
  * pinned bounce buffers; -1 auto, 0 leaves the staging to the driver) */
 int ntl_set_option(ntl_ctx* ctx, const char* name, double value);
 
@@ -286,6 +286,12 @@ int ntl_map_resident(ntl_ctx* ctx, uint64_t first_read_ordinal, const ntl_params
 int ntl_target_upload(ntl_ctx* ctx, const char* seq, const uint64_t* offsets, uint32_t ncontig,
                       const uint32_t* name_rank);
 int ntl_index_build_resident(ntl_ctx* ctx, int k, int w);
+/* multi-GPU: sketch contigs [first, first + count) of the resident target; the triples (hash, GLOBAL
+ * contig id, pos|strand) stay on the device for the caller's all-gather, ntl_index_build_device then builds the replicated
+ * index from the gathered arrays with the lengths / name ranks ntl_target_resident_meta returns ([ncontig] each). */
+int ntl_target_sketch_resident(ntl_ctx* ctx, uint32_t first, uint32_t count, int k, int w, uint64_t* n_mx, void** d_hash,
+                               void** d_contig, void** d_pos_strand);
+int ntl_target_resident_meta(ntl_ctx* ctx, uint32_t* contig_len, uint32_t* name_rank);
 /* device timings (ms, CUDA events on the library's stream) of the last call, indexed by NTL_T_*; and the
  * number of kernels this library launched since ntl_timing_reset */
 enum { NTL_T_PACK = 0, NTL_T_DENSE, NTL_T_SELECT, NTL_T_GAP, NTL_T_EMIT, NTL_T_LOOKUP, NTL_T_CHAIN, NTL_T_TALLY,
@@ -308,6 +314,26 @@ int ntl_mark_elapsed(ntl_ctx* ctx, double* ms);
 /* device-to-device copy on the library's stream (synchronous on return); lets the caller move the library's device
  * arrays into buffers it owns (e.g. torch tensors handed to NCCL) */
 int ntl_copy_device(ntl_ctx* ctx, void* d_dst, const void* d_src, uint64_t bytes);
+
+/* ---- synthetic benchmark / test inputs ------------------------------------------------
+ * Deterministic, counter-based: the device entry points fill the resident target / reads (the multi-Gbp configurations of
+ * BASELINE.json never exist on the host), the host entry points produce the same bytes for the tests and for the CPU
+ * reference arm. A genome base is a function of (seed, position); a contig / read is a genome slice, optionally
+ * reverse-complemented; contigs may carry one run of N; reads get iid substitutions / deletions / insertions drawn per
+ * source position with thresholds out of 65536 (ONT-like: 4 % / 3 % / 3 % = 2621 / 1966 / 1966). */
+typedef struct { uint64_t start; uint32_t len, flip, n_start, n_len; uint32_t pad[2]; } ntl_synth_contig;
+typedef struct { uint64_t start; uint32_t len, flip; uint64_t id; } ntl_synth_read;
+int ntl_synth_target_resident(ntl_ctx* ctx, uint64_t seed, const ntl_synth_contig* contigs, uint32_t ncontig, const uint32_t* name_rank);
+int ntl_synth_reads_resident(ntl_ctx* ctx, uint64_t seed, const ntl_synth_read* reads, uint32_t nreads, uint32_t sub16, uint32_t del16,
+                             uint32_t ins16, uint64_t* total_bases);
+/* which: 0 = resident target, 1 = resident reads */
+int ntl_resident_info(ntl_ctx* ctx, int which, uint32_t* nseq, uint64_t* nbases);
+/* sequences [first, first + count) of the resident target / reads -> host: off_out[count + 1] (rebased to 0), seq_out may be NULL */
+int ntl_resident_download(ntl_ctx* ctx, int which, uint32_t first, uint32_t count, char* seq_out, uint64_t* off_out);
+/* host generators: off_out[n + 1] is always written; with seq_out == NULL only the offsets (sizes) are computed */
+int ntl_synth_host_contigs(uint64_t seed, const ntl_synth_contig* contigs, uint32_t ncontig, uint64_t* off_out, char* seq_out, int threads);
+int ntl_synth_host_reads(uint64_t seed, const ntl_synth_read* reads, uint32_t nreads, uint32_t sub16, uint32_t del16, uint32_t ins16,
+                         uint64_t* off_out, char* seq_out, int threads);
 
 #ifdef __cplusplus
 }

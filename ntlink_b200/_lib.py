@@ -124,6 +124,14 @@ SIGNATURES = {
     "ntl_mark": (C.c_int, [_VP, C.c_int]),
     "ntl_mark_elapsed": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "ntl_copy_device": (C.c_int, [_VP, _VP, _VP, C.c_uint64]),
+    "ntl_target_sketch_resident": (C.c_int, [_VP, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _U64P, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    "ntl_target_resident_meta": (C.c_int, [_VP, _VP, _VP]),
+    "ntl_synth_target_resident": (C.c_int, [_VP, C.c_uint64, _VP, C.c_uint32, _VP]),
+    "ntl_synth_reads_resident": (C.c_int, [_VP, C.c_uint64, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _U64P]),
+    "ntl_resident_info": (C.c_int, [_VP, C.c_int, _U32P, _U64P]),
+    "ntl_resident_download": (C.c_int, [_VP, C.c_int, C.c_uint32, C.c_uint32, _VP, _VP]),
+    "ntl_synth_host_contigs": (C.c_int, [C.c_uint64, _VP, C.c_uint32, _VP, _VP, C.c_int]),
+    "ntl_synth_host_reads": (C.c_int, [C.c_uint64, _VP, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP, C.c_int]),
 }
 
 _lib = None

@@ -520,6 +520,46 @@ class Context:
     def index_build_resident(self, k, w):
         self._check(self.lib.ntl_index_build_resident(self.h, k, w), "ntl_index_build_resident")
 
+    # ---- synthetic resident inputs (bench / tests; csrc/synth_logic.cuh)
+    def synth_target_resident(self, seed, plan, names):
+        "generate the contigs of a synth.plan_assembly plan straight into the resident target"
+        plan = np.ascontiguousarray(plan)
+        rank = name_ranks(names)
+        self._check(self.lib.ntl_synth_target_resident(self.h, seed, plan.ctypes.data, len(plan), _ptr(rank)), "ntl_synth_target_resident")
+
+    def synth_reads_resident(self, seed, plan, err=(2621, 1966, 1966)):
+        "generate the reads of a synth.plan_reads plan straight into the resident reads; returns the number of bases"
+        plan = np.ascontiguousarray(plan)
+        tot = C.c_uint64()
+        self._check(self.lib.ntl_synth_reads_resident(self.h, seed, plan.ctypes.data, len(plan), err[0], err[1], err[2], C.byref(tot)),
+                    "ntl_synth_reads_resident")
+        return tot.value
+
+    def resident_info(self, which):
+        "(number of sequences, bases) of the resident target (which=0) or reads (which=1)"
+        n, b = C.c_uint32(), C.c_uint64()
+        self._check(self.lib.ntl_resident_info(self.h, which, C.byref(n), C.byref(b)), "ntl_resident_info")
+        return n.value, b.value
+
+    def resident_download(self, which, first, count, names, pinned=False):
+        """sequences [first, first+count) of the resident target / reads as a SeqBatch on the host (pinned=True: the
+        arrays live in pinned memory obtained through torch, for end-to-end timing)"""
+        off = np.zeros(count + 1, np.uint64)
+        self._check(self.lib.ntl_resident_download(self.h, which, first, count, None, _ptr(off)), "ntl_resident_download")
+        nb = int(off[-1])
+        keep = None
+        if pinned:
+            import torch
+            keep = torch.empty(nb + 64, dtype=torch.uint8, pin_memory=True)
+            seq = keep.numpy()
+        else:
+            seq = np.empty(nb + 64, np.uint8)
+        seq[nb:] = ord("N")
+        self._check(self.lib.ntl_resident_download(self.h, which, first, count, seq.ctypes.data, _ptr(off)), "ntl_resident_download")
+        out = SeqBatch.__new__(SeqBatch)
+        out.seq, out.offsets, out.names, out._name_blob, out._keep = seq[:nb], off, list(names), None, keep
+        return out
+
     def stat(self, name):
         "counters since init: async_calls, async_fallbacks, graph_launches"
         v = C.c_double()

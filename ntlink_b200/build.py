@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libntlink_b200.so")
 SOURCES = ["capi.cu", "sketch.cu", "map.cu", "scan.cu", "emit.cpp"]
-HEADERS = ["common.cuh", "nthash.cuh", "sketch_logic.cuh", "map_logic.cuh", os.path.join("..", "..", "include", "ntlink_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "ntlink_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 

@@ -4,10 +4,12 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <functional>
 #include <thread>
 
 #include "common.cuh"
 #include "lift_logic.cuh"
+#include "synth_kernels.cuh"
 
 namespace ntl {
 int expand_contig_ids(ntl_ctx* c, const DeviceSketch& sk, DevBuf& ctg_ids);
@@ -54,7 +56,14 @@ struct Results {
     std::vector<ntl_pair> pairs;
     std::vector<int32_t> gaps;
     // resident inputs (bench)
+    // resident reads: ASCII of all reads back to back, cut into chunks of whole reads (< 4 Gbp each, 32-bit positions
+    // inside a device batch); r_off holds the offsets of every chunk rebased to the chunk's first base, back to back
+    struct ResChunk { uint32_t first, count; uint64_t base, nbases, dev_base; size_t off_at; };   // dev_base: 256-byte aligned place in r_seq
     DevBuf r_seq, r_off, r_len; uint32_t r_nreads = 0; uint64_t r_bases = 0;
+    std::vector<ResChunk> r_chunks;
+    std::vector<uint64_t> r_abs_off;           // host copy of the absolute offsets [r_nreads + 1]
+    std::vector<cudaGraphExec_t> resident_execs;
+    uint64_t resident_chunk_bases = 512ull << 20;
     DevBuf t_seq, t_off, t_ctg; uint32_t t_ncontig = 0; uint64_t t_bases = 0;
     std::vector<uint32_t> t_len, t_rank;
     DevBuf stage_off, ctg_ids, read_len, in_hash, in_posf, in_ctg;
@@ -68,7 +77,7 @@ struct Results {
     cudaEvent_t comp_done[2] = {nullptr, nullptr};
     PinnedBuf pin_slot[2];                     // bounce buffers for callers that pass pageable memory
     std::vector<cudaGraphExec_t> chunk_execs;
-    cudaGraphExec_t resident_exec = nullptr, index_exec = nullptr;
+    cudaGraphExec_t index_exec = nullptr;
     PinnedBuf idx_meta;                        // contig lengths + name ranks of the index being built (stable for the graph)
     PinnedBuf call_hoff;
     uint64_t last_call_hits = 0, last_call_bases = 0;
@@ -178,14 +187,13 @@ int ntl_init(int device, ntl_ctx** out) {
     c->res = new Results();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete res_of(c); delete c; return NTL_ERR_CUDA; }
-    for (int i = 0; i < 2 * T_NUM; i++) cudaEventCreate(&c->ev[i]);
     cudaEventCreate(&c->mark[0]); cudaEventCreate(&c->mark[1]);
     cudaStreamCreateWithFlags(&res_of(c)->copy_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&res_of(c)->h2d_done[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&res_of(c)->h2d_done[1], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&res_of(c)->comp_done[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&res_of(c)->comp_done[1], cudaEventDisableTiming);
-    for (int i = 0; i < T_NUM; i++) { c->ev_used[i] = false; c->ms_accum[i] = 0; }
+    for (int i = 0; i < T_NUM; i++) { c->ev_open[i] = -1; c->ms_accum[i] = 0; }
     *out = c;
     return NTL_OK;
 }
@@ -224,13 +232,14 @@ void ntl_destroy(ntl_ctx* c) {
     R->pin_slot[0].release(); R->pin_slot[1].release();
     for (cudaGraphExec_t e : R->chunk_execs) if (e) cudaGraphExecDestroy(e);
     R->chunk_execs.clear();
-    if (R->resident_exec) cudaGraphExecDestroy(R->resident_exec);
+    for (cudaGraphExec_t e : R->resident_execs) if (e) cudaGraphExecDestroy(e);
+    R->resident_execs.clear();
     if (R->index_exec) cudaGraphExecDestroy(R->index_exec);
     R->idx_meta.release();
     cudaStreamSynchronize(R->copy_stream);
     cudaStreamDestroy(R->copy_stream);
     c->h_status.release();
-    for (int i = 0; i < 2 * T_NUM; i++) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]);
     cudaStreamDestroy(c->stream);
     delete R;
@@ -257,6 +266,9 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
     } else if (!strcmp(name, "pipeline_min_bases")) {
         if (value < 1024 || value > 3.9e9) { c->err = "pipeline_min_bases out of range"; return NTL_ERR_ARG; }
         c->pipeline_min_bases = (uint64_t)value;
+    } else if (!strcmp(name, "resident_chunk_bases")) {
+        if (value < 65536 || value > 3.9e9) { c->err = "resident_chunk_bases out of range"; return NTL_ERR_ARG; }
+        res_of(c)->resident_chunk_bases = (uint64_t)value;
     } else if (!strcmp(name, "batch_bases")) {
         if (value < 1024 || value > 3.9e9) { c->err = "batch_bases out of range"; return NTL_ERR_ARG; }
         c->batch_bases = (uint64_t)value;
@@ -1042,20 +1054,45 @@ int ntl_pairs_finish(ntl_ctx* c, ntl_pairs_out* out) {
 }
 
 // ------------------------------------------------------------------------------------------- resident (bench)
+// cut the resident reads into chunks of whole reads and put the rebased offsets of every chunk on the device
+static int plan_resident_chunks(ntl_ctx* c, uint32_t nreads) {
+    Results* R = res_of(c);
+    const std::vector<uint64_t>& ao = R->r_abs_off;
+    R->r_chunks.clear();
+    std::vector<uint32_t> bounds;
+    const uint64_t per = std::min<uint64_t>(R->resident_chunk_bases, (1ull << 32) - 8192);
+    plan_batches(ao.data(), nreads, per, bounds);
+    std::vector<uint64_t> ho;
+    ho.reserve((size_t)nreads + bounds.size() + 1);
+    uint64_t dev_at = 0;
+    for (size_t i = 0; i + 1 < bounds.size(); i++) {
+        Results::ResChunk ch;
+        ch.first = bounds[i]; ch.count = bounds[i + 1] - bounds[i];
+        ch.base = ao[ch.first] - ao[0]; ch.nbases = ao[bounds[i + 1]] - ao[ch.first]; ch.off_at = ho.size();
+        ch.dev_base = dev_at; dev_at = (dev_at + ch.nbases + 511) & ~255ull;
+        if (ch.nbases >= (1ull << 32) - 4096) { c->err = "a single resident read/chunk exceeds 4 Gbp"; return NTL_ERR_ARG; }
+        for (uint32_t r = ch.first; r <= bounds[i + 1]; r++) ho.push_back(ao[r] - ao[ch.first]);
+        R->r_chunks.push_back(ch);
+    }
+    NTL_CUDA(c, R->r_off.ensure((ho.size() + 1) * 8));
+    NTL_CUDA(c, R->r_seq.ensure(dev_at + 512));
+    if (!ho.empty()) NTL_CUDA(c, cudaMemcpyAsync(R->r_off.p, ho.data(), ho.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    R->r_nreads = nreads; R->r_bases = ao[nreads] - ao[0];
+    return NTL_OK;
+}
+
 int ntl_reads_upload(ntl_ctx* c, const char* seq, const uint64_t* offsets, uint32_t nreads) {
     if (!c || (!seq && nreads) || !offsets) return NTL_ERR_ARG;
     Results* R = res_of(c);
     cudaSetDevice(c->device);
     const uint64_t nb = offsets[nreads] - offsets[0];
-    if (nb >= (1ull << 32) - 4096) { c->err = "resident batch exceeds 4 Gbp"; return NTL_ERR_ARG; }
-    std::vector<uint64_t> ho((size_t)nreads + 1);
-    for (uint32_t i = 0; i <= nreads; i++) ho[i] = offsets[i] - offsets[0];
-    NTL_CUDA(c, R->r_seq.ensure(nb + 256));
-    NTL_CUDA(c, R->r_off.ensure(((size_t)nreads + 1) * 8));
-    if (nb) NTL_CUDA(c, cudaMemcpyAsync(R->r_seq.p, seq + offsets[0], nb, cudaMemcpyHostToDevice, c->stream));
-    NTL_CUDA(c, cudaMemcpyAsync(R->r_off.p, ho.data(), ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    (void)nb;
+    R->r_abs_off.assign(offsets, offsets + nreads + 1);
+    NTL_TRY(plan_resident_chunks(c, nreads));
+    for (const Results::ResChunk& ch : R->r_chunks)
+        if (ch.nbases) NTL_CUDA(c, cudaMemcpyAsync(R->r_seq.as<char>() + ch.dev_base, seq + offsets[ch.first], ch.nbases, cudaMemcpyHostToDevice, c->stream));
     NTL_CUDA(c, cudaStreamSynchronize(c->stream));
-    R->r_nreads = nreads; R->r_bases = nb;
     return NTL_OK;
 }
 
@@ -1064,58 +1101,67 @@ int ntl_map_resident(ntl_ctx* c, uint64_t first_read_ordinal, const ntl_params* 
     Results* R = res_of(c);
     cudaSetDevice(c->device);
     if (!R->r_nreads) { c->err = "ntl_map_resident: no resident reads"; return NTL_ERR_STATE; }
+    if (!c->index.built) { c->err = "ntl_map_resident: no target index"; return NTL_ERR_STATE; }
+    const size_t nch = R->r_chunks.size();
+    auto chunk_seq = [&](const Results::ResChunk& ch) { return R->r_seq.as<uint8_t>() + ch.dev_base; };
+    auto chunk_off = [&](const Results::ResChunk& ch) { return R->r_off.as<uint64_t>() + ch.off_at; };
     if (c->async_mode) {
-        // sync-free: sketch + mapping enqueued back to back (as one CUDA graph, updated in place from call to call),
-        // one synchronisation at the end (see map_reads_async)
+        // sync-free: every chunk's sketch + mapping enqueued back to back (one CUDA graph per chunk position, updated in
+        // place from call to call), one synchronisation at the end (see map_reads_async)
         CallState* call = nullptr;
         NTL_TRY(call_begin(c, &call));
-        auto enqueue = [&]() -> int {
-            tick(c, T_TOTAL);
-            NTL_TRY(sketch_device(c, R->r_seq.as<uint8_t>(), R->r_off.as<uint64_t>(), R->r_nreads, R->r_bases, (uint32_t)prm->k,
-                                  (uint32_t)prm->w, c->dsk, call));
-            NTL_TRY(read_len_device(c, R->r_off.as<uint64_t>(), R->r_nreads, R->read_len));
-            NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), R->r_nreads, first_read_ordinal, prm, nullptr, nullptr, nullptr, call));
-            NTL_TRY(call_chunk_finish(c, call, 0, R->r_nreads, nullptr));
-            tock(c, T_TOTAL);
-            return NTL_OK;
-        };
-        bool launched = false;
-        if (c->graph_mode) {
-            NTL_TRY(sketch_prepare(c, (uint32_t)prm->k));
-            NTL_TRY(call_reserve_events(c, R->r_nreads));
-            cudaGraph_t graph = nullptr;
-            NTL_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
-            c->capturing = true;
-            const int rc = enqueue();
-            c->capturing = false;
-            cudaError_t ge = cudaStreamEndCapture(c->stream, &graph);
-            if (rc != NTL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (ge == cudaSuccess && inject_graph_failure("resident")) ge = cudaErrorUnknown;
-            if (ge == cudaSuccess && R->resident_exec) {
-                cudaGraphExecUpdateResultInfo info;
-                if (cudaGraphExecUpdate(R->resident_exec, graph, &info) != cudaSuccess) {
-                    cudaGetLastError();
-                    cudaGraphExecDestroy(R->resident_exec);
-                    R->resident_exec = nullptr;
+        NTL_TRY(sketch_prepare(c, (uint32_t)prm->k));
+        if (R->resident_execs.size() < nch) R->resident_execs.resize(nch, nullptr);
+        tick(c, T_TOTAL);
+        for (size_t i = 0; i < nch; i++) {
+            const Results::ResChunk& ch = R->r_chunks[i];
+            auto enqueue = [&]() -> int {
+                NTL_TRY(sketch_device(c, chunk_seq(ch), chunk_off(ch), ch.count, ch.nbases, (uint32_t)prm->k, (uint32_t)prm->w, c->dsk, call));
+                NTL_TRY(read_len_device(c, chunk_off(ch), ch.count, R->read_len));
+                NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), ch.count, first_read_ordinal + ch.first, prm, nullptr, nullptr, nullptr, call));
+                NTL_TRY(call_chunk_finish(c, call, ch.first, ch.count, nullptr));
+                return NTL_OK;
+            };
+            bool launched = false;
+            if (c->graph_mode) {
+                NTL_TRY(call_reserve_events(c, ch.count));
+                cudaGraph_t graph = nullptr;
+                NTL_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+                c->capturing = true;
+                const int rc = enqueue();
+                c->capturing = false; c->no_stage_timing = false;
+                cudaError_t ge = cudaStreamEndCapture(c->stream, &graph);
+                if (rc != NTL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ge == cudaSuccess && inject_graph_failure("resident")) ge = cudaErrorUnknown;
+                cudaGraphExec_t& exec = R->resident_execs[i];
+                if (ge == cudaSuccess && exec) {
+                    cudaGraphExecUpdateResultInfo info;
+                    if (cudaGraphExecUpdate(exec, graph, &info) != cudaSuccess) {
+                        cudaGetLastError();
+                        cudaGraphExecDestroy(exec);
+                        exec = nullptr;
+                    }
                 }
+                if (ge == cudaSuccess && !exec) {
+                    ge = cudaGraphInstantiate(&exec, graph, 0);
+                    if (ge != cudaSuccess) exec = nullptr;
+                }
+                if (graph) cudaGraphDestroy(graph);
+                if (ge == cudaSuccess) ge = cudaGraphLaunch(exec, c->stream);
+                if (ge == cudaSuccess) { c->n_graph_launches++; launched = true; }
+                else graph_failed(c, "graph step of ntl_map_resident", ge);        // plain launches below
             }
-            if (ge == cudaSuccess && !R->resident_exec) {
-                ge = cudaGraphInstantiate(&R->resident_exec, graph, 0);
-                if (ge != cudaSuccess) R->resident_exec = nullptr;
-            }
-            if (graph) cudaGraphDestroy(graph);
-            if (ge == cudaSuccess) ge = cudaGraphLaunch(R->resident_exec, c->stream);
-            if (ge == cudaSuccess) { c->n_graph_launches++; launched = true; }
-            else graph_failed(c, "graph step of ntl_map_resident", ge);        // plain launches below
+            if (!launched) NTL_TRY(enqueue());
         }
-        if (!launched) NTL_TRY(enqueue());
+        tock(c, T_TOTAL);
         CallState hs;
         NTL_TRY(call_end(c, call, &hs));
         collect_timing(c);
         c->n_async_calls++;
         if (hs.err) c->n_async_fallbacks++;
         if (hs.err == 0) {
-            c->dsk.n_mx = hs.mx_total;
+            c->dsk.n_mx = nch == 1 ? hs.mx_total : 0;
+            note_mx_density(c, hs.mx_total, R->r_bases, (uint32_t)prm->w);
             if (counts) {
                 memset(counts, 0, sizeof *counts);
                 counts->n_reads = R->r_nreads; counts->n_mx = hs.mx_total; counts->n_hits = hs.hits_total; counts->n_runs = hs.runs_total;
@@ -1124,18 +1170,21 @@ int ntl_map_resident(ntl_ctx* c, uint64_t first_read_ordinal, const ntl_params* 
             return NTL_OK;
         }
     }
-    tick(c, T_TOTAL);
-    NTL_TRY(sketch_device(c, R->r_seq.as<uint8_t>(), R->r_off.as<uint64_t>(), R->r_nreads, R->r_bases, (uint32_t)prm->k,
-                          (uint32_t)prm->w, c->dsk));
-    NTL_TRY(read_len_device(c, R->r_off.as<uint64_t>(), R->r_nreads, R->read_len));
-    MapStatus cs; uint64_t log_base = 0;
-    NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), R->r_nreads, first_read_ordinal, prm, &cs, &log_base));
-    tock(c, T_TOTAL);
-    NTL_TRY(finish_call(c));
+    uint64_t mx = 0, hits = 0, runs = 0, events = 0;
+    for (size_t i = 0; i < nch; i++) {
+        const Results::ResChunk& ch = R->r_chunks[i];
+        tick(c, T_TOTAL);
+        NTL_TRY(sketch_device(c, chunk_seq(ch), chunk_off(ch), ch.count, ch.nbases, (uint32_t)prm->k, (uint32_t)prm->w, c->dsk));
+        NTL_TRY(read_len_device(c, chunk_off(ch), ch.count, R->read_len));
+        MapStatus cs; uint64_t log_base = 0;
+        NTL_TRY(map_device(c, c->dsk, R->read_len.as<uint32_t>(), ch.count, first_read_ordinal + ch.first, prm, &cs, &log_base));
+        tock(c, T_TOTAL);
+        NTL_TRY(finish_call(c));
+        mx += c->dsk.n_mx; hits += cs.n_hits; runs += cs.n_runs; events += cs.n_events;
+    }
     if (counts) {
         memset(counts, 0, sizeof *counts);
-        counts->n_reads = R->r_nreads; counts->n_mx = c->dsk.n_mx; counts->n_hits = cs.n_hits; counts->n_runs = cs.n_runs;
-        counts->n_events = cs.n_events;
+        counts->n_reads = R->r_nreads; counts->n_mx = mx; counts->n_hits = hits; counts->n_runs = runs; counts->n_events = events;
     }
     return NTL_OK;
 }
@@ -1175,6 +1224,53 @@ int ntl_index_build_resident(ntl_ctx* c, int k, int w) {
     NTL_TRY(index_build_device(c, c->dsk.hash.as<uint64_t>(), R->t_ctg.as<uint32_t>(), c->dsk.posf.as<uint32_t>(), c->dsk.n_mx,
                                R->t_len.data(), R->t_rank.data(), R->t_ncontig));
     return finish_call(c);
+}
+
+static __global__ void k_add_u32(uint32_t* p, uint32_t v, const uint32_t* n_dev, uint32_t n_bound) {
+    const uint32_t n = n_dev ? min(*n_dev, n_bound) : n_bound;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] += v;
+}
+
+// Multi-GPU: sketch contigs [first, first + count) of the resident target; the minimizer triples stay on the device
+// (hash, GLOBAL contig id, pos|strand) for the caller's all-gather (ntlink_b200/dist.py). Synchronous.
+int ntl_target_sketch_resident(ntl_ctx* c, uint32_t first, uint32_t count, int k, int w, uint64_t* n_mx, void** d_hash, void** d_contig,
+                               void** d_pos_strand) {
+    if (!c || k <= 0 || w <= 0) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    if ((uint64_t)first + count > R->t_ncontig) { c->err = "ntl_target_sketch_resident: contig range"; return NTL_ERR_ARG; }
+    uint64_t a = 0, nb = 0;
+    for (uint32_t i = 0; i < first; i++) a += R->t_len[i];
+    std::vector<uint64_t> ho((size_t)count + 1, 0);
+    for (uint32_t i = 0; i < count; i++) ho[i + 1] = ho[i] + R->t_len[first + i];
+    nb = ho[count];
+    // the shard starts at an arbitrary base: the sketch kernels want a 16-byte aligned batch, so the shard is staged
+    NTL_CUDA(c, c->d_seq.ensure(nb + 256));
+    NTL_CUDA(c, c->d_off.ensure(((size_t)count + 1) * 8));
+    if (nb) NTL_CUDA(c, cudaMemcpyAsync(c->d_seq.p, R->t_seq.as<char>() + a, nb, cudaMemcpyDeviceToDevice, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(c->d_off.p, ho.data(), ((size_t)count + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    NTL_TRY(sketch_device(c, c->d_seq.as<uint8_t>(), c->d_off.as<uint64_t>(), count, nb, (uint32_t)k, (uint32_t)w, c->dsk));
+    NTL_TRY(expand_contig_ids(c, c->dsk, R->ctg_ids));
+    if (c->dsk.n_mx && first) {
+        k_add_u32<<<std::min<uint32_t>((c->dsk.n_mx + 255) / 256, 148 * 8), 256, 0, c->stream>>>(R->ctg_ids.as<uint32_t>(), first, nullptr, c->dsk.n_mx);
+        c->launches++;
+    }
+    NTL_TRY(finish_call(c));
+    if (n_mx) *n_mx = c->dsk.n_mx;
+    if (d_hash) *d_hash = c->dsk.hash.p;
+    if (d_contig) *d_contig = R->ctg_ids.p;
+    if (d_pos_strand) *d_pos_strand = c->dsk.posf.p;
+    return NTL_OK;
+}
+
+// contig lengths / name ranks of the resident target (the arguments ntl_index_build_device needs)
+int ntl_target_resident_meta(ntl_ctx* c, uint32_t* contig_len, uint32_t* name_rank) {
+    if (!c) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    if (contig_len) memcpy(contig_len, R->t_len.data(), (size_t)R->t_ncontig * 4);
+    if (name_rank) memcpy(name_rank, R->t_rank.data(), (size_t)R->t_ncontig * 4);
+    return NTL_OK;
 }
 
 int ntl_timing_reset(ntl_ctx* c) {
@@ -1234,6 +1330,162 @@ int ntl_device_sync(ntl_ctx* c) {
     if (!c) return NTL_ERR_ARG;
     cudaSetDevice(c->device);
     NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NTL_OK;
+}
+
+// ------------------------------------------------------------------------------------------- synthetic inputs
+// Benchmark / test inputs only: the same counter-based generator on the device (resident target and
+// reads, no host copy of multi-Gbp inputs) and on the host (tests, the CPU reference arm).
+static_assert(sizeof(ntl_synth_contig) == sizeof(SynthContig) && sizeof(ntl_synth_read) == sizeof(SynthRead), "synth record layout");
+
+int ntl_synth_target_resident(ntl_ctx* c, uint64_t seed, const ntl_synth_contig* contigs, uint32_t ncontig, const uint32_t* name_rank) {
+    if (!c || !contigs || !ncontig || !name_rank) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    std::vector<uint64_t> ho((size_t)ncontig + 1, 0);
+    R->t_len.resize(ncontig); R->t_rank.assign(name_rank, name_rank + ncontig);
+    for (uint32_t i = 0; i < ncontig; i++) { R->t_len[i] = contigs[i].len; ho[i + 1] = ho[i] + contigs[i].len; }
+    const uint64_t nb = ho[ncontig];
+    if (nb >= (1ull << 32) - 4096) { c->err = "resident target exceeds 4 Gbp"; return NTL_ERR_ARG; }
+    DevBuf d_ctg;
+    NTL_CUDA(c, d_ctg.ensure((size_t)ncontig * sizeof(SynthContig)));
+    NTL_CUDA(c, R->t_seq.ensure(nb + 256));
+    NTL_CUDA(c, R->t_off.ensure(((size_t)ncontig + 1) * 8));
+    NTL_CUDA(c, cudaMemcpyAsync(d_ctg.p, contigs, (size_t)ncontig * sizeof(SynthContig), cudaMemcpyHostToDevice, c->stream));
+    NTL_CUDA(c, cudaMemcpyAsync(R->t_off.p, ho.data(), ((size_t)ncontig + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    k_synth_contigs<<<dim3(32, std::min<uint32_t>(ncontig, 4096)), 256, 0, c->stream>>>(seed, d_ctg.as<SynthContig>(), R->t_off.as<uint64_t>(), ncontig,
+                                                                                      R->t_seq.as<uint8_t>());
+    NTL_CUDA(c, cudaGetLastError());
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    d_ctg.release();
+    R->t_ncontig = ncontig; R->t_bases = nb;
+    return NTL_OK;
+}
+
+int ntl_synth_reads_resident(ntl_ctx* c, uint64_t seed, const ntl_synth_read* reads, uint32_t nreads, uint32_t sub16, uint32_t del16,
+                             uint32_t ins16, uint64_t* total_bases) {
+    if (!c || !reads || !nreads || sub16 + del16 + ins16 > 65536u) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    const SynthErr e{sub16, del16, ins16};
+    DevBuf d_rd, d_len, d_abs;
+    NTL_CUDA(c, d_rd.ensure((size_t)nreads * sizeof(SynthRead)));
+    NTL_CUDA(c, d_len.ensure((size_t)nreads * 4));
+    NTL_CUDA(c, cudaMemcpyAsync(d_rd.p, reads, (size_t)nreads * sizeof(SynthRead), cudaMemcpyHostToDevice, c->stream));
+    const uint32_t blocks = (uint32_t)(((uint64_t)nreads * 32 + 255) / 256);
+    k_synth_read_len<<<blocks, 256, 0, c->stream>>>(seed, d_rd.as<SynthRead>(), nreads, e, d_len.as<uint32_t>());
+    std::vector<uint32_t> len(nreads);
+    NTL_CUDA(c, cudaMemcpyAsync(len.data(), d_len.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    R->r_abs_off.assign((size_t)nreads + 1, 0);
+    for (uint32_t i = 0; i < nreads; i++) R->r_abs_off[i + 1] = R->r_abs_off[i] + len[i];
+    NTL_TRY(plan_resident_chunks(c, nreads));
+    // destination of every read inside the chunked device buffer
+    std::vector<uint64_t> dst((size_t)nreads);
+    for (const Results::ResChunk& ch : R->r_chunks)
+        for (uint32_t r = ch.first; r < ch.first + ch.count; r++) dst[r] = ch.dev_base + (R->r_abs_off[r] - R->r_abs_off[ch.first]);
+    NTL_CUDA(c, d_abs.ensure((size_t)nreads * 8));
+    NTL_CUDA(c, cudaMemcpyAsync(d_abs.p, dst.data(), (size_t)nreads * 8, cudaMemcpyHostToDevice, c->stream));
+    k_synth_reads<<<blocks, 256, 0, c->stream>>>(seed, d_rd.as<SynthRead>(), d_abs.as<uint64_t>(), nreads, e, R->r_seq.as<uint8_t>());
+    NTL_CUDA(c, cudaGetLastError());
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    d_rd.release(); d_len.release(); d_abs.release();
+    if (total_bases) *total_bases = R->r_bases;
+    return NTL_OK;
+}
+
+int ntl_resident_info(ntl_ctx* c, int which, uint32_t* nseq, uint64_t* nbases) {
+    if (!c) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    if (nseq) *nseq = which ? R->r_nreads : R->t_ncontig;
+    if (nbases) *nbases = which ? R->r_bases : R->t_bases;
+    return NTL_OK;
+}
+
+int ntl_resident_download(ntl_ctx* c, int which, uint32_t first, uint32_t count, char* seq_out, uint64_t* off_out) {
+    if (!c || !off_out) return NTL_ERR_ARG;
+    Results* R = res_of(c);
+    cudaSetDevice(c->device);
+    if (which == 0) {
+        if ((uint64_t)first + count > R->t_ncontig) { c->err = "ntl_resident_download: range"; return NTL_ERR_ARG; }
+        uint64_t a = 0;
+        for (uint32_t i = 0; i < first; i++) a += R->t_len[i];
+        off_out[0] = 0;
+        for (uint32_t i = 0; i < count; i++) off_out[i + 1] = off_out[i] + R->t_len[first + i];
+        if (seq_out && off_out[count]) NTL_CUDA(c, cudaMemcpyAsync(seq_out, R->t_seq.as<char>() + a, off_out[count], cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        if ((uint64_t)first + count > R->r_nreads) { c->err = "ntl_resident_download: range"; return NTL_ERR_ARG; }
+        const std::vector<uint64_t>& ao = R->r_abs_off;
+        for (uint32_t i = 0; i <= count; i++) off_out[i] = ao[first + i] - ao[first];
+        if (seq_out)
+            for (const Results::ResChunk& ch : R->r_chunks) {
+                const uint32_t a = std::max(first, ch.first), b = std::min(first + count, ch.first + ch.count);
+                if (a >= b) continue;
+                NTL_CUDA(c, cudaMemcpyAsync(seq_out + (ao[a] - ao[first]), R->r_seq.as<char>() + ch.dev_base + (ao[a] - ao[ch.first]), ao[b] - ao[a],
+                                            cudaMemcpyDeviceToHost, c->stream));
+            }
+    }
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NTL_OK;
+}
+
+static void run_threads(int threads, uint32_t n, const std::function<void(uint32_t, uint32_t)>& fn) {
+    threads = std::max(1, std::min<int>(threads, (int)std::max<uint32_t>(1, n / 64)));
+    std::vector<std::thread> th;
+    const uint32_t per = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        const uint32_t a = std::min<uint64_t>(n, (uint64_t)t * per), b = std::min<uint64_t>(n, (uint64_t)a + per);
+        if (a < b) th.emplace_back(fn, a, b);
+    }
+    for (auto& x : th) x.join();
+}
+
+int ntl_synth_host_contigs(uint64_t seed, const ntl_synth_contig* contigs, uint32_t ncontig, uint64_t* off_out, char* seq_out, int threads) {
+    if (!contigs || !off_out) return NTL_ERR_ARG;
+    off_out[0] = 0;
+    for (uint32_t i = 0; i < ncontig; i++) off_out[i + 1] = off_out[i] + contigs[i].len;
+    if (!seq_out) return NTL_OK;
+    const SynthContig* sc = reinterpret_cast<const SynthContig*>(contigs);
+    run_threads(threads, ncontig, [&](uint32_t a, uint32_t b) {
+        for (uint32_t i = a; i < b; i++) {
+            uint8_t* dst = reinterpret_cast<uint8_t*>(seq_out) + off_out[i];
+            for (uint32_t j = 0; j < sc[i].len; j++) dst[j] = contig_base(seed, sc[i], j);
+        }
+    });
+    return NTL_OK;
+}
+
+int ntl_synth_host_reads(uint64_t seed, const ntl_synth_read* reads, uint32_t nreads, uint32_t sub16, uint32_t del16, uint32_t ins16,
+                         uint64_t* off_out, char* seq_out, int threads) {
+    if (!reads || !off_out || sub16 + del16 + ins16 > 65536u) return NTL_ERR_ARG;
+    const SynthErr e{sub16, del16, ins16};
+    const SynthRead* sr = reinterpret_cast<const SynthRead*>(reads);
+    if (!seq_out) {                     // first call: lengths -> offsets
+        std::vector<uint32_t> len(nreads);
+        run_threads(threads, nreads, [&](uint32_t a, uint32_t b) {
+            for (uint32_t i = a; i < b; i++) {
+                const uint64_t key = read_key(seed, sr[i].id);
+                uint32_t n = 0;
+                for (uint32_t j = 0; j < sr[i].len; j++) n += read_emit_count(key, j, e);
+                len[i] = n;
+            }
+        });
+        off_out[0] = 0;
+        for (uint32_t i = 0; i < nreads; i++) off_out[i + 1] = off_out[i] + len[i];
+        return NTL_OK;
+    }
+    run_threads(threads, nreads, [&](uint32_t a, uint32_t b) {
+        for (uint32_t i = a; i < b; i++) {
+            const uint64_t key = read_key(seed, sr[i].id);
+            uint8_t* p = reinterpret_cast<uint8_t*>(seq_out) + off_out[i];
+            for (uint32_t j = 0; j < sr[i].len; j++) {
+                uint8_t o[2];
+                const uint32_t m = read_emit(seed, key, sr[i], j, e, o);
+                if (m) *p++ = o[0];
+                if (m == 2) *p++ = o[1];
+            }
+        }
+    });
     return NTL_OK;
 }
 

@@ -153,14 +153,16 @@ struct ntl_ctx {
     uint64_t batch_bases = 1ull << 30;
     uint64_t pipeline_min_bases = 80ull << 20;   // smallest batch worth pipelining (copy/compute overlap)
     // timing
-    cudaEvent_t ev[2 * ntl::T_NUM];
+    struct StageRec { int stage; uint32_t ev; bool closed; uint64_t bases; };
+    std::vector<cudaEvent_t> ev_pool;      // stage-timer events, two per record, recycled by collect_timing
+    std::vector<StageRec> ev_recs;
+    size_t ev_next = 0;
+    int ev_open[ntl::T_NUM];
     cudaEvent_t mark[2];
-    bool ev_used[ntl::T_NUM];
     double ms_accum[ntl::T_NUM];           // accumulated since ntl_timing_reset
     uint64_t launches = 0;                 // kernels launched since ntl_timing_reset
     uint64_t dense_launches = 0;
     uint64_t dense_bases = 0;
-    uint64_t last_dense_bases = 0;         // size of the most recent k_dense launch
     double big_dense_ms = 0;               // k_dense launches over >= 16 Mbp only (read batches)
     uint64_t big_dense_launches = 0, big_dense_bases = 0;
     // tally state (pairs accumulated over calls)
@@ -230,8 +232,10 @@ static __global__ void k_fill_segs(FillSegs s) {
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n[q]; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint8_t)s.v[q];
     }
 }
-// inside a stream capture the records become event-record nodes of the graph (cudaEventRecordExternal), so the stage
-// times of a graph launch can be read like those of plain launches
+// Stage timers: every tick/tock pair takes its own pair of CUDA events from a pool that is recycled by collect_timing, so
+// that a call made of several chunks (each with the same stages, several of them in flight) still yields every stage's
+// device time. Inside a stream capture the records become event-record nodes of the graph (cudaEventRecordExternal), so
+// the stage times of a graph launch can be read like those of plain launches.
 inline void note_mx_density(ntl_ctx* c, uint64_t n_mx, uint64_t bases, uint32_t w) {
     if (bases < 100000) return;                                   // too small to say anything
     const double seen = (double)n_mx * ((double)w + 1.0) / (double)bases;
@@ -239,25 +243,41 @@ inline void note_mx_density(ntl_ctx* c, uint64_t n_mx, uint64_t bases, uint32_t 
 }
 inline void tick(ntl_ctx* c, int stage) {
     if (c->no_stage_timing) return;
-    cudaEventRecordWithFlags(c->ev[2 * stage], c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+    if (c->ev_next + 2 > c->ev_pool.size()) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        c->ev_pool.push_back(a); c->ev_pool.push_back(b);
+    }
+    ntl_ctx::StageRec r;
+    r.stage = stage; r.ev = (uint32_t)c->ev_next; r.closed = false; r.bases = 0;
+    c->ev_next += 2;
+    c->ev_open[stage] = (int)c->ev_recs.size();
+    c->ev_recs.push_back(r);
+    cudaEventRecordWithFlags(c->ev_pool[r.ev], c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
-inline void tock(ntl_ctx* c, int stage) {
+inline void tock(ntl_ctx* c, int stage, uint64_t bases = 0) {
     if (c->no_stage_timing) return;
-    cudaEventRecordWithFlags(c->ev[2 * stage + 1], c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
-    c->ev_used[stage] = true;
+    const int i = c->ev_open[stage];
+    if (i < 0 || (size_t)i >= c->ev_recs.size()) return;
+    ntl_ctx::StageRec& r = c->ev_recs[(size_t)i];
+    cudaEventRecordWithFlags(c->ev_pool[r.ev + 1], c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+    r.closed = true; r.bases = bases;
+    c->ev_open[stage] = -1;
 }
 // after a stream synchronize: fold the recorded stage times into the accumulators
 inline void collect_timing(ntl_ctx* c) {
-    for (int s = 0; s < T_NUM; s++) {
-        if (!c->ev_used[s]) continue;
+    for (const ntl_ctx::StageRec& r : c->ev_recs) {
+        if (!r.closed) continue;
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->ev[2 * s], c->ev[2 * s + 1]) == cudaSuccess) {
-            c->ms_accum[s] += ms;
-            if (s == T_DENSE && c->last_dense_bases >= (16ull << 20)) {
-                c->big_dense_ms += ms; c->big_dense_launches += 1; c->big_dense_bases += c->last_dense_bases;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[r.ev], c->ev_pool[r.ev + 1]) == cudaSuccess) {
+            c->ms_accum[r.stage] += ms;
+            if (r.stage == T_DENSE && r.bases >= (16ull << 20)) {
+                c->big_dense_ms += ms; c->big_dense_launches += 1; c->big_dense_bases += r.bases;
             }
-        }
-        c->ev_used[s] = false;
+        } else cudaGetLastError();
     }
+    c->ev_recs.clear();
+    c->ev_next = 0;
+    for (int s = 0; s < T_NUM; s++) c->ev_open[s] = -1;
 }
 }  // namespace ntl

@@ -590,8 +590,8 @@ retry:
     k_dense<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,
                                                             W.tbl.as<RollEntry>(), W.slots.as<Cand>(), W.cnt.as<uint32_t>(),
                                                             W.nv.as<uint32_t>(), W.has_cand.as<uint8_t>(), st);
-    tock(c, T_DENSE);
-    c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases; c->last_dense_bases = total_bases;
+    tock(c, T_DENSE, total_bases);
+    c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases;
 
     tick(c, T_SELECT);
     k_overflow<<<div_up(nstrips_max, 128), 128, 0, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,

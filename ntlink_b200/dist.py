@@ -90,3 +90,127 @@ class EventGather:
                 return [r[1:1 + c] for r, c in zip(self.recv, counts)]
             self.cap = int(max(counts) * 2)
             self.send = None
+
+
+class GpuExchange:
+    """The two exchange steps on GPUs, driving the library through its C ABI (ctx = ntlink_b200.Context of this rank):
+
+      build_index_sharded*   every rank sketches its contig shard of the target (by cumulative length), the minimizer
+                             triples are all-gathered over NCCL, every GPU builds the same replicated index;
+      gather_events          pair events of every rank -> rank 0's device event log in rank order = global read order,
+                             ONE fixed-capacity all_gather_into_tensor. After agree_capacity() the exchange runs without
+                             any host synchronisation (export kernel -> collective -> import kernel; streams ordered by
+                             events, per-rank counts interpreted on the device); before it the counts are read on the host
+                             and the buffers grow as needed.
+    """
+
+    def __init__(self, ctx, dist, rank, world, device=None):
+        self.ctx, self.dist, self.rank, self.world = ctx, dist, rank, world
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.cap, self.send, self.recv, self.agreed, self.stream = 8192, None, None, False, None
+        self.index_bytes = 0
+
+    # ---- replicated index
+    def _build_from_shard(self, n_mx, dh, dc, dp, contig_len, name_rank):
+        import ctypes as C
+        ctx = self.ctx
+        m = int(n_mx)
+        h = torch.empty(m, device=self.dev, dtype=torch.int64)
+        ctg = torch.empty(m, device=self.dev, dtype=torch.int32)
+        posf = torch.empty(m, device=self.dev, dtype=torch.int32)
+        if m:
+            ctx._check(ctx.lib.ntl_copy_device(ctx.h, h.data_ptr(), dh, m * 8), "copy")
+            ctx._check(ctx.lib.ntl_copy_device(ctx.h, ctg.data_ptr(), dc, m * 4), "copy")
+            ctx._check(ctx.lib.ntl_copy_device(ctx.h, posf.data_ptr(), dp, m * 4), "copy")
+        hashes, ctgs, posfs = gather_triples(h, ctg, posf, self.dist)
+        torch.cuda.synchronize()
+        self.index_bytes = int(hashes.numel()) * 16
+        ctx._check(ctx.lib.ntl_index_build_device(ctx.h, hashes.data_ptr(), ctgs.data_ptr(), posfs.data_ptr(), int(hashes.numel()),
+                                                  contig_len.ctypes.data, name_rank.ctypes.data, len(contig_len)), "ntl_index_build_device")
+        return int(hashes.numel())
+
+    def build_index_sharded_resident(self, k, w):
+        "target = the context's resident target (ntl_target_upload / ntl_synth_target_resident)"
+        import ctypes as C
+        ctx = self.ctx
+        ncontig, _ = ctx.resident_info(0)
+        cl = np.empty(ncontig, np.uint32)
+        rk = np.empty(ncontig, np.uint32)
+        ctx._check(ctx.lib.ntl_target_resident_meta(ctx.h, cl.ctypes.data, rk.ctypes.data), "ntl_target_resident_meta")
+        off = np.zeros(ncontig + 1, np.int64)
+        off[1:] = np.cumsum(cl.astype(np.int64))
+        a, b = contig_shard(off, self.rank, self.world)
+        n, dh, dc, dp = C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx._check(ctx.lib.ntl_target_sketch_resident(ctx.h, a, b - a, k, w, C.byref(n), C.byref(dh), C.byref(dc), C.byref(dp)),
+                   "ntl_target_sketch_resident")
+        return self._build_from_shard(n.value, dh, dc, dp, cl, rk)
+
+    def build_index_sharded(self, contigs, k, w):
+        "target = a host SeqBatch (every rank holds it; each one copies and sketches only its shard)"
+        import ctypes as C
+        from .api import SeqBatch, name_ranks
+        ctx = self.ctx
+        cum = contigs.offsets.astype(np.int64)
+        a, b = contig_shard(contigs.offsets, self.rank, self.world)
+        part = SeqBatch(contigs.seq[int(cum[a]):int(cum[b])], contigs.offsets[a:b + 1] - contigs.offsets[a], contigs.names[a:b])
+        sk = ctx.sketch(part, k, w)            # the triples also stay on the device; the host copy gives the contig ids
+        m = len(sk.hash)
+        nmx, dh, dp, do = C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx._check(ctx.lib.ntl_device_sketch_arrays(ctx.h, C.byref(nmx), C.byref(dh), C.byref(dp), C.byref(do)), "arrays")
+        ctg = torch.from_numpy(np.repeat(np.arange(a, b, dtype=np.int32), np.diff(sk.seq_off).astype(np.int64))).to(self.dev)
+        return self._build_from_shard(m, dh, ctg.data_ptr(), dp, contigs.lengths.astype(np.uint32), name_ranks(contigs.names))
+
+    # ---- pair events
+    def _buffers(self):
+        if self.send is None or self.send.shape[0] != (self.cap + 1) * 6:
+            self.send = torch.zeros((self.cap + 1) * 6, device=self.dev, dtype=torch.int32)
+            self.recv = torch.zeros(self.world * (self.cap + 1) * 6, device=self.dev, dtype=torch.int32)
+
+    def _gather_sync(self):
+        import ctypes as C
+        ctx = self.ctx
+        while True:
+            self._buffers()
+            n = C.c_uint64()
+            ctx._check(ctx.lib.ntl_events_export(ctx.h, self.send.data_ptr(), self.cap, C.byref(n)), "ntl_events_export")
+            self.dist.all_gather_into_tensor(self.recv, self.send)
+            counts = self.recv.view(self.world, -1)[:, 0].tolist()
+            if max(counts) <= self.cap:
+                if self.rank == 0:
+                    ovf = C.c_int(0)
+                    ctx._check(ctx.lib.ntl_events_import_gathered(ctx.h, self.recv.data_ptr(), self.world, self.cap, C.byref(ovf)),
+                               "ntl_events_import_gathered")
+                return
+            self.cap = int(max(counts)) * 2
+            self.send = None
+
+    def gather_events(self, force_sync=False):
+        import ctypes as C
+        ctx = self.ctx
+        if force_sync or not self.agreed:
+            self._gather_sync()
+            return
+        if self.stream is None:
+            sp = C.c_void_p()
+            ctx._check(ctx.lib.ntl_stream(ctx.h, C.byref(sp)), "ntl_stream")
+            self.stream = torch.cuda.ExternalStream(sp.value, device=self.dev)
+        n = C.c_uint64()
+        ctx._check(ctx.lib.ntl_events_export_async(ctx.h, self.send.data_ptr(), self.cap, C.byref(n)), "ntl_events_export_async")
+        if n.value > self.cap:
+            raise RuntimeError("event exchange buffer too small for this step; run more warm-up steps")
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self.dist.all_gather_into_tensor(self.recv, self.send)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        if self.rank == 0:
+            ctx._check(ctx.lib.ntl_events_import_device(ctx.h, self.recv.data_ptr(), self.world, self.cap), "ntl_events_import_device")
+
+    def agree_capacity(self):
+        "after some synchronous exchanges: every rank takes the same capacity (4x the largest count seen, >= 8192 events)"
+        seen = int(self.recv.view(self.world, -1)[:, 0].max().item()) if self.recv is not None else 0
+        t = torch.tensor([seen], device=self.dev, dtype=torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        self.cap = max(8192, 4 * int(t.item()))
+        self.send = None
+        self._buffers()
+        torch.cuda.synchronize()
+        self.agreed = True
