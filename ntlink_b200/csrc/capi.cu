@@ -205,7 +205,7 @@ void ntl_destroy(ntl_ctx* c) {
     Results* R = res_of(c);
     SketchWork& W = c->sw;
     DevBuf* sb[] = {&W.packed, &W.scnt, &W.strip_off, &W.blocksums, &W.slots, &W.cnt, &W.nv, &W.vbase, &W.ovf_off, &W.sel,
-                    &W.selcnt, &W.selmask, &W.selbase, &W.strip_seq, &W.gaps, &W.gap_head, &W.extras, &W.has_cand, &W.status, &W.tbl};
+                    &W.selcnt, &W.selmask, &W.selbase, &W.strip_seq, &W.gaps, &W.gap_head, &W.extras, &W.has_cand, &W.status, &W.tbl, &W.tile_state, &W.stage_hash, &W.stage_posf};
     for (DevBuf* b : sb) b->release();
     MapWork& M = c->mw;
     DevBuf* mb[] = {&M.hit_tmp, &M.hit_flag, &M.hit_pref, &M.hits, &M.runs, &M.mark, &M.hit_off, &M.nruns, &M.events,
@@ -261,6 +261,8 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
         c->async_mode = value != 0.0;
     } else if (!strcmp(name, "copy_threads")) {
         c->copy_threads = (int)value;
+    } else if (!strcmp(name, "tile")) {
+        c->tile_mode = value != 0.0;
     } else if (!strcmp(name, "graph")) {
         c->graph_mode = value != 0.0;
     } else if (!strcmp(name, "pipeline_min_bases")) {
@@ -1301,6 +1303,8 @@ int ntl_get_stat(ntl_ctx* c, const char* name, double* value) {
     else if (!strcmp(name, "async_fallbacks")) *value = (double)c->n_async_fallbacks;
     else if (!strcmp(name, "graph_launches")) *value = (double)c->n_graph_launches;
     else if (!strcmp(name, "graph_failures")) *value = (double)c->n_graph_failures;
+    else if (!strcmp(name, "tile_batches")) *value = (double)c->n_tile_batches;
+    else if (!strcmp(name, "tile_fallbacks")) *value = (double)c->n_tile_fallbacks;
     else { c->err = std::string("unknown stat ") + name; return NTL_ERR_ARG; }
     return NTL_OK;
 }

@@ -77,7 +77,7 @@ enum { T_PACK = NTL_T_PACK, T_DENSE = NTL_T_DENSE, T_SELECT = NTL_T_SELECT, T_GA
 
 struct SketchWork {           // device workspace of the sketch pipeline (reused across calls)
     DevBuf packed, scnt, strip_off, blocksums, slots, cnt, nv, vbase, ovf_off, sel, selcnt, selmask, selbase, strip_seq,
-        gaps, gap_head, extras, has_cand, status, tbl;
+        gaps, gap_head, extras, has_cand, status, tbl, tile_state, stage_hash, stage_posf;
     uint32_t tbl_k = 0;       // k the device roll table was built for
 };
 
@@ -178,6 +178,8 @@ struct ntl_ctx {
     uint64_t n_async_calls = 0, n_async_fallbacks = 0, n_graph_launches = 0, n_graph_failures = 0;   // ntl_get_stat
     double mx_density_factor = 2.6;        // minimizers per base * (w + 1), upper estimate (see sketch_out_bound)
     int copy_threads = -1;                 // host threads of the pageable->pinned bounce copy (-1 auto, 0 = off)
+    uint64_t n_tile_batches = 0, n_tile_fallbacks = 0;   // ntl_get_stat "tile_batches" / "tile_fallbacks"
+    int tile_mode = 1;                     // single-pass sketch kernel (tile_kernel.cuh) where the window size allows (option "tile")
     int graph_mode = 1;                    // sync-free ntl_map_reads: one CUDA graph per chunk (option "graph")
     bool capturing = false;                // c->stream is being captured: no synchronisation, no allocation-by-copy
     bool no_stage_timing = false;          // chunk graphs of a pipelined call: several in flight, stage events meaningless

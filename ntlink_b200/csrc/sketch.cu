@@ -395,6 +395,7 @@ __global__ void k_seq_gaps(const uint64_t* __restrict__ seq_off, const uint32_t*
 }  // namespace
 }  // namespace ntl
 #include "gap_kernel.cuh"      // k_gap (one warp per candidate-free stretch)
+#include "tile_kernel.cuh"     // k_tile (the single-pass sketch for w >= 13)
 namespace ntl {
 namespace {
 
@@ -482,7 +483,7 @@ __global__ void k_publish_sketch(const SketchStatus* __restrict__ st, const uint
                                  const uint32_t* __restrict__ selbase, uint32_t* __restrict__ host) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(st);
     if (threadIdx.x < sizeof(SketchStatus) / 4) host[threadIdx.x] = src[threadIdx.x];
-    if (threadIdx.x == 0) { const uint32_t ns = *nstrips_p; host[16] = ns; host[17] = selbase[ns]; }
+    if (threadIdx.x == 0) { const uint32_t ns = *nstrips_p; host[16] = ns; host[17] = selbase ? selbase[ns] : st->n_mx; }
     __threadfence_system();
 }
 
@@ -507,6 +508,139 @@ int sketch_prepare(ntl_ctx* c, uint32_t k) {
     return NTL_OK;
 }
 
+// Shape of the single-pass path for a window size: strip length S (largest of 256 / 128 / 64 whose expected number of
+// candidates per strip fits a slot row), slot row capacity (odd: conflict-free shared-memory rows), halo strips.
+struct TileShape { bool ok; uint32_t S, cap, H, flat_cap, shared_at; size_t smem; };
+static TileShape tile_shape(uint32_t k, uint32_t w, double cand_c) {
+    TileShape t{false, 0, 0, 0, 0};
+    if (w < 2 || k > 4096) return t;
+    for (uint32_t S : {256u, 128u, 64u}) {
+        const double mu = (double)S * cand_c / (double)w;
+        if (mu > 36.0) continue;
+        const uint32_t cap = 0;
+        const uint32_t H = (w - 1 + S - 1) / S;
+        if (H < 1 || 2 * H > TILE_THREADS / 2) continue;
+        t.ok = true; t.S = S; t.cap = cap; t.H = H;
+        const double view = TILE_THREADS * mu;
+        t.flat_cap = ((uint32_t)(view + 5.0 * sqrt(view) + 48.0) + 3u) & ~3u;     // pool and flat list: mean + 5 sigma, no per-strip slack
+        if (t.flat_cap > 16384 || S > 256) continue;
+        size_t at = (size_t)TILE_TBL_BYTES + (size_t)t.flat_cap * 12 + ((size_t)t.flat_cap + 2) * 6 + ((size_t)t.flat_cap + 2);
+        at = (at + 7) & ~(size_t)7;
+        at += std::max<size_t>(((size_t)t.flat_cap + 2 * TILE_KPAD) * 4, (size_t)TILE_GT * 9);     // select keys, later the exact-scan buffers
+        at = (at + 15) & ~(size_t)15;
+        t.shared_at = (uint32_t)at;
+        t.smem = at + sizeof(TileShared);
+        return t;
+    }
+    return t;
+}
+
+// The single-pass sketch (tile_kernel.cuh). Returns NTL_OK with *done = false when the batch has to take the multi-pass
+// path below (a tile ran out of exact-scan records).
+static int sketch_device_tile(ntl_ctx* c, const TileShape& shape, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
+                              uint32_t k, uint32_t w, DeviceSketch& out, CallState* call_state, bool* done) {
+    SketchWork& W = c->sw;
+    *done = false;
+    const uint32_t S = shape.S, NS = TILE_THREADS - 2 * shape.H;
+    const uint32_t nstrips_max = (uint32_t)(total_bases / S + nseq + 1);
+    const uint32_t ntiles_max = nstrips_max / NS + 1;
+    uint32_t extras_cap = (uint32_t)std::min<uint64_t>(0xFFFF0000ull, total_bases / 64 + 65536);
+    uint32_t out_cap = sketch_out_bound(total_bases, nseq, w, c->mx_density_factor);
+    static int smem_set = 0;
+    if (smem_set < (int)shape.smem) {
+        NTL_CUDA(c, cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        smem_set = 227 * 1024;
+    }
+    int attempt = 0;
+retry:
+    TileParams P;
+    P.k = k; P.w = w; P.S = S; P.cap = shape.cap; P.tau_hi = candidate_threshold(w, c->cand_c); P.nseq = nseq; P.H = shape.H;
+    P.mult = second_hash_multiplier(k); P.out_cap = out_cap; P.extras_cap = extras_cap; P.ntiles_max = ntiles_max;
+    P.flat_cap = shape.flat_cap; P.shared_at = shape.shared_at;
+    NTL_CUDA(c, W.packed.ensure(total_bases / 2 + 512));
+    NTL_CUDA(c, W.scnt.ensure(((size_t)nseq + 2) * 4));
+    NTL_CUDA(c, W.strip_off.ensure(((size_t)nseq + 2) * 4));
+    NTL_CUDA(c, W.strip_seq.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.extras.ensure((size_t)extras_cap * sizeof(Cand)));
+    // staging: every tile writes its minimizers to its own segment of tcap entries (what random sequence needs x the density
+    // head room of the output bound + 25 %); tile_state = counts [ntiles_max + 1] | bases [ntiles_max + 1]
+    const uint32_t tcap = (uint32_t)((double)NS * S * c->mx_density_factor / ((double)w + 1.0) * 1.25) + 64;
+    NTL_CUDA(c, W.tile_state.ensure(((size_t)ntiles_max + 2) * 8));
+    NTL_CUDA(c, W.stage_hash.ensure((size_t)ntiles_max * tcap * 8 + 8));
+    NTL_CUDA(c, W.stage_posf.ensure((size_t)ntiles_max * tcap * 4 + 4));
+    P.tcap = tcap;
+    uint32_t* tile_cnt = W.tile_state.as<uint32_t>();
+    uint32_t* tile_base = tile_cnt + ntiles_max + 1;
+    NTL_CUDA(c, W.status.ensure(sizeof(SketchStatus) + 64));
+    NTL_CUDA(c, c->h_status.ensure(256));
+    NTL_CUDA(c, out.hash.ensure((size_t)out_cap * 8 + 8));
+    NTL_CUDA(c, out.posf.ensure((size_t)out_cap * 4 + 4));
+    SketchStatus* st = W.status.as<SketchStatus>();
+    uint32_t* nseq_dev = (uint32_t*)((char*)W.status.p + sizeof(SketchStatus));
+    uint32_t* ticket = nseq_dev + 1;
+    NTL_TRY(sketch_prepare(c, k));
+    uint32_t* const d_packed = reinterpret_cast<uint32_t*>(W.packed.as<char>() + 64);
+    {
+        FillSegs fs{};
+        fs.p[0] = st; fs.n[0] = sizeof(SketchStatus) + 64; fs.v[0] = 0;
+        fs.p[1] = W.tile_state.p; fs.n[1] = ((size_t)ntiles_max + 2) * 8; fs.v[1] = 0;
+        fs.p[2] = W.packed.p; fs.n[2] = 64; fs.v[2] = 0x44;
+        fs.p[3] = W.packed.as<char>() + 64 + total_bases / 2; fs.n[3] = 192; fs.v[3] = 0x44;
+        k_fill_segs<<<std::max<uint32_t>(1, std::min<uint32_t>(div_up((uint64_t)ntiles_max * 8, 256), 148)), 256, 0, c->stream>>>(fs);
+        c->launches += 1;
+    }
+    tick(c, T_PACK);
+    k_pack<<<div_up(div_up(total_bases, 16), 256 * PACK_CHUNKS), 256, 0, c->stream>>>(d_seq, total_bases, d_packed);
+    k_strip_count<<<div_up(nseq, 256), 256, 0, c->stream>>>(d_off, nseq, k, w, S, W.scnt.as<uint32_t>(), nseq_dev);
+    c->launches += 2;
+    NTL_TRY(exclusive_scan_u32(c, W.scnt.as<uint32_t>(), W.strip_off.as<uint32_t>(), nseq_dev, nseq, W.blocksums));
+    k_strip_seq<<<div_up(nstrips_max, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), nseq, W.strip_seq.as<uint32_t>());
+    c->launches += 1;
+    tock(c, T_PACK);
+
+    tick(c, T_DENSE);
+    {
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile, TILE_THREADS, shape.smem);
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(ntiles_max, 148u * (uint32_t)std::max(per_sm, 1)));
+        k_tile<<<grid, TILE_THREADS, shape.smem, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,
+                                                              W.tbl.as<RollEntry>(), tile_cnt, ticket, W.extras.as<Cand>(),
+                                                              W.stage_hash.as<uint64_t>(), W.stage_posf.as<uint32_t>(), out.mx_off.as<uint32_t>(), st);
+    }
+    tock(c, T_DENSE, total_bases);
+    c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases;
+    tick(c, T_EMIT);
+    k_tile_scan<<<1, 1024, 0, c->stream>>>(W.strip_off.as<uint32_t>(), P, tile_cnt, tile_base, st);
+    k_tile_gather<<<std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(ntiles_max, div_up((uint64_t)nseq + 1, 256)), 148 * 8)), 256, 0, c->stream>>>(
+        W.strip_off.as<uint32_t>(), P, tile_cnt, tile_base, W.stage_hash.as<uint64_t>(), W.stage_posf.as<uint32_t>(), out.hash.as<uint64_t>(),
+        out.posf.as<uint32_t>(), out.mx_off.as<uint32_t>(), st, call_state, call_state ? 1u : 0u);
+    c->launches += 2;
+    tock(c, T_EMIT);
+    NTL_CUDA(c, cudaGetLastError());
+    out.n_dev = &st->n_mx;
+    if (call_state) { out.n_mx = out_cap; *done = true; return NTL_OK; }
+    k_publish_sketch<<<1, 32, 0, c->stream>>>(st, W.strip_off.as<uint32_t>() + nseq, nullptr, c->h_status.as<uint32_t>());
+    c->launches += 1;
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    {
+        const SketchStatus hs = *c->h_status.as<SketchStatus>();
+        if (hs.err) {
+            if (hs.err & SKERR_GAPS) return NTL_OK;                        // *done stays false: multi-pass path
+            if (++attempt > 6) { c->err = "sketch: device workspace exhausted"; return NTL_ERR_WORKSPACE; }
+            if (hs.err & SKERR_EXTRAS) extras_cap = (uint32_t)std::min<uint64_t>(0xFFFF0000ull, std::max<uint64_t>((uint64_t)hs.extras_used + 1024, (uint64_t)extras_cap * 4));
+            if (hs.err & SKERR_OUT) {                               // denser than the bound (low complexity): more room per tile and overall
+                c->mx_density_factor *= 2.0;
+                out_cap = (uint32_t)std::min<uint64_t>(total_bases, (uint64_t)out_cap * 2);
+            }
+            goto retry;
+        }
+        out.n_mx = hs.n_mx;
+        note_mx_density(c, hs.n_mx, total_bases, w);
+    }
+    *done = true;
+    return NTL_OK;
+}
+
 // Sketch `nseq` sequences that are already on the device (ASCII d_seq, offsets d_off). The result stays on the
 // device in `out`. One host synchronisation (to learn the number of minimizers before the final compaction).
 int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
@@ -518,6 +652,17 @@ int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint3
     if (nseq == 0 || total_bases == 0) {
         NTL_CUDA(c, cudaMemsetAsync(out.mx_off.p, 0, ((size_t)nseq + 1) * 4, c->stream));
         return NTL_OK;
+    }
+    if (c->tile_mode) {
+        const TileShape shape = tile_shape(k, w, c->cand_c);
+        if (shape.ok) {
+            bool done = false;
+            NTL_TRY(sketch_device_tile(c, shape, d_seq, d_off, nseq, total_bases, k, w, out, call_state, &done));
+            c->n_tile_batches++;
+            if (done) return NTL_OK;
+            c->n_tile_fallbacks++;
+            if (call_state) return NTL_OK;      // deferred: the error bit is set, the caller repeats the call synchronously
+        }
     }
     const uint32_t S = c->strip_len;
     double mu = (double)S * c->cand_c / (double)w;
