@@ -123,6 +123,13 @@ struct SlotEmit {
         count++;
     }
     __device__ __forceinline__ bool room_for_block() const { return count + 8 <= cap; }
+    // interior blocks: the caller guaranteed room for 8, so the candidate test costs one predicated 128-bit store and a
+    // predicated increment instead of a divergent branch (some lane of a warp finds a candidate at almost every step)
+    __device__ __forceinline__ void push(bool c, uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) {
+        if (c) base[count] = make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), pos | (fwd ? FWD_BIT : 0u), lord);
+        count += c ? 1u : 0u;
+    }
+    __device__ __forceinline__ void flush_block() {}
 };
 
 // ---- the hot loop, device-only formulation --------------------------------------------------------------------
@@ -277,8 +284,9 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
                     roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
                     const uint64_t fh = ((uint64_t)h.fhi << 32) | h.flo, rh = ((uint64_t)h.rhi << 32) | h.rlo;
                     const uint64_t h0 = fh + rh;
-                    if ((uint32_t)(h0 >> 32) < tau_hi) emit.fast(h0, pos0 + j, fh <= rh, nv + j);
+                    emit.push((uint32_t)(h0 >> 32) < tau_hi, h0, pos0 + j, fh <= rh, nv + j);
                 }
+                emit.flush_block();
                 nv += 8;
             } else {
                 generic_block(h, wi, wo, t, lead, T, (int32_t)k, last_bad, nv, p0, tau_hi, tbl_s, lanebase, emit);
@@ -527,6 +535,9 @@ static TileShape tile_shape(uint32_t k, uint32_t w, double cand_c) {
         size_t at = (size_t)TILE_TBL_BYTES + (size_t)t.flat_cap * 12 + ((size_t)t.flat_cap + 2) * 6 + ((size_t)t.flat_cap + 2);
         at = (at + 7) & ~(size_t)7;
         at += std::max<size_t>(((size_t)t.flat_cap + 2 * TILE_KPAD) * 4, (size_t)TILE_GT * 9);     // select keys, later the exact-scan buffers
+        // the dense phase stages candidates (8 slots x 12 bytes per thread) in the region that starts at the flat list
+        const size_t mini_from = ((size_t)TILE_TBL_BYTES + (size_t)t.flat_cap * 14 + 4 + 7) & ~(size_t)7;
+        at = std::max(at, mini_from + (size_t)8 * 12 * TILE_THREADS);
         at = (at + 15) & ~(size_t)15;
         t.shared_at = (uint32_t)at;
         t.smem = at + sizeof(TileShared);

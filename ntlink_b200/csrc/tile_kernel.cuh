@@ -51,11 +51,13 @@ struct TileRec {                          // one exact scan
     uint32_t out_at;                      // tile-local output rank of the first one
 };
 
+struct Scan4 { uint32_t a_ex, b_ex, a_tot, b_tot, mx, mn; };
+struct Scan4Scratch { uint32_t a[4], b[4], mx[4], mn[4]; };
 struct TileShared {
     uint32_t cnt[TILE_THREADS], nv[TILE_THREADS], vbase[TILE_THREADS + 1], foff[TILE_THREADS + 1];
     uint32_t seq[TILE_THREADS], p0[TILE_THREADS], npos_strip[TILE_THREADS], flags[TILE_THREADS];   // flags: 1 first, 2 last strip of its sequence
     uint32_t pre[TILE_THREADS], prex[TILE_THREADS];       // outputs of leading records of a strip; exclusive prefix over the strips
-    uint32_t scan[34];
+    Scan4Scratch scan4[2];
     TileRec rec[TILE_MAXREC];
     uint32_t nrec, overflow, tile, gbase, err, pool_n;
     uint8_t sfirst[TILE_THREADS], slast[TILE_THREADS];    // first / last view strip of the strip's sequence
@@ -70,6 +72,9 @@ struct SmemEmit {
     uint16_t* prev;
     uint32_t* pool_n;
     uint32_t cap, count, p0, vbits, tail;
+    // staging of the 8-step interior blocks: slot s of this thread lives at index s * TILE_THREADS (conflict-free columns)
+    unsigned long long* m_h; uint32_t* m_m; uint32_t n;
+    // slow path (blocks with bounds / validity checks): one candidate, straight into the pool
     __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) {
         const uint32_t i = atomicAdd(pool_n, 1u);
         if (i < cap) {
@@ -80,6 +85,27 @@ struct SmemEmit {
     }
     __device__ __forceinline__ void fast(uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) { (*this)(h0, pos, fwd, lord); }
     __device__ __forceinline__ bool room_for_block() const { return true; }
+    // fast path: the candidate test of every step costs a predicated store pair, nothing else; the pool slot (a
+    // shared-memory atomic) is taken once per 8-step block for everything the block found
+    __device__ __forceinline__ void push(bool c, uint64_t h0, uint32_t pos, bool fwd, uint32_t lord) {
+        const uint32_t m = (pos - p0) | (fwd ? 0x100u : 0u) | vbits | (lord << 16);
+        if (c) { m_h[n * TILE_THREADS] = h0; m_m[n * TILE_THREADS] = m; }
+        n += c ? 1u : 0u;
+    }
+    __device__ __forceinline__ void flush_block() {
+        if (n) {
+            const uint32_t base = atomicAdd(pool_n, n);
+            for (uint32_t s = 0; s < n; s++) {
+                const uint32_t i = base + s;
+                if (i < cap) {
+                    const unsigned long long h0 = m_h[s * TILE_THREADS];
+                    lo[i] = (uint32_t)h0; hi[i] = (uint32_t)(h0 >> 32); meta[i] = m_m[s * TILE_THREADS];
+                    prev[i] = (uint16_t)tail; tail = i;
+                }
+            }
+            count += n; n = 0;
+        }
+    }
 };
 
 struct GapTileEmit {
@@ -232,28 +258,33 @@ __device__ void tile_exact_scan(const uint32_t* __restrict__ packed, const RollE
 // tile state word: bits 63..62 = 0 empty, 1 aggregate, 2 inclusive prefix; low 62 bits = count
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
 
-// inclusive max-scan (fwd) / min-scan (reverse) of one value per thread over the block, through shared memory
-__device__ __forceinline__ uint32_t tile_block_maxscan(uint32_t v, uint32_t* sm) {
+// One barrier for four block-wide scans of per-thread values: exclusive sums of a and b, inclusive forward max of mx,
+// inclusive reverse min of mn. Warp-level shuffles, the warp aggregates go through one of two scratch sets (alternating:
+// a scratch set is only rewritten after the barrier of the call in between).
+__device__ __forceinline__ Scan4 tile_scan4(uint32_t a, uint32_t b, uint32_t mx, uint32_t mn, Scan4Scratch* sc) {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t ai = a, bi = b;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (uint32_t)d) v = max(v, t); }
-    if (lane == 31) sm[wid] = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ta = __shfl_up_sync(0xffffffffu, ai, d), tb = __shfl_up_sync(0xffffffffu, bi, d), tm = __shfl_up_sync(0xffffffffu, mx, d);
+        const uint32_t tn = __shfl_down_sync(0xffffffffu, mn, d);
+        if (lane >= (uint32_t)d) { ai += ta; bi += tb; mx = max(mx, tm); }
+        if (lane + d < 32) mn = min(mn, tn);
+    }
+    if (lane == 31) { sc->a[wid] = ai; sc->b[wid] = bi; sc->mx[wid] = mx; }
+    if (lane == 0) sc->mn[wid] = mn;
     __syncthreads();
-    uint32_t carry = 0;
-    for (uint32_t q = 0; q < wid; q++) carry = max(carry, sm[q]);
-    __syncthreads();
-    return max(v, carry);
-}
-__device__ __forceinline__ uint32_t tile_block_minscan_rev(uint32_t v, uint32_t* sm) {
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Scan4 r;
+    uint32_t ca = 0, cb = 0, ta = 0, tb = 0, cm = 0, cn = 0xFFFFFFFFu;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_down_sync(0xffffffffu, v, d); if (lane + d < 32) v = min(v, t); }
-    if (lane == 0) sm[wid] = v;
-    __syncthreads();
-    uint32_t carry = 0xFFFFFFFFu;
-    for (uint32_t q = wid + 1; q < TILE_THREADS / 32; q++) carry = min(carry, sm[q]);
-    __syncthreads();
-    return min(v, carry);
+    for (uint32_t q = 0; q < TILE_THREADS / 32; q++) {
+        const uint32_t xa = sc->a[q], xb = sc->b[q];
+        if (q < wid) { ca += xa; cb += xb; cm = max(cm, sc->mx[q]); }
+        if (q > wid) cn = min(cn, sc->mn[q]);
+        ta += xa; tb += xb;
+    }
+    r.a_ex = ca + ai - a; r.b_ex = cb + bi - b; r.a_tot = ta; r.b_tot = tb; r.mx = max(mx, cm); r.mn = min(mn, cn);
+    return r;
 }
 
 // meta word of a candidate: offset in its strip (8 bits) | forward strand (bit 8) | view strip (bits 9..15) | valid-k-mer
@@ -287,6 +318,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const uint32_t* __restric
     unsigned char* const key_region = dyn + ((TILE_TBL_BYTES + P.flat_cap * 12 + (P.flat_cap + 2) * 6 + (P.flat_cap + 2) + 7u) & ~7u);
     uint32_t* k_hi = reinterpret_cast<uint32_t*>(key_region) + TILE_KPAD;
     uint16_t* k_ord = f_rank;
+    unsigned char* const mini_region = dyn + ((TILE_TBL_BYTES + P.flat_cap * 12 + P.flat_cap * 2 + 4 + 7u) & ~7u);     // from f_idx on
     unsigned long long* gap_h = reinterpret_cast<unsigned long long*>(key_region);  // exact-scan buffers: after the select phase
     uint8_t* gap_f = reinterpret_cast<uint8_t*>(gap_h + TILE_GT);
     TileShared& T = *reinterpret_cast<TileShared*>(dyn + P.shared_at);
@@ -303,7 +335,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const uint32_t* __restric
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) T.tile = atomicAdd(ticket, 1u);
+        // the previous tile is finished for thread 0 once it gets here; the others may still be writing its outputs, which
+        // touches neither of the words reset below
+        if (tid == 0) {
+            if (T.err) { atomicOr(&st->err, T.err); T.err = 0; }
+            T.tile = atomicAdd(ticket, 1u); T.nrec = 0; T.pool_n = 0;
+        }
         __syncthreads();
         const uint32_t tile = T.tile;
         if (tile >= ntiles) break;
@@ -326,38 +363,36 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const uint32_t* __restric
         }
         T.seq[tid] = q; T.p0[tid] = p0; T.flags[tid] = fl; T.npos_strip[tid] = np; T.pre[tid] = 0;
         uint32_t tau_hi = P.tau_hi;
-        uint32_t vb = 0, fo = 0, ncand = 0, tail = 0xFFFFu;
-        // ---- 1: dense (again with a smaller threshold while a slot row or the flat list overflows)
+        uint32_t vb = 0, fo = 0, tail = 0xFFFFu, sfirst = 0, slast = 0, count = 0;
+        // ---- 1: dense (again with a smaller threshold while the candidate pool overflows)
         for (;;) {
-            if (tid == 0) { T.overflow = 0; T.nrec = 0; T.pool_n = 0; }
-            __syncthreads();
-            uint32_t count = 0, nvalid = 0;
+            uint32_t nvalid = 0;
+            count = 0;
             if (live) {
-                SmemEmit em{p_lo, p_hi, p_meta, p_prev, &T.pool_n, P.flat_cap, 0u, p0, tid << 9, 0xFFFFu};
+                // the staging columns use the flat-list / select-key region, which is dead during the dense phase
+                SmemEmit em{p_lo, p_hi, p_meta, p_prev, &T.pool_n, P.flat_cap, 0u, p0, tid << 9, 0xFFFFu,
+                            reinterpret_cast<unsigned long long*>(mini_region) + tid, reinterpret_cast<uint32_t*>(mini_region + 8 * 8 * TILE_THREADS) + tid, 0u};
                 nvalid = process_strip_dev(packed, gseq, p0, n, P.k, tbl_s, (tid & 15u) << 4, tau_hi, em);
                 count = em.count;
                 tail = em.tail;
             }
-            T.cnt[tid] = count; T.nv[tid] = nvalid;
-            uint32_t total_v;
-            vb = tile_block_scan(nvalid, T.scan, &total_v);
-            fo = tile_block_scan(count, T.scan, &ncand);
-            if (tid == 0 && ncand > P.flat_cap) T.overflow = 1;
-            T.vbase[tid] = vb; T.foff[tid] = fo;
-            if (tid == TILE_THREADS - 1) { T.vbase[TILE_THREADS] = total_v; T.foff[TILE_THREADS] = ncand; }
+            // valid k-mers and candidates before my strip; first / last view strip of my strip's sequence (the view may
+            // cut the sequence on either side)
+            const Scan4 sc = tile_scan4(nvalid, count, (fl & 1u) ? tid : 0u, (fl & 2u) ? tid : (live ? TILE_THREADS - 1 : tid), &T.scan4[0]);
+            vb = sc.a_ex; fo = sc.b_ex; sfirst = sc.mx; slast = sc.mn;
+            T.cnt[tid] = count; T.nv[tid] = nvalid; T.vbase[tid] = vb; T.foff[tid] = fo;
+            T.sfirst[tid] = (uint8_t)sfirst; T.slast[tid] = (uint8_t)slast;
+            if (tid == TILE_THREADS - 1) { T.vbase[TILE_THREADS] = sc.a_tot; T.foff[TILE_THREADS] = sc.b_tot; }
+            if (sc.b_tot <= P.flat_cap) break;           // same value in every thread
             __syncthreads();
-            if (!T.overflow) break;
+            if (tid == 0) T.pool_n = 0;
             __syncthreads();
             tau_hi = tau_hi >> 3;            // tau = 0: nothing is a candidate, the exact scan does everything
         }
-        // first / last view strip of every strip's sequence (the view may cut the sequence on either side)
-        const uint32_t sfirst = tile_block_maxscan((fl & 1u) ? tid : 0u, T.scan);
-        const uint32_t slast = tile_block_minscan_rev((fl & 2u) ? tid : (live ? TILE_THREADS - 1 : tid), T.scan);
-        T.sfirst[tid] = (uint8_t)sfirst; T.slast[tid] = (uint8_t)slast;
         // flat list of the view's candidates in position order; ordinals into the meta words
         {
             uint32_t i = tail;
-            for (uint32_t j = T.cnt[tid]; j-- > 0;) {                                 // my candidates, last one first
+            for (uint32_t j = count; j-- > 0;) {                                      // my candidates, last one first
                 const uint32_t m = c_meta(i) + (vb << 16);
                 c_meta(i) = m;
                 f_idx[fo + j] = (uint16_t)i; k_hi[fo + j] = c_hi(i); k_ord[fo + j] = (uint16_t)TM_ORD(m);
@@ -447,24 +482,19 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const uint32_t* __restric
                 if (tie || !fA || !fB) r = decide_linear(e);                 // equal high words or a crowded window: the exact walk
                 else if ((hitA && unkA) || (hitB && unkB)) r = 2;
                 else r = min(A, W1) + min(B, W1) >= W1 ? 1u : 0u;
+                // records: a candidate the view cannot decide, the candidate-free stretch after this candidate
+                const uint32_t m0 = c_meta(f_idx[e]), v = TM_V(m0), pos = T.p0[v] + TM_OFF(m0);
+                const uint32_t vl = T.slast[v];
+                if (r == 2) { r = 0; add_rec(v, pos, pos + 1, 0, T.npos_strip[v], pos, e); }
                 f_sel[e] = (uint8_t)r;
-            }
-        }
-        __syncthreads();
-        // records: candidates the view cannot decide, candidate-free stretches after own candidates
-        for (uint32_t eb = e_own0; eb < e_own1; eb += TILE_THREADS) {
-            const uint32_t e = eb + tid;
-            if (e >= e_own1) continue;
-            const uint32_t m0 = c_meta(f_idx[e]), v = TM_V(m0), ord = TM_ORD(m0), pos = T.p0[v] + TM_OFF(m0);
-            const uint32_t vl = T.slast[v], e_hi = T.foff[vl + 1];
-            if (f_sel[e] == 2) { f_sel[e] = 0; add_rec(v, pos, pos + 1, 0, T.npos_strip[v], pos, e); }
-            uint32_t gap_len, nxt_pos; bool nxt_known = true;
+                uint32_t gap_len, nxt_pos; bool nxt_known = true;
             if (e + 1 < e_hi) { const uint32_t m = c_meta(f_idx[e + 1]); gap_len = TM_ORD(m) - ord - 1; nxt_pos = T.p0[TM_V(m)] + TM_OFF(m); }
             else if (T.flags[vl] & 2u) { gap_len = T.vbase[vl] + T.nv[vl] - 1 - ord; nxt_pos = T.npos_strip[v]; }
             else { gap_len = 0xFFFFFFFFu; nxt_pos = 0; nxt_known = false; }
-            if (gap_len >= w) {
-                const uint32_t seg_hi = seg_hi_of(v);
-                add_rec(v, pos + 1, min(nxt_known ? nxt_pos : seg_hi, seg_hi), pos + 1, nxt_known ? nxt_pos : T.npos_strip[v], NONE32, e);
+                if (gap_len >= w) {
+                    const uint32_t seg_hi = seg_hi_of(v);
+                    add_rec(v, pos + 1, min(nxt_known ? nxt_pos : seg_hi, seg_hi), pos + 1, nxt_known ? nxt_pos : T.npos_strip[v], NONE32, e);
+                }
             }
         }
         // the stretch that reaches an own segment from the left: handled by the segment's first own strip
@@ -503,7 +533,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const uint32_t* __restric
                 tile_exact_scan(packed, tbl_g, tbl_s, gs, (uint32_t)(seq_off[qq + 1] - gs), T.npos_strip[r.v], P, tau_hi, r, extras, &st->extras_used,
                                 &T.err, gap_h, gap_f);
             }
-        __syncthreads();
+        if (nrec) __syncthreads();                                                 // same value in every thread
         // ---- 4: output ranks (own candidates in flat order, each followed by its records), tile offset, emit
         const uint32_t n_own = e_own1 - e_own0;
         const uint32_t chunk = (n_own + TILE_THREADS - 1) / TILE_THREADS;
@@ -517,13 +547,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const uint32_t* __restric
                 else if (r.attach - e_own0 >= ca && r.attach - e_own0 < cb) mine += r.out_cnt;
             }
         }
-        uint32_t tot_c, tot_p;
-        const uint32_t cbase = tile_block_scan(mine, T.scan, &tot_c);
-        const uint32_t pbase = tile_block_scan(T.pre[tid], T.scan, &tot_p);        // leading records of the strips before mine
-        T.prex[tid] = pbase;
-        const uint32_t tile_total = tot_c + tot_p;
+        // outputs of the chunks before mine; leading records of the strips before mine
+        const Scan4 so = tile_scan4(mine, T.pre[tid], 0u, 0u, &T.scan4[1]);
+        const uint32_t tot_c = so.a_tot;
+        T.prex[tid] = so.b_ex;
+        const uint32_t tile_total = so.a_tot + so.b_tot;
         {
-            uint32_t r = cbase;
+            uint32_t r = so.a_ex;
             for (uint32_t i = ca; i < cb; i++) {
                 f_rank[e_own0 + i] = (uint16_t)r;
                 r += f_sel[e_own0 + i];
@@ -534,11 +564,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const uint32_t* __restric
         // the tile's minimizers go to its own staging segment (no waiting for other tiles); k_tile_gather packs the segments
         if (tid == 0) {
             tile_cnt[tile] = tile_total;
-            T.gbase = tile * P.tcap;
             if (tile_total > P.tcap) T.err |= SKERR_OUT;
         }
         __syncthreads();
-        const uint32_t gb = T.gbase;
+        const uint32_t gb = tile * P.tcap;
         const bool writable = tile_total <= P.tcap;
         if (own && (fl & 1u)) {                                                      // a sequence starts here: its offset inside the
             const uint32_t o = f_rank[T.foff[tid]] + T.prex[tid];                    // tile, and that of the empty sequences before it
@@ -567,9 +596,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const uint32_t* __restric
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0 && T.err) { atomicOr(&st->err, T.err); T.err = 0; }
-        __syncthreads();
+        __syncthreads();       // the pool and the flat list are free again (thread 0 may take the next ticket)
     }
 }
 
