@@ -277,6 +277,26 @@ int ntl_verbose_read(ntl_verbose_file* f, uint64_t max_hits, int share_repeated,
 const char* ntl_verbose_error(ntl_verbose_file* f);
 void ntl_verbose_close(ntl_verbose_file* f);
 
+/* indexlr TSV (plain or gzip, "-" = stdin) -> sketch arrays in bounded batches. Replaces the Python line / token splitting
+ * of NtLink.read_minimizers and find_scaffold_pairs (bin/ntlink_pair.py:196-203,355-366) for the reference's own text
+ * interface `indexlr ... | ntlink_pair.py ... -` (ntLink:221-225). with_len = 1 for `indexlr --len` output (reads). Each
+ * call returns whole records until about max_mx minimizers (0 = the rest of the file); n_seq == 0 at the end. Arrays are
+ * malloc'ed: release with ntl_free. */
+typedef struct ntl_tsv_file ntl_tsv_file;
+typedef struct ntl_tsv_out {
+    uint32_t n_seq, reserved;
+    uint64_t n_mx;
+    uint64_t* hash;           /* [n_mx] */
+    uint32_t* pos_strand;     /* [n_mx] */
+    uint64_t* mx_off;         /* [n_seq + 1] */
+    uint32_t* seq_len;        /* [n_seq] or NULL without --len */
+    char* names;  uint64_t* name_off;   /* [n_seq + 1] */
+} ntl_tsv_out;
+int ntl_tsv_open(const char* path, int with_len, ntl_tsv_file** out);
+int ntl_tsv_read(ntl_tsv_file* f, uint64_t max_mx, ntl_tsv_out* out);
+const char* ntl_tsv_error(ntl_tsv_file* f);
+void ntl_tsv_close(ntl_tsv_file* f);
+
 /* ---- device-resident / timing interface (bench.py) ----------------------------------------------- */
 /* copy a read batch to the device once; ntl_map_resident then runs the whole hot path on it without touching
  * the host (results stay on the device; only the counters come back). */

@@ -69,6 +69,12 @@ class PairsOut(C.Structure):
                 ("gaps", C.POINTER(C.c_int32))]
 
 
+class TsvOut(C.Structure):
+    _fields_ = [("n_seq", C.c_uint32), ("reserved", C.c_uint32), ("n_mx", C.c_uint64),
+                ("hash", C.POINTER(C.c_uint64)), ("pos_strand", C.POINTER(C.c_uint32)), ("mx_off", C.POINTER(C.c_uint64)),
+                ("seq_len", C.POINTER(C.c_uint32)), ("names", C.c_void_p), ("name_off", C.POINTER(C.c_uint64))]
+
+
 # every symbol include/ntlink_b200.h declares: name -> (restype, argtypes)
 _VP, _U64P, _U32P = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
 SIGNATURES = {
@@ -96,6 +102,10 @@ SIGNATURES = {
     "ntl_verbose_read": (C.c_int, [_VP, C.c_uint64, C.c_int, C.POINTER(MappingsOut)]),
     "ntl_verbose_error": (C.c_char_p, [_VP]),
     "ntl_verbose_close": (None, [_VP]),
+    "ntl_tsv_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ntl_tsv_read": (C.c_int, [_VP, C.c_uint64, C.POINTER(TsvOut)]),
+    "ntl_tsv_error": (C.c_char_p, [_VP]),
+    "ntl_tsv_close": (None, [_VP]),
     "ntl_events_reset": (C.c_int, [_VP]),
     "ntl_events_append": (C.c_int, [_VP, _VP, C.c_uint64]),
     "ntl_events_count": (C.c_int, [_VP, _U64P]),

@@ -187,6 +187,38 @@ def read_verbose_mappings(path, contig_names=None, share_repeated=True, max_hits
         lib.ntl_verbose_close(h)
 
 
+def read_sketch_tsv(path, with_len, max_mx=0):
+    """indexlr TSV (plain or gzip, '-' = stdin) -> batches (names, lengths u32 or None, Sketch) through the library's
+    native parser (ntl_tsv_*): whole records until about max_mx minimizers per batch (0 = one batch for the whole file)."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    if lib.ntl_tsv_open(path.encode(), int(bool(with_len)), C.byref(h)) != 0:
+        raise OSError(f"cannot open {path}")
+    try:
+        while True:
+            to = _lib.TsvOut()
+            if lib.ntl_tsv_read(h, max_mx, C.byref(to)) != 0:
+                raise ValueError((lib.ntl_tsv_error(h) or b"malformed sketch TSV").decode())
+            n = to.n_seq
+            hashes = _np_from(to.hash, to.n_mx, np.uint64)
+            posf = _np_from(to.pos_strand, to.n_mx, np.uint32)
+            off = _np_from(to.mx_off, n + 1, np.uint64)
+            lens = _np_from(to.seq_len, n, np.uint32) if with_len else None
+            no = _np_from(to.name_off, n + 1, np.uint64).tolist()
+            nb = C.string_at(to.names, no[-1]) if n else b""
+            for ptr in (to.hash, to.pos_strand, to.mx_off, to.seq_len, to.name_off):
+                if ptr:
+                    lib.ntl_free(C.cast(ptr, C.c_void_p))
+            lib.ntl_free(to.names)
+            if n == 0:
+                return
+            yield [nb[no[i]:no[i + 1]].decode() for i in range(n)], lens, Sketch(hashes, posf, off)
+            if max_mx == 0:
+                return
+    finally:
+        lib.ntl_tsv_close(h)
+
+
 def read_sequences(path, max_bases=0):
     """FASTA/FASTQ (plain or gzip, multi-line) -> SeqBatch of the whole file (or of its first ~max_bases bases)."""
     with SeqFile(path) as f:

@@ -989,4 +989,105 @@ void ntl_verbose_close(ntl_verbose_file* f) {
     delete f;
 }
 
+// ------------------------------------------------------------------------------------------- indexlr TSV parser
+// The reference's own read interface is text: `indexlr --long --pos --strand [--len] ... | ntlink_pair.py ... -`
+// (ntLink:221-225); ntlink_pair.py splits every line and every token in Python (bin/ntlink_pair.py:196-203,355-366), which
+// is where its time goes. Same parse, natively, in bounded batches (a 30x human read set is ~10^9 minimizers of text).
+//   target TSV:  name \t tok( tok)*          reads TSV:  name \t length \t tok( tok)*      tok = hash:pos:strand
+// Lines are strip()ped and split at tabs like the reference does; records with fewer fields are kept as empty sketches
+// (the reference skips them, pair:200,357 -- they cannot hit anything either way).
+struct ntl_tsv_file {
+    ntl_seqfile* src = nullptr;
+    bool with_len = false, done = false;
+    std::string err;
+};
+
+int ntl_tsv_open(const char* path, int with_len, ntl_tsv_file** out) {
+    if (!path || !out) return NTL_ERR_ARG;
+    ntl_tsv_file* f = new ntl_tsv_file();
+    if (ntl_seqfile_open(path, &f->src) != NTL_OK) { delete f; return NTL_ERR_ARG; }
+    f->src->parallel = false;
+    if (f->src->fd >= 0) lseek(f->src->fd, 0, SEEK_SET);
+    f->with_len = with_len != 0;
+    *out = f;
+    return NTL_OK;
+}
+const char* ntl_tsv_error(ntl_tsv_file* f) { return f ? f->err.c_str() : ""; }
+
+int ntl_tsv_read(ntl_tsv_file* f, uint64_t max_mx, ntl_tsv_out* out) {
+    if (!f || !out) return NTL_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    std::vector<uint64_t> hash, mx_off(1, 0), name_off(1, 0);
+    std::vector<uint32_t> posf, lens;
+    std::string names;
+    const char* lp = nullptr;
+    size_t ll = 0;
+    while (!f->done && !(max_mx && hash.size() >= max_mx)) {
+        if (!f->src->getline(lp, ll)) { f->done = true; break; }
+        const char* b = lp;
+        const char* e = lp + ll;
+        while (b < e && (unsigned char)*b <= ' ') b++;
+        while (e > b && (unsigned char)e[-1] <= ' ') e--;
+        if (b == e) continue;
+        const char* t1 = (const char*)memchr(b, '\t', (size_t)(e - b));
+        const char* name_end = t1 ? t1 : e;
+        names.append(b, (size_t)(name_end - b));
+        name_off.push_back(names.size());
+        const char* p = t1 ? t1 + 1 : e;
+        if (f->with_len) {
+            uint64_t L = 0;
+            const char* t2 = p < e ? (const char*)memchr(p, '\t', (size_t)(e - p)) : nullptr;
+            const char* le = t2 ? t2 : e;
+            for (const char* q = p; q < le; q++) {
+                if (*q < '0' || *q > '9') { f->err = "malformed length column in the sketch TSV"; return NTL_ERR_ARG; }
+                L = L * 10 + (uint64_t)(*q - '0');
+            }
+            if (L > 0xFFFFFFFFull) { f->err = "sequence length does not fit 32 bits"; return NTL_ERR_ARG; }
+            lens.push_back((uint32_t)L);
+            p = t2 ? t2 + 1 : e;
+        }
+        // tokens up to the next tab (further columns are ignored, like the reference's line[1] / line[2])
+        const char* col_end = p < e ? (const char*)memchr(p, '\t', (size_t)(e - p)) : nullptr;
+        if (!col_end) col_end = e;
+        while (p < col_end) {
+            while (p < col_end && *p == ' ') p++;
+            if (p >= col_end) break;
+            uint64_t h = 0, pos = 0;
+            const char* q = p;
+            if (*q < '0' || *q > '9') { f->err = "malformed minimizer in the sketch TSV"; return NTL_ERR_ARG; }
+            while (q < col_end && *q >= '0' && *q <= '9') h = h * 10 + (uint64_t)(*q++ - '0');
+            if (q >= col_end || *q != ':') { f->err = "malformed minimizer in the sketch TSV (hash:pos:strand expected)"; return NTL_ERR_ARG; }
+            q++;
+            if (q >= col_end || *q < '0' || *q > '9') { f->err = "malformed minimizer position in the sketch TSV"; return NTL_ERR_ARG; }
+            while (q < col_end && *q >= '0' && *q <= '9') pos = pos * 10 + (uint64_t)(*q++ - '0');
+            uint32_t fw = 0;
+            if (q < col_end && *q == ':') {                       // strand column (absent with `indexlr --pos` only)
+                if (q + 1 >= col_end || (q[1] != '+' && q[1] != '-')) { f->err = "malformed minimizer strand in the sketch TSV"; return NTL_ERR_ARG; }
+                fw = q[1] == '+' ? 0x80000000u : 0u;
+                q += 2;
+            }
+            if (q < col_end && *q != ' ') { f->err = "malformed minimizer in the sketch TSV"; return NTL_ERR_ARG; }
+            if (pos > 0x7FFFFFFFull) { f->err = "minimizer position does not fit 31 bits"; return NTL_ERR_ARG; }
+            hash.push_back(h); posf.push_back((uint32_t)pos | fw);
+            p = q;
+        }
+        mx_off.push_back(hash.size());
+    }
+    out->n_seq = (uint32_t)(mx_off.size() - 1);
+    out->n_mx = hash.size();
+    out->hash = vec_to_malloc(hash); out->pos_strand = vec_to_malloc(posf); out->mx_off = vec_to_malloc(mx_off);
+    out->seq_len = f->with_len ? vec_to_malloc(lens) : nullptr;
+    out->names = (char*)malloc(names.size() + 1);
+    if (out->names) memcpy(out->names, names.data(), names.size());
+    out->name_off = vec_to_malloc(name_off);
+    if (!out->hash || !out->pos_strand || !out->mx_off || (f->with_len && !out->seq_len) || !out->names || !out->name_off) { f->err = "out of memory"; return NTL_ERR_ARG; }
+    return NTL_OK;
+}
+
+void ntl_tsv_close(ntl_tsv_file* f) {
+    if (!f) return;
+    ntl_seqfile_close(f->src);
+    delete f;
+}
+
 }  // extern "C"

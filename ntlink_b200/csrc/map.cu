@@ -12,6 +12,7 @@
 //   k_compact_events                    append to the device event log
 //   k_tally_*                           edge table with atomics (n, anchor, first-seen), gap lists in read order
 #include <algorithm>
+#include <thread>
 
 #include "common.cuh"
 #include "lift_logic.cuh"
@@ -1045,7 +1046,26 @@ int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>&
     memcpy(gaps.data(), hs + pair_bytes, gap_bytes_copy);
 #undef TL_CUDA
     cleanup();
-    std::sort(pairs.begin(), pairs.end(), [](const ntl_pair& a, const ntl_pair& b) { return a.first_key < b.first_key; });
+    // first-seen order (the reference's dict order). Sorted as (key, index) records on a few host threads and then permuted:
+    // at human scale the table has > 10^5 pairs and a plain sort of the 40-byte rows was most of rank 0's tally time.
+    {
+        const size_t np_ = pairs.size();
+        std::vector<std::pair<uint64_t, uint32_t>> key(np_);
+        for (size_t i = 0; i < np_; i++) key[i] = {pairs[i].first_key, (uint32_t)i};
+        const int nt = np_ >= 65536 ? 4 : 1;
+        std::vector<size_t> cut(nt + 1);
+        for (int t = 0; t <= nt; t++) cut[t] = np_ * t / nt;
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back([&, t]() { std::sort(key.begin() + cut[t], key.begin() + cut[t + 1]); });
+        std::sort(key.begin() + cut[0], key.begin() + cut[1]);
+        for (auto& x : th) x.join();
+        for (int step = 1; step < nt; step *= 2)
+            for (int t = 0; t + step < nt; t += 2 * step)
+                std::inplace_merge(key.begin() + cut[t], key.begin() + cut[t + step], key.begin() + cut[std::min(nt, t + 2 * step)]);
+        std::vector<ntl_pair> sorted(np_);
+        for (size_t i = 0; i < np_; i++) sorted[i] = pairs[key[i].second];
+        pairs.swap(sorted);
+    }
     return NTL_OK;
 }
 

@@ -204,19 +204,32 @@ def parse_arguments(argv=None):
     p.add_argument("--sketch-target", action="store_true", help="Sketch the target (-s) on the GPU instead of reading -m")
     p.add_argument("--write-target-tsv", help="Also write the target sketch TSV here", default=None)
     p.add_argument("--device", type=int, default=0)
+    p.add_argument("--gpus", type=int, default=1, help="GPUs of this node: read batches are dealt to the ranks, the target index is "
+                                                       "replicated, pair events are gathered over NCCL (one process per GPU, torchrun)")
     p.add_argument("--batch-bases", type=float, default=1e9, help="bases per streamed read batch with --reads-fasta [1e9]")
+    p.add_argument("--batch-minimizers", type=float, default=5e7, help="minimizers per streamed batch of a read TSV [5e7]")
     p.add_argument("-t", type=int, default=4, help="host threads for text output")
-    return p.parse_args(argv)
+    a = p.parse_args(argv)
+    # the reference declares FILES with nargs='+' (pair:510); here reads may also come from --reads-fasta or a checkpoint
+    if not a.FILES and not a.reads_fasta and not a.checkpoint and not os.path.isfile(a.p + ".verbose_mapping.tsv"):
+        p.error("the following arguments are required: FILES (or --reads-fasta)")
+    return a
 
 
 class NtLink:
     "GPU-backed counterpart of the reference's NtLink class (bin/ntlink_pair.py:115-617)"
 
-    def __init__(self, args, ctx=None):
+    def __init__(self, args, ctx=None, rank=0, world=1, dist=None):
         self.args = args
+        self.rank, self.world, self.dist = rank, world, dist
         self.ctx = ctx or api.Context(args.device)
         self.contigs = None          # SeqBatch of the target (names/lengths)
         self.lengths = None          # name -> length
+        self.xch = None
+        self.created = []            # output files this run created (removed again if the run fails)
+        if world > 1:
+            from . import dist as nd
+            self.xch = nd.GpuExchange(self.ctx, dist, rank, world)
 
     # -- M1
     def read_minimizers(self):
@@ -226,53 +239,105 @@ class NtLink:
         self.contigs = api.read_sequences(a.s)
         self.lengths = {n: int(l) for n, l in zip(self.contigs.names, self.contigs.lengths)}
         if a.sketch_target or not a.m:
-            if a.w is None:
-                raise NtlinkPairError("-w is required to sketch the target on the GPU")
-            sk = self.ctx.build_index_from_sequences(self.contigs, a.k, a.w, want_sketch=bool(a.write_target_tsv))
-            if a.write_target_tsv:
-                with open(a.write_target_tsv, "wb") as fout:
-                    fout.write(sk.to_tsv(self.contigs, with_len=False, threads=a.t))
+            if self.world > 1 and not a.write_target_tsv:
+                # every rank sketches its contig shard, the triples are all-gathered, every GPU builds the same index
+                self.xch.build_index_sharded(self.contigs, a.k, a.w)
+            else:
+                sk = self.ctx.build_index_from_sequences(self.contigs, a.k, a.w, want_sketch=bool(a.write_target_tsv))
+                if a.write_target_tsv and self.rank == 0:
+                    with open(a.write_target_tsv, "wb") as fout:
+                        fout.write(sk.to_tsv(self.contigs, with_len=False, threads=a.t))
         else:
-            with (sys.stdin if a.m == "-" else open(a.m)) as fin:
-                names, _, hashes, posf, off = parse_sketch_tsv(fin, with_len=False)
             idx = {n: i for i, n in enumerate(self.contigs.names)}
-            ctg = np.repeat(np.array([idx[n] for n in names], np.uint32), np.diff(off).astype(np.int64))
-            self.ctx.build_index(hashes, ctg, posf, self.contigs.lengths.astype(np.uint32), self.contigs.names)
+            hs, ps, cs = [], [], []
+            try:
+                for names, _, sk in api.read_sketch_tsv(a.m, with_len=False, max_mx=int(a.batch_minimizers)):
+                    hs.append(sk.hash)
+                    ps.append(sk.pos_strand)
+                    cs.append(np.repeat(np.array([idx[n] for n in names], np.uint32), np.diff(sk.seq_off).astype(np.int64)))
+            except (ValueError, KeyError) as exc:
+                raise NtlinkPairError(f"target minimizer file {a.m}: {exc}") from exc
+            cat = lambda parts, dt: np.concatenate(parts) if parts else np.empty(0, dt)   # noqa: E731
+            self.ctx.build_index(cat(hs, np.uint64), cat(cs, np.uint32), cat(ps, np.uint32), self.contigs.lengths.astype(np.uint32),
+                                 self.contigs.names)
         return self.ctx.index_stats()["unique"]
+
+    def _read_batches(self):
+        "(reads SeqBatch, read lengths, Sketch or None) of every batch of the run, in input order -- the same on every rank"
+        a = self.args
+        if a.reads_fasta:
+            # streamed: batches of ~batch_bases, the next one is decoded by a background thread while this one is on the
+            # GPU (a 60x human read set does not fit in host memory, and gzip decoding is the slowest stage)
+            for reads in api.prefetch_batches(a.reads_fasta, int(a.batch_bases)):
+                yield reads, reads.lengths.astype(np.uint32), None
+        else:
+            # the reference's text interface (indexlr --len TSV, '-' = stdin), parsed natively in bounded batches
+            for path in a.FILES:
+                try:
+                    for names, lens, sk in api.read_sketch_tsv(path, with_len=True, max_mx=int(a.batch_minimizers)):
+                        yield api.SeqBatch(np.empty(0, np.uint8), np.zeros(len(names) + 1, np.uint64), names), lens, sk
+                except ValueError as exc:
+                    raise NtlinkPairError(f"{path}: {exc}") from exc
 
     # -- M2..M6, M8, M9
     def find_scaffold_pairs(self):
-        "replaces pair:336-414; returns the ordered pairs dict"
+        "replaces pair:336-414; returns the ordered pairs dict (rank 0; None on the other ranks)"
         a = self.args
         print(datetime.datetime.today(), ": Finding pairs", file=sys.stdout)
         prm = self.ctx.params(a.k, a.w or 1, a.z, a.f, a.x, a.sensitive, a.repeat_filter)
         self.ctx.events_reset()
-        vf = open(a.p + ".verbose_mapping.tsv", "wb") if a.verbose else None
-        pf = open(a.p + ".paf", "wb") if a.paf else None
-        ordinal = 0
+        single = self.world == 1
+        outs = {}
+        for key, suffix, on in (("v", ".verbose_mapping.tsv", a.verbose), ("p", ".paf", a.paf)):
+            if on and (single or self.rank == 0):
+                outs[key] = open(a.p + suffix, "wb")
+                self.created.append(a.p + suffix)
+        ordinal, parts = 0, []
         try:
-            if a.reads_fasta:
-                if a.w is None:
-                    raise NtlinkPairError("-w is required with --reads-fasta")
-                # streamed: batches of ~batch_bases, the next one is decoded by a background thread while this one is
-                # on the GPU (a 60x human read set does not fit in host memory, and gzip decoding is the slowest stage)
-                for reads in api.prefetch_batches(a.reads_fasta, int(a.batch_bases)):
-                    res = self.ctx.map_reads(reads, prm, ordinal)
-                    self._emit(res, reads, reads.lengths.astype(np.uint32), vf, pf)
-                    ordinal += len(reads)
-            else:
-                for path in a.FILES:
-                    with (sys.stdin if path == "-" else open(path)) as fin:
-                        names, lens, hashes, posf, off = parse_sketch_tsv(fin, with_len=True)
-                    reads = api.SeqBatch(np.empty(0, np.uint8), np.zeros(len(names) + 1, np.uint64), names)
-                    res = self.ctx.map_sketch(api.Sketch(hashes, posf, off), lens, prm, ordinal)
-                    self._emit(res, reads, lens, vf, pf)
-                    ordinal += len(names)
+            for i, (reads, lens, sk) in enumerate(self._read_batches()):
+                if i % self.world == self.rank:          # batches are dealt round robin; global read ordinals keep the order
+                    res = self.ctx.map_reads(reads, prm, ordinal) if sk is None else self.ctx.map_sketch(sk, lens, prm, ordinal)
+                    if single:
+                        self._emit(res, reads, lens, outs.get("v"), outs.get("p"))
+                    else:
+                        files = {}
+                        try:
+                            for key, on in (("v", a.verbose), ("p", a.paf)):
+                                if on:
+                                    path = f"{a.p}.part{i:06d}.{key}"
+                                    self.created.append(path)
+                                    files[key] = open(path, "wb")
+                            self._emit(res, reads, lens, files.get("v"), files.get("p"))
+                        finally:
+                            for f in files.values():
+                                f.close()
+                parts.append(i)
+                ordinal += len(reads)
+            if not single:
+                self.xch.gather_events(force_sync=True)      # every rank's pair events -> rank 0's event log
+                self.dist.barrier()                          # all part files are complete
+                if self.rank == 0:
+                    for key, suffix in (("v", ".verbose_mapping.tsv"), ("p", ".paf")):
+                        if key in outs:
+                            for i in parts:
+                                with open(f"{a.p}.part{i:06d}.{key}", "rb") as fin:
+                                    while True:
+                                        blk = fin.read(1 << 24)
+                                        if not blk:
+                                            break
+                                        outs[key].write(blk)
+                self.dist.barrier()
+                for i in parts:
+                    if i % self.world == self.rank:
+                        for key in ("v", "p"):
+                            path = f"{a.p}.part{i:06d}.{key}"
+                            if os.path.isfile(path):
+                                os.remove(path)
         finally:
-            if vf:
-                vf.close()
-            if pf:
-                pf.close()
+            for f in outs.values():
+                f.close()
+        if self.rank != 0:
+            return None
         return pairs_dict(self.ctx.pairs(), self.contigs.names)
 
     def find_scaffold_pairs_checkpoints(self, chunk_hits=50_000_000):
@@ -307,38 +372,77 @@ class NtLink:
     def main(self):
         a = self.args
         print("Running pairing stage of ntLink ...\n")
+        ok = False
         try:
             if os.path.isfile(a.p + ".verbose_mapping.tsv"):       # pair:565-566
                 a.checkpoint = a.p + ".verbose_mapping.tsv"
+            if not a.checkpoint and a.w is None and (a.reads_fasta or a.sketch_target or not a.m):
+                raise NtlinkPairError("-w is required to sketch on the GPU (--reads-fasta / --sketch-target / no -m)")
             if a.checkpoint:
                 print("Found checkpoint file, bypassing read mapping...\n")
                 if a.paf:
                     print("Warning: --paf specified, but not compatible with checkpoint")
-                pairs = self.find_scaffold_pairs_checkpoints()
+                pairs = self.find_scaffold_pairs_checkpoints() if self.rank == 0 else None
             else:
                 self.read_minimizers()
                 pairs = self.find_scaffold_pairs()
-            pairs = filter_pairs_distances(pairs, self.lengths)
-            pairs = filter_weak_anchor_pairs(pairs, a.a)
-            if a.pairs:
-                with open(a.p + ".pairs.tsv", "w") as fout:
-                    fout.write(pairs_tsv(pairs))
-            print(datetime.datetime.today(), ": Building scaffold graph", file=sys.stdout)
-            out_graph = f"{a.p}.n{a.n}.scaffold.dot"
-            print(datetime.datetime.today(), ": Printing graph", out_graph, sep=" ", file=sys.stdout)
-            with open(out_graph, "w") as fout:
-                fout.write(scaffold_dot(pairs, self.lengths, int(a.n)))
-            print(datetime.datetime.today(), ": DONE!", file=sys.stdout)
-        except Exception as exc:
-            # same clean-up as the reference (pair:608-613): never leave a partial checkpoint behind
-            for suffix, on in ((".verbose_mapping.tsv", a.verbose), (".paf", a.paf)):
-                if on and not a.checkpoint and os.path.isfile(a.p + suffix) and not isinstance(exc, NtlinkPairError):
-                    os.remove(a.p + suffix)
+            if self.rank == 0:
+                pairs = filter_pairs_distances(pairs, self.lengths)
+                pairs = filter_weak_anchor_pairs(pairs, a.a)
+                if a.pairs:
+                    with open(a.p + ".pairs.tsv", "w") as fout:
+                        fout.write(pairs_tsv(pairs))
+                print(datetime.datetime.today(), ": Building scaffold graph", file=sys.stdout)
+                out_graph = f"{a.p}.n{a.n}.scaffold.dot"
+                print(datetime.datetime.today(), ": Printing graph", out_graph, sep=" ", file=sys.stdout)
+                with open(out_graph, "w") as fout:
+                    fout.write(scaffold_dot(pairs, self.lengths, int(a.n)))
+                print(datetime.datetime.today(), ": DONE!", file=sys.stdout)
+            ok = True
+        except BaseException as exc:
+            # The reference's bare `except:` (pair:608-613): whatever ends the run -- an error, a failed assertion of the
+            # PAF writer, Ctrl-C, a kill -- must not leave a partial verbose_mapping.tsv behind, because the next run would
+            # take it for a checkpoint (pair:565-566) and silently write a truncated graph.
+            if isinstance(exc, (KeyboardInterrupt, SystemExit)):
+                raise
             raise NtlinkPairError("ntLink pairing stage encountered an error..") from exc
+        finally:
+            if not ok:
+                for path in self.created:
+                    if os.path.isfile(path):
+                        os.remove(path)
 
 
 def main(argv=None):
-    NtLink(parse_arguments(argv)).main()
+    argv = sys.argv[1:] if argv is None else list(argv)
+    args = parse_arguments(argv)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # one process per GPU through torchrun, same argv
+        import socket
+        import subprocess
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), "-m", "ntlink_b200.pair"] + argv
+        rc = subprocess.call(cmd)
+        if rc != 0:
+            raise NtlinkPairError(f"multi-GPU run failed (torchrun exit code {rc})")
+        return
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        args.device = local
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        try:
+            NtLink(args, rank=rank, world=world, dist=dist).main()
+        finally:
+            dist.destroy_process_group()
+        return
+    NtLink(args).main()
 
 
 if __name__ == "__main__":
