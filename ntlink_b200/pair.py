@@ -376,6 +376,10 @@ class NtLink:
         try:
             if os.path.isfile(a.p + ".verbose_mapping.tsv"):       # pair:565-566
                 a.checkpoint = a.p + ".verbose_mapping.tsv"
+            if self.world > 1:
+                # every rank must have looked before rank 0 creates this run's verbose_mapping.tsv, or a late rank would
+                # take the new file for a checkpoint and never join the collectives
+                self.dist.barrier()
             if not a.checkpoint and a.w is None and (a.reads_fasta or a.sketch_target or not a.m):
                 raise NtlinkPairError("-w is required to sketch on the GPU (--reads-fasta / --sketch-target / no -m)")
             if a.checkpoint:
@@ -436,7 +440,8 @@ def main(argv=None):
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         args.device = local
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime as _dt
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=_dt.timedelta(minutes=10))
         try:
             NtLink(args, rank=rank, world=world, dist=dist).main()
         finally:

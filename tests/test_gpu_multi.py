@@ -34,7 +34,7 @@ def _inputs(tmp, genome=4_000_000, cov=6, n_frac=0.2):
 
 def _run_cli(argv):
     env = dict(os.environ, PYTHONPATH=util.REPO + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    r = subprocess.run([sys.executable, "-m", "ntlink_b200.pair"] + argv, env=env, cwd=util.REPO, capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, "-m", "ntlink_b200.pair"] + argv, env=env, cwd=util.REPO, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
@@ -118,5 +118,5 @@ dist.barrier(); dist.destroy_process_group()
     script = tmp_path / "shard.py"
     script.write_text(code)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-                        "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=900)
+                        "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
