@@ -68,7 +68,7 @@ struct MapStatus {
     uint32_t n_runs;        // accepted (read, contig) runs
     uint32_t pad[12];
 };
-enum : uint32_t { MAPERR_EVENTS = 1, MAPERR_ASSERT = 2 };
+enum : uint32_t { MAPERR_EVENTS = 1, MAPERR_ASSERT = 2, MAPERR_READ_EVENTS = 4 };
 
 // per-stage device timings (CUDA events on ctx->stream), milliseconds; stage ids are NTL_T_* of the public header
 enum { T_PACK = NTL_T_PACK, T_DENSE = NTL_T_DENSE, T_SELECT = NTL_T_SELECT, T_GAP = NTL_T_GAP, T_EMIT = NTL_T_EMIT,

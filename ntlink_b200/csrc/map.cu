@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(128) k_events(const Hit* __restrict__ hits, co
     uint32_t ne = 0;
     if (nr >= 2) {
         const uint32_t eo = ev_off[r];
-        if ((uint64_t)eo + max_events(nr, P.f) > ev_cap) atomicOr(&st->err, MAPERR_EVENTS);
+        if (max_events(nr, P.f) > MAX_EVENTS_PER_READ) atomicOr(&st->err, MAPERR_READ_EVENTS);
+        else if ((uint64_t)eo + max_events(nr, P.f) > ev_cap) atomicOr(&st->err, MAPERR_EVENTS);
         else {
             const uint32_t o = hit_off[r];
             ne = tally_read(hits + o, runs + o, nr, read_len[r], first_ordinal + r, ctg_len, name_rank, P, events + eo);
@@ -827,6 +828,10 @@ retry_events:
     if (hs.err & MAPERR_ASSERT) {
         c->err = "an assertion of the reference would fail (bin/ntlink_pair.py:225 / :173-184): minimizer order or overhang";
         return NTL_ERR_ASSERT;
+    }
+    if (hs.err & MAPERR_READ_EVENTS) {
+        c->err = "a read maps to so many contigs that it would emit more than 16,777,215 contig pairs (-f too large for this read)";
+        return NTL_ERR_ARG;
     }
     if (hs.err & MAPERR_EVENTS) {
         if (++attempt > 2) { c->err = "map: event buffer exhausted"; return NTL_ERR_WORKSPACE; }

@@ -244,10 +244,13 @@ NTL_HD bool make_event(const Hit* hits, const Run& ri, const Run& rj, uint32_t r
 }
 
 // upper bound of the number of events a read with nr accepted contigs can emit
+// (64-bit arithmetic, saturated at MAX_EVENTS_PER_READ + 1: the order key of the pair tally holds the event's ordinal
+// within its read in 24 bits; a read that could emit more is rejected with an explicit error instead of colliding keys)
+enum : uint32_t { MAX_EVENTS_PER_READ = 0xFFFFFFu };
 NTL_HD uint32_t max_events(uint32_t nr, int32_t f) {
     if (nr < 2) return 0;
-    if ((int64_t)nr <= (int64_t)f) return nr * (nr - 1) / 2;
-    return 2 * (nr - 1);
+    const uint64_t n = (int64_t)nr <= (int64_t)f ? (uint64_t)nr * (nr - 1) / 2 : 2ull * (nr - 1);
+    return n > MAX_EVENTS_PER_READ ? MAX_EVENTS_PER_READ + 1u : (uint32_t)n;
 }
 
 // Writes the events of one read in reference order; returns how many were written.

@@ -65,5 +65,11 @@ def map_long_reads(ctx, scaffolds_masked_fa, reads_masked_fa, scaffold_lengths, 
             hits = [MinimizerPositions(None, int(h[1]) & 0x7FFFFFFF, "+" if int(h[1]) >> 31 else "-",
                                        int(h[2]) & 0x7FFFFFFF, "+" if int(h[2]) >> 31 else "-") for h in hs]
             accepted.append(AnchorRun(ids[int(ctg)], hits, len(hits)))
+        if ids[2 * g] == ids[2 * g + 1] and len(accepted) > 1:
+            # both ends of the gap belong to the same scaffold (A+ -> A-): the reference keys its minimizer table, the runs and
+            # the accepted dict by scaffold id (patch:427-442), so it can never see two accepted contigs here and falls back;
+            # the two runs are folded into one entry so that the caller's `len(accepted) != 2` test takes the same branch
+            merged = [h for run in accepted for h in run.hits]
+            accepted = [AnchorRun(ids[2 * g], merged, len(merged))]
         out.append(GapMapping(read, source, target, accepted))
     return out
