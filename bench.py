@@ -63,6 +63,9 @@ def pick_config(args, world):
     if args.scale != 1.0:
         cfg["genome"] = max(200_000, int(cfg["genome"] * args.scale))
         cfg["reads_per_gpu"] = max(2_000_000, int(cfg["reads_per_gpu"] * args.scale))
+    if getattr(args, "reads_per_gpu", None):
+        cfg["reads_per_gpu"] = int(args.reads_per_gpu)
+        cfg["what"] += f" [reads per GPU overridden: {int(args.reads_per_gpu)} bp]"
     cfg["workload"] = (f"{cfg['label']}: {cfg['what']}, 1-200 kbp contigs, reads ~12 kbp lognormal with 4% sub / 3% del / 3% ins, "
                        f"k={cfg['k']} w={cfg['w']} z={Z}{' --sensitive' if cfg['sensitive'] else ''}"
                        + (f" [scaled x{args.scale}]" if args.scale != 1.0 else ""))
@@ -301,7 +304,7 @@ def run_gpu(args, rank, world, local_rank):
     shard_target = world > 1 and (args.shard_target == "always" or (args.shard_target == "auto" and target_bases >= (256 << 20)))
     ctx = Context(local_rank)
     for opt, env in (("cand_c", "NTL_CAND_C"), ("strip_len", "NTL_STRIP_LEN"), ("pipeline_min_bases", "NTL_PIPE_MIN"), ("async", "NTL_ASYNC"),
-                     ("graph", "NTL_GRAPH"), ("resident_chunk_bases", "NTL_RESIDENT_CHUNK")):   # sweeps / profiling only
+                     ("graph", "NTL_GRAPH"), ("resident_chunk_bases", "NTL_RESIDENT_CHUNK"), ("tile", "NTL_TILE")):   # sweeps / profiling only
         if os.environ.get(env):
             ctx.set_option(opt, float(os.environ[env]))
     prm = ctx.params(K, W, Z, 10, 0.0, cfg["sensitive"], False)
@@ -516,6 +519,7 @@ def main():
     ap.add_argument("--impl", default="ntlink_b200", choices=["ntlink_b200", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="default: c2 (configs[2]) up to 4 GPUs, c3 (configs[3]) at 8")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink genome and reads (smoke runs)")
+    ap.add_argument("--reads-per-gpu", type=float, default=None, help="override the read bases per GPU (profiling runs)")
     ap.add_argument("--cpu-window", type=float, default=10e6, help="genome window (bp) of the CPU arm's scale model")
     ap.add_argument("--parity-reads", type=int, default=3000)
     ap.add_argument("--no-cpu", action="store_true")

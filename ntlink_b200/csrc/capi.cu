@@ -183,6 +183,10 @@ int ntl_init(int device, ntl_ctx** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NTL_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return NTL_ERR_CUDA;
+    // The index probes are the one random-access pattern of the path: 16-byte entries of a table that is DRAM-resident at
+    // human scale. With the default 64/128-byte L2 fetch granularity every probe pulls 2+ sectors from DRAM
+    // (profiles/r2_k_lookup_dram_index_ncu_full.txt); 32 bytes halves that. Streaming kernels request whole lines anyway.
+    if (const char* g = getenv("NTL_L2_FETCH")) { if (atoi(g) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)); }
     ntl_ctx* c = new ntl_ctx();
     c->res = new Results();
     c->device = device;
@@ -346,7 +350,10 @@ static int sketch_to_host(ntl_ctx* c, const char* seq, const uint64_t* offsets, 
     Results* R = res_of(c);
     cudaSetDevice(c->device);
     std::vector<uint32_t> bounds;
-    plan_batches(offsets, nseq, c->batch_bases, bounds);
+    // the index is built from ONE device batch: a target larger than the batch size option still goes in one piece as long as
+    // it fits the 32-bit positions of a batch
+    const uint64_t all_bases = nseq ? offsets[nseq] - offsets[0] : 0;
+    plan_batches(offsets, nseq, build_index && all_bases < 3900000000ull ? std::max<uint64_t>(c->batch_bases, all_bases) : c->batch_bases, bounds);
     R->sk_hash.used = R->sk_posf.used = R->sk_off.used = 0;
     if (R->sk_off.reserve(((size_t)nseq + 1) * 8)) { c->err = "pinned alloc failed"; return NTL_ERR_CUDA; }
     uint64_t* seq_off = R->sk_off.at<uint64_t>(0);

@@ -18,6 +18,9 @@ namespace ntl {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    // state of the single-pass scan when the buffer serves as its scratch (scan.cu)
+    uint64_t scan_epoch = 0;
+    void* scan_ready_for = nullptr;
     // grows geometrically; contents are NOT preserved
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
@@ -231,7 +234,14 @@ static __global__ void k_fill_segs(FillSegs s) {
 #pragma unroll
     for (int q = 0; q < 6; q++) {
         uint8_t* p = (uint8_t*)s.p[q];
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n[q]; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint8_t)s.v[q];
+        const uint32_t b = s.v[q] & 0xFFu;
+        if ((((uintptr_t)p | s.n[q]) & 15u) == 0) {                      // aligned segments: 16 bytes per store
+            const uint32_t w = b * 0x01010101u;
+            uint4* p4 = (uint4*)p;
+            for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n[q] / 16; i += (uint64_t)gridDim.x * blockDim.x) p4[i] = make_uint4(w, w, w, w);
+        } else {
+            for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n[q]; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint8_t)b;
+        }
     }
 }
 // Stage timers: every tick/tock pair takes its own pair of CUDA events from a pool that is recycled by collect_timing, so

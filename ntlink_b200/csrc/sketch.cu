@@ -482,9 +482,8 @@ __global__ void k_seq_offsets(const uint32_t* __restrict__ strip_off, const uint
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     const bool bad = call != nullptr && st->err != 0;
     if (q <= nseq) mx_off[q] = bad ? 0u : selbase[strip_off[q]];
-    if (q == 0 && bad) atomicOr(&call->err, CALLERR_SKETCH);
+    if (q == 0 && bad) { atomicOr(&call->err, CALLERR_SKETCH); st->n_mx = 0; }
 }
-__global__ void k_sketch_gate(SketchStatus* __restrict__ st) { if (st->err) st->n_mx = 0; }
 
 // status block + number of strips + number of minimizers -> host-mapped memory
 __global__ void k_publish_sketch(const SketchStatus* __restrict__ st, const uint32_t* __restrict__ nstrips_p,
@@ -709,7 +708,7 @@ retry:
     NTL_CUDA(c, W.selmask.ensure(((size_t)nstrips_max + 1) * 8));
     NTL_CUDA(c, W.strip_seq.ensure(((size_t)nstrips_max + 1) * 4));
     NTL_CUDA(c, W.selbase.ensure(((size_t)nstrips_max + 2) * 4));
-    NTL_CUDA(c, W.gap_head.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.gap_head.ensure(((size_t)nstrips_max + 1) * 4 + 16));
     NTL_CUDA(c, W.gaps.ensure((size_t)gaps_cap * sizeof(GapRec)));
     NTL_CUDA(c, W.extras.ensure((size_t)extras_cap * sizeof(Cand)));
     NTL_CUDA(c, W.has_cand.ensure((size_t)nseq + 1));
@@ -728,7 +727,8 @@ retry:
         fs.p[1] = W.has_cand.p; fs.n[1] = (size_t)nseq + 1; fs.v[1] = 0;
         fs.p[2] = W.packed.p; fs.n[2] = 64; fs.v[2] = 0x44;
         fs.p[3] = W.packed.as<char>() + 64 + total_bases / 2; fs.n[3] = 192; fs.v[3] = 0x44;
-        k_fill_segs<<<std::max<uint32_t>(1, std::min<uint32_t>(div_up((uint64_t)nseq + 1, 256), 148)), 256, 0, c->stream>>>(fs);
+        fs.p[4] = W.gap_head.p; fs.n[4] = (((size_t)nstrips_max + 1) * 4 + 15) & ~(size_t)15; fs.v[4] = 0xFF;          // NONE32
+        k_fill_segs<<<std::max<uint32_t>(1, std::min<uint32_t>(div_up((uint64_t)nstrips_max * 4, 4096), 296)), 256, 0, c->stream>>>(fs);
         c->launches += 1;
     }
 
@@ -737,9 +737,8 @@ retry:
     k_strip_count<<<div_up(nseq, 256), 256, 0, c->stream>>>(d_off, nseq, k, w, S, W.scnt.as<uint32_t>(), nseq_dev);
     c->launches += 2;
     NTL_TRY(exclusive_scan_u32(c, W.scnt.as<uint32_t>(), W.strip_off.as<uint32_t>(), nseq_dev, nseq, W.blocksums));
-    k_fill_u32<<<296, 256, 0, c->stream>>>(W.gap_head.as<uint32_t>(), NONE32, (uint64_t)nstrips_max + 1);
     k_strip_seq<<<div_up(nstrips_max, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), nseq, W.strip_seq.as<uint32_t>());
-    c->launches += 2;
+    c->launches += 1;
     tock(c, T_PACK);
 
     tick(c, T_DENSE);
@@ -823,7 +822,6 @@ emit:
     k_seq_offsets<<<div_up((uint64_t)nseq + 1, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), W.selbase.as<uint32_t>(), nseq,
                                                                         out.mx_off.as<uint32_t>(), st, call_state);
     c->launches += 2;
-    if (call_state) { k_sketch_gate<<<1, 1, 0, c->stream>>>(st); c->launches += 1; }
     tock(c, T_EMIT);
     NTL_CUDA(c, cudaGetLastError());
     return NTL_OK;

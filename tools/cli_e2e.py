@@ -1,60 +1,74 @@
 #!/usr/bin/env python3
-"""Wall time of the drop-in command line on files (the way ntLink's make recipe would call it): FASTA in, the four output
-files out. Shows where a real run spends its time now that the kernels take milliseconds.
+"""T_e2e-file: wall time of the drop-in command line on FILES, the way ntLink's make recipe calls it --
+target FASTA + read FASTA (optionally .gz) in, <p>.n1.scaffold.dot / .pairs.tsv (/ .verbose_mapping.tsv / .paf) out.
 
-    python tools/cli_e2e.py [--gz]"""
+    python tools/cli_e2e.py [--config c1|c2] [--scale 0.25] [--gz] [--gpus N]
+
+Inputs are the bench workloads (generated on the device, written as FASTA to tmpfs before the clock starts)."""
 import argparse
 import contextlib
 import io
 import json
 import os
+import shutil
 import subprocess
 import sys
-import tempfile
 import time
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-
-
-def write_fasta(path, batch):
-    seq, off = batch.seq.tobytes(), batch.offsets
-    with open(path, "wb") as f:
-        for i, n in enumerate(batch.names):
-            f.write(b">" + n.encode() + b"\n" + seq[int(off[i]):int(off[i + 1])] + b"\n")
+sys.path.insert(0, os.path.join(REPO, "oracle"))
 
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c1")
+    ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--gz", action="store_true")
+    ap.add_argument("--gpus", type=int, default=1)
     a = ap.parse_args()
     import bench
-    from ntlink_b200 import pair
-    contigs, reads = bench.make_inputs(0, 1)
-    d = tempfile.mkdtemp(prefix="ntl_cli_")
-    tgt, rd = os.path.join(d, "target.fa"), os.path.join(d, "reads.fa")
-    write_fasta(tgt, contigs)
-    write_fasta(rd, reads)
-    if a.gz:
-        subprocess.check_call(["gzip", "-1", rd])
-        rd += ".gz"
-    bases = int(reads.offsets[-1])
-    for mode, extra in (("pairs + dot only", []), ("+ verbose_mapping.tsv + paf", ["--verbose", "--paf"])):
-        times = []
-        for it in range(3):
-            prefix = os.path.join(d, f"out{it}")
-            argv = ["-p", prefix, "-n", "1", "-s", tgt, "-k", "32", "-w", "100", "-a", "1", "-z", "1000", "-f", "10", "-x", "0", "--pairs",
-                    "--sketch-target", "--reads-fasta", rd, "-t", "8"] + extra
-            t0 = time.perf_counter()
-            with contextlib.redirect_stdout(io.StringIO()):
-                pair.main(argv)
-            times.append(time.perf_counter() - t0)
-            for suffix in (".verbose_mapping.tsv", ".paf"):
-                if os.path.exists(prefix + suffix):
-                    os.remove(prefix + suffix)
-        best = min(times)
-        print(json.dumps({"cli": "python -m ntlink_b200.pair --sketch-target --reads-fasta reads.fa" + (".gz" if a.gz else ""), "outputs": mode,
-                          "read_bases": bases, "wall_s": [round(t, 3) for t in times], "gbp_per_s_best": round(bases / best / 1e9, 3)}), flush=True)
+    import cpu_pipeline as cp
+    from ntlink_b200 import Context, pair, synth
+    args = argparse.Namespace(config=a.config, scale=a.scale)
+    cfg = bench.pick_config(args, 1)
+    cplan, cnames, rplan = bench.plans(cfg, 0)
+    ctx = Context(0)
+    ctx.synth_target_resident(bench.SEED, cplan, cnames)
+    ctx.synth_reads_resident(bench.SEED, rplan)
+    contigs = ctx.resident_download(0, 0, len(cplan), cnames)
+    reads = ctx.resident_download(1, 0, len(rplan), synth.read_names(rplan))
+    ctx.close()
+    d = bench.scratch_dir()
+    try:
+        tgt, rd = os.path.join(d, "target.fa"), os.path.join(d, "reads.fa")
+        cp.write_fasta(tgt, contigs)
+        cp.write_fasta(rd, reads)
+        if a.gz:
+            subprocess.check_call(["gzip", "-1", rd])
+            rd += ".gz"
+        bases = int(reads.offsets[-1])
+        for mode, extra in (("scaffold.dot + pairs.tsv", []), ("+ verbose_mapping.tsv + paf", ["--verbose", "--paf"])):
+            times = []
+            for it in range(3):
+                prefix = os.path.join(d, f"out{it}")
+                argv = ["-p", prefix, "-n", "1", "-s", tgt, "-k", str(cfg["k"]), "-w", str(cfg["w"]), "-a", "1", "-z", "1000", "-f", "10", "-x", "0",
+                        "--pairs", "--sketch-target", "--reads-fasta", rd, "-t", "8"] + extra + (["--sensitive"] if cfg["sensitive"] else [])
+                if a.gpus > 1:
+                    argv += ["--gpus", str(a.gpus)]
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    pair.main(argv)
+                times.append(time.perf_counter() - t0)
+                for suffix in (".verbose_mapping.tsv", ".paf"):
+                    if os.path.exists(prefix + suffix):
+                        os.remove(prefix + suffix)
+            best = min(times)
+            print(json.dumps({"T_e2e_file": "python -m ntlink_b200.pair --sketch-target --reads-fasta reads.fa" + (".gz" if a.gz else ""),
+                              "workload": cfg["workload"], "outputs": mode, "gpus": a.gpus, "read_bases": bases, "target_bases": int(contigs.offsets[-1]),
+                              "wall_s": [round(t, 3) for t in times], "gbp_per_s_best": round(bases / best / 1e9, 3)}), flush=True)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 if __name__ == "__main__":
