@@ -183,10 +183,6 @@ int ntl_init(int device, ntl_ctx** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NTL_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return NTL_ERR_CUDA;
-    // The index probes are the one random-access pattern of the path: 16-byte entries of a table that is DRAM-resident at
-    // human scale. With the default 64/128-byte L2 fetch granularity every probe pulls 2+ sectors from DRAM
-    // (profiles/r2_k_lookup_dram_index_ncu_full.txt); 32 bytes halves that. Streaming kernels request whole lines anyway.
-    if (const char* g = getenv("NTL_L2_FETCH")) { if (atoi(g) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)); }
     ntl_ctx* c = new ntl_ctx();
     c->res = new Results();
     c->device = device;
