@@ -252,7 +252,7 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
     if (!c || !name) return NTL_ERR_ARG;
     if (!strcmp(name, "strip_len")) {
         uint32_t v = (uint32_t)value;
-        if (v < 8 || v > 65536 || (v & 7)) { c->err = "strip_len must be a multiple of 8 in [8, 65536]"; return NTL_ERR_ARG; }
+        if (v != 0 && (v < 8 || v > 65536 || (v & 7))) { c->err = "strip_len must be 0 (automatic) or a multiple of 8 in [8, 65536]"; return NTL_ERR_ARG; }
         c->strip_len = v;
     } else if (!strcmp(name, "cand_c")) {
         if (!(value > 0)) { c->err = "cand_c must be positive"; return NTL_ERR_ARG; }

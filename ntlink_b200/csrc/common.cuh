@@ -151,7 +151,7 @@ struct ntl_ctx {
     ntl::DeviceSketch dsk;                 // sketch of the current batch
     ntl::PinnedBuf h_status;
     // tuning knobs
-    uint32_t strip_len = 256;
+    uint32_t strip_len = 0;                // k-mer positions per thread of the dense pass; 0 = chosen per batch (auto_strip_len)
     double cand_c = 7.0;
     uint64_t batch_bases = 1ull << 30;
     uint64_t pipeline_min_bases = 80ull << 20;   // smallest batch worth pipelining (copy/compute overlap)

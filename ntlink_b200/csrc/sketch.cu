@@ -674,7 +674,10 @@ int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint3
             if (call_state) return NTL_OK;      // deferred: the error bit is set, the caller repeats the call synchronously
         }
     }
-    const uint32_t S = c->strip_len;
+    // Strip length: 256 k-mer positions per thread keeps the k-1 lead-in at ~10 % and gives small batches enough threads;
+    // with wide windows and batches of hundreds of Mbp 768 is ~9 % faster end to end (the select pass stages fewer context
+    // strips per decided strip, the lead-in shrinks), measured on configs[2].
+    const uint32_t S = c->strip_len ? c->strip_len : (w >= 200 && total_bases >= (256ull << 20) ? 768u : 256u);
     double mu = (double)S * c->cand_c / (double)w;
     if (mu > S) mu = S;
     uint32_t cap = (uint32_t)(mu + 6.0 * sqrt(mu) + 8.0);
