@@ -16,7 +16,7 @@ sys.path.insert(0, REPO)
 
 def main():
     from ntlink_b200 import Context
-    import bench
+    import r1_inputs as bench
     contigs, reads = bench.make_inputs(0, 1)
     ctx = Context(0)
     ctx.target_upload(contigs)

@@ -11,7 +11,7 @@ sys.path.insert(0, REPO)
 
 
 def main():
-    import bench
+    import r1_inputs as bench
     from ntlink_b200 import Context
     contigs, reads = bench.make_inputs(0, 1)
     ctx = Context(0)
