@@ -77,6 +77,47 @@ def map_reads(target_fa, target_tsv, reads_fa, prefix, k, w, z, threads, sensiti
     return dt
 
 
+def next_round(verbose_path, agp_path, scaffolds_fa, prefix, k, z, f=10, x=0, a=1, n=1, kind=None):
+    """One later round of ntLink_rounds on the CPU (ntLink_rounds:122-145): the reference's liftover script writes
+    <prefix>.verbose_mapping.tsv, which its pair stage then takes as a checkpoint instead of mapping again
+    (bin/ntlink_pair.py:565-575). Returns (liftover seconds, pair seconds)."""
+    kind = kind or mapper_kind()
+    here = os.path.dirname(REF_PAIR)
+    lift = os.path.join(here, "ntlink_liftover_mappings.py")
+    env = dict(os.environ, PYTHONHASHSEED="0", PYTHONPATH=here + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = prefix + ".verbose_mapping.tsv"
+    for suffix in (".pairs.tsv", f".n{n}.scaffold.dot"):
+        if os.path.exists(prefix + suffix):
+            os.remove(prefix + suffix)
+    t0 = time.perf_counter()
+    if kind == "reference" and os.path.exists(lift):
+        subprocess.check_call([sys.executable, lift, "-m", verbose_path, "-a", agp_path, "-o", out, "-k", str(k)], env=env,
+                              stdout=subprocess.DEVNULL)
+        t1 = time.perf_counter()
+        cmd = [sys.executable, REF_PAIR, "-p", prefix, "-n", str(n), "-m", "unused.tsv", "-s", scaffolds_fa, "-k", str(k), "-a", str(a),
+               "-z", str(z), "-f", str(f), "-x", str(x), "--pairs", "unused_reads.tsv"]
+        r = subprocess.run(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        if r.returncode != 0:
+            raise RuntimeError("CPU checkpoint round failed: " + r.stderr.decode()[-2000:])
+        return t1 - t0, time.perf_counter() - t1
+    # the port, in this process (pair_oracle.py has no command line for the checkpoint path)
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import liftover_oracle
+    import pair_oracle as po
+    with open(verbose_path) as fin, open(agp_path) as fagp:
+        lifted = liftover_oracle.liftover(fin, fagp.readlines(), k)
+    with open(out, "w") as fout:
+        fout.writelines(lifted)
+    t1 = time.perf_counter()
+    lengths = po.read_fasta_lengths(scaffolds_fa)
+    prm = po.default_params(k, z=z, a=a, f=f, x=x, n=n)
+    pairs = po.filter_pairs(po.retally_from_verbose(lifted, lengths, prm), lengths, a)
+    with open(prefix + ".pairs.tsv", "w") as fout:
+        fout.writelines(po.pairs_tsv_lines(pairs))
+    return t1 - t0, time.perf_counter() - t1
+
+
 def outputs(prefix, n=1):
     "bytes of the files the mapper wrote (missing file -> None)"
     out = {}
