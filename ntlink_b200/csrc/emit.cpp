@@ -352,12 +352,67 @@ bool ntl_pool_release(void* p) {
     return true;
 }
 
+
+// ---- BGZF (bgzip) input: independent gzip members of <= 64 KiB whose compressed size is in the header, so the members
+// of the next stretch of the file are located by walking the headers and inflated by several threads straight into a
+// window of decompressed text that the parallel FASTA / FASTQ parser then treats like a mapped plain file.
+// Ordinary single-stream gzip has no such structure and stays on zlib's sequential gzread.
+struct BgzfBlock { uint64_t coff; uint32_t bsize, hdr, isize; uint64_t out; };
+struct BgzfSource {
+    int fd = -1;
+    const unsigned char* cmap = nullptr;   // the compressed file, mapped read-only
+    size_t csize = 0, cpos = 0;            // file size, first block not walked yet
+    char* w = nullptr;                     // window of decompressed bytes [wbase, wbase + wlen)
+    size_t wcap = 0, wlen = 0;
+    uint64_t wbase = 0;
+    bool done = false, bad = false;
+    int threads = 1;
+
+    ~BgzfSource() {
+        free(w);
+        if (cmap) munmap((void*)cmap, csize);
+        if (fd >= 0) ::close(fd);
+    }
+    // header of the member at p (n bytes available): total member size and payload offset; false = not a BGZF member
+    static bool parse_header(const unsigned char* p, size_t n, uint32_t& bsize, uint32_t& hdr) {
+        if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return false;
+        const uint32_t xlen = p[10] | (uint32_t)p[11] << 8;
+        if (12 + (size_t)xlen > n) return false;
+        bsize = 0;
+        for (uint32_t at = 12; at + 4 <= 12 + xlen;) {
+            const uint32_t slen = p[at + 2] | (uint32_t)p[at + 3] << 8;
+            if (p[at] == 'B' && p[at + 1] == 'C' && slen == 2 && at + 6 <= 12 + xlen) bsize = (p[at + 4] | (uint32_t)p[at + 5] << 8) + 1;
+            at += 4 + slen;
+        }
+        if (!bsize) return false;
+        size_t h = 12 + xlen;
+        if (p[3] & 8) { while (h < n && p[h]) h++; h++; }          // FNAME
+        if (p[3] & 16) { while (h < n && p[h]) h++; h++; }         // FCOMMENT
+        if (p[3] & 2) h += 2;                                      // FHCRC
+        if (h + 8 > bsize) return false;
+        hdr = (uint32_t)h;
+        return true;
+    }
+    bool open(int file, size_t size, int nthreads) {
+        void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, file, 0);
+        if (m == MAP_FAILED) return false;
+        madvise(m, size, MADV_SEQUENTIAL);
+        fd = file; cmap = (const unsigned char*)m; csize = size; threads = std::max(1, nthreads);
+        return true;
+    }
+    // make [start, start + need) of the decompressed stream available at w (wbase becomes start); fewer bytes only at
+    // the end of the file (done). false = corrupt input or out of memory.
+    bool ensure(uint64_t start, uint64_t need);
+};
+
 struct ntl_seqfile {
+    BgzfSource* bg = nullptr;    // BGZF input, inflated in parallel
+    std::string path;
     gzFile gz = nullptr;         // gzip input (or stdin)
     int fd = -1;                 // plain file
     std::vector<char> buf;
     size_t pos = 0, len = 0;
-    bool eof = false;
+    bool eof = false, io_error = false;
     std::string carry;           // assembled line that straddled two blocks
     std::string pending;         // header line read ahead
     bool have_pending = false;
@@ -376,7 +431,13 @@ struct ntl_seqfile {
             do { n = (long)::read(fd, buf.data(), buf.size()); } while (n < 0 && errno == EINTR);
         } else {
             n = gzread(gz, buf.data(), (unsigned)buf.size());
+            if (n <= 0) {                          // a damaged or truncated gzip stream is an error, not the end of the file
+                int errnum = Z_OK;
+                gzerror(gz, &errnum);
+                if (n < 0 || (errnum != Z_OK && errnum != Z_STREAM_END)) io_error = true;
+            }
         }
+        if (n < 0 && fd >= 0) io_error = true;
         if (n <= 0) { eof = true; pos = len = 0; return false; }
         pos = 0; len = (size_t)n;
         return true;
@@ -555,30 +616,109 @@ void run_threads(size_t n, F&& body) {
     for (auto& x : th) x.join();
 }
 
+}  // namespace
+
+bool BgzfSource::ensure(uint64_t start, uint64_t need) {
+    if (bad || start < wbase || start > wbase + wlen) return false;
+    if (start > wbase) {                                           // drop what the parser has consumed
+        const size_t drop = (size_t)(start - wbase);
+        memmove(w, w + drop, wlen - drop);
+        wlen -= drop; wbase = start;
+    }
+    while (!done && wlen < need) {
+        // walk the headers of the next stretch: enough members for what is missing, at least 32 MiB of output per pass
+        const uint64_t goal = std::max<uint64_t>(need - wlen, 32u << 20);
+        std::vector<BgzfBlock> blk;
+        uint64_t out = 0;
+        while (cpos < csize && out < goal) {
+            BgzfBlock b;
+            if (!parse_header(cmap + cpos, csize - cpos, b.bsize, b.hdr) || cpos + b.bsize > csize) { bad = true; return false; }
+            const unsigned char* tail = cmap + cpos + b.bsize - 4;
+            b.isize = tail[0] | (uint32_t)tail[1] << 8 | (uint32_t)tail[2] << 16 | (uint32_t)tail[3] << 24;
+            b.coff = cpos; b.out = out;
+            out += b.isize;
+            cpos += b.bsize;
+            blk.push_back(b);
+        }
+        if (cpos >= csize) done = true;
+        if (wlen + out + 64 > wcap) {
+            size_t c = wcap ? wcap : (64u << 20);
+            while (c < wlen + out + 64) c += c / 2;
+            char* q = (char*)realloc(w, c);
+            if (!q) { bad = true; return false; }
+            w = q; wcap = c;
+        }
+        const size_t nt = (size_t)std::min<size_t>((size_t)threads, std::max<size_t>(1, blk.size() / 16));
+        std::vector<int> failed(nt, 0);
+        char* dst = w + wlen;
+        run_threads(nt, [&](size_t t) {
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) { failed[t] = 1; return; }
+            const size_t b0 = blk.size() * t / nt, b1 = blk.size() * (t + 1) / nt;
+            for (size_t i = b0; i < b1 && !failed[t]; i++) {
+                const BgzfBlock& b = blk[i];
+                const unsigned char* src = cmap + b.coff;
+                zs.next_in = (Bytef*)(src + b.hdr);
+                zs.avail_in = b.bsize - b.hdr - 8;
+                zs.next_out = (Bytef*)(dst + b.out);
+                zs.avail_out = b.isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                const unsigned char* c = src + b.bsize - 8;
+                const uint32_t crc = c[0] | (uint32_t)c[1] << 8 | (uint32_t)c[2] << 16 | (uint32_t)c[3] << 24;
+                if (rc != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)(dst + b.out), b.isize) != crc)
+                    failed[t] = 1;
+                inflateReset(&zs);
+            }
+            inflateEnd(&zs);
+        });
+        for (int x : failed) if (x) { bad = true; return false; }
+        wlen += (size_t)out;
+    }
+    return true;
+}
+
+namespace {
+
 // Parallel FASTA batch straight from the mapped file: pass 1 finds the records of every segment, pass 2 copies the
 // sequence lines to their final place. Returns 1 = batch produced, 0 = not applicable (the caller uses the sequential
 // reader from f->ppos), -1 = out of memory.
 int read_parallel(ntl_seqfile* f, uint64_t max_bases, GrowBuf& seq, GrowBuf& names, std::vector<uint64_t>& offs,
                   std::vector<uint64_t>& noffs) {
     const off_t start = f->ppos;
-    if (start >= f->fsize) return 1;                               // end of file: empty batch
-    if (!f->map) {
-        void* m = mmap(nullptr, (size_t)f->fsize, PROT_READ, MAP_PRIVATE, f->fd, 0);
-        if (m == MAP_FAILED) { f->parallel = false; return 0; }
-        f->map = (const char*)m;
-        madvise(m, (size_t)f->fsize, MADV_SEQUENTIAL);
+    const bool bz = f->bg != nullptr;
+    const uint64_t margin = 32u << 20;                             // look-ahead past the batch: the record that crosses its end
+    if (!bz) {
+        if (start >= f->fsize) return 1;                           // end of file: empty batch
+        if (!f->map) {
+            void* m = mmap(nullptr, (size_t)f->fsize, PROT_READ, MAP_PRIVATE, f->fd, 0);
+            if (m == MAP_FAILED) { f->parallel = false; return 0; }
+            f->map = (const char*)m;
+            madvise(m, (size_t)f->fsize, MADV_SEQUENTIAL);
+        }
     }
-    const char* raw = f->map + start;
-    uint64_t want = max_bases ? max_bases + max_bases / 16 + (16u << 20) : (uint64_t)(f->fsize - start);
+    // the text the parser sees: raw[0, limit); final = nothing follows it
+    const char* raw = nullptr;
+    uint64_t limit = 0;
+    bool final = true;
+    auto view = [&](uint64_t need) -> bool {
+        if (!bz) { raw = f->map + start; limit = (uint64_t)(f->fsize - start); return true; }
+        if (!f->bg->ensure((uint64_t)start, std::min<uint64_t>(need, 1ull << 60) + margin)) return false;
+        raw = f->bg->w; limit = f->bg->wlen; final = f->bg->done;
+        return true;
+    };
+    uint64_t want = max_bases ? max_bases + max_bases / 16 + (16u << 20) : (bz ? 1ull << 60 : (uint64_t)(f->fsize - start));
+    if (!view(want)) return -1;
+    if (limit == 0 && final) return 1;
     size_t n = 0, cut = 0;
     for (;;) {
-        n = (size_t)std::min<uint64_t>(want, (uint64_t)(f->fsize - start));
-        if (start + (off_t)n >= f->fsize) { cut = n; break; }       // the rest of the file: every record is complete
+        n = (size_t)std::min<uint64_t>(want, limit);
+        if (final && n >= limit) { cut = n; break; }                // the rest of the file: every record is complete
         // cut at the last record start in the range; a range without one (a record larger than the range) grows
         size_t q = n;
         cut = 0;
         if (f->fastq) {
-            const size_t total = (size_t)(f->fsize - start);
+            const size_t total = (size_t)limit;
             for (size_t window = 4u << 20; cut == 0; window *= 4) {
                 size_t p = n > window ? n - window : 0;
                 p = next_fastq_start(raw, p, total);
@@ -593,6 +733,7 @@ int read_parallel(ntl_seqfile* f, uint64_t max_bases, GrowBuf& seq, GrowBuf& nam
             }
             if (cut > 0) break;
             want *= 2;
+            if (!view(want)) return -1;
             continue;
         }
         while (q > 1) {
@@ -604,11 +745,12 @@ int read_parallel(ntl_seqfile* f, uint64_t max_bases, GrowBuf& seq, GrowBuf& nam
         }
         if (cut > 0) break;
         want *= 2;
+        if (!view(want)) return -1;
     }
     // segments at record starts
     std::vector<size_t> bounds;
     bounds.push_back(0);
-    const size_t file_end = (size_t)(f->fsize - start);
+    const size_t file_end = (size_t)limit;
     for (int t = 1; t < f->threads; t++) {
         const size_t at = (size_t)((uint64_t)cut * t / f->threads);
         const size_t b = f->fastq ? next_fastq_start(raw, at, cut) : next_record_start(raw, at, cut);
@@ -687,9 +829,32 @@ int ntl_seqfile_open(const char* path, ntl_seqfile** out) {
         if (fd < 0) { delete f; return NTL_ERR_ARG; }
         unsigned char magic[2] = {0, 0};
         const long got = (long)::pread(fd, magic, 2, 0);
+        const char* env = getenv("NTL_READER_THREADS");
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nthreads = env ? atoi(env) : (int)std::max(1u, std::min(8u, hw / 2));
+        f->path = path;
         if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-            ::close(fd);
-            f->gz = gzopen(path, "rb");
+            // bgzip output (BGZF) is inflated by several threads; any other gzip goes through zlib's sequential reader
+            unsigned char head[64];
+            const long hn = (long)::pread(fd, head, sizeof head, 0);
+            uint32_t bsize = 0, hdr = 0;
+            struct stat sb;
+            if (nthreads > 1 && hn >= 18 && BgzfSource::parse_header(head, (size_t)hn, bsize, hdr) && fstat(fd, &sb) == 0 &&
+                S_ISREG(sb.st_mode) && sb.st_size > 0) {
+                f->bg = new BgzfSource();
+                if (f->bg->open(fd, (size_t)sb.st_size, env ? nthreads : (int)std::max(2u, std::min(16u, hw / 2))) && f->bg->ensure(0, 1) && f->bg->wlen > 0 &&
+                    (f->bg->w[0] == '>' || f->bg->w[0] == '@')) {
+                    f->parallel = true; f->threads = nthreads; f->ppos = 0; f->fastq = f->bg->w[0] == '@';
+                } else {                                   // not something the parallel parser takes: sequential gzip
+                    if (f->bg->fd < 0) ::close(fd);
+                    delete f->bg;
+                    f->bg = nullptr;
+                    f->gz = gzopen(path, "rb");
+                }
+            } else {
+                ::close(fd);
+                f->gz = gzopen(path, "rb");
+            }
         } else {
             f->fd = fd;
 #ifdef POSIX_FADV_SEQUENTIAL
@@ -698,15 +863,13 @@ int ntl_seqfile_open(const char* path, ntl_seqfile** out) {
             // a regular file that starts like FASTA is parsed by several threads (ntl_seqfile_read falls back to the
             // sequential reader the moment it meets something that is not plain FASTA)
             struct stat sb;
-            const char* env = getenv("NTL_READER_THREADS");
-            const unsigned hw = std::thread::hardware_concurrency();
-            f->threads = env ? atoi(env) : (int)std::max(1u, std::min(8u, hw / 2));
+            f->threads = nthreads;
             if (f->threads > 1 && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && got >= 1 && (magic[0] == '>' || magic[0] == '@')) {
                 f->parallel = true; f->fsize = sb.st_size; f->ppos = 0; f->fastq = magic[0] == '@';
             }
         }
     }
-    if (!f->gz && f->fd < 0) { delete f; return NTL_ERR_ARG; }
+    if (!f->gz && f->fd < 0 && !f->bg) { delete f; return NTL_ERR_ARG; }
     if (f->gz) gzbuffer(f->gz, 1u << 20);
     *out = f;
     return NTL_OK;
@@ -736,7 +899,15 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_
         // not plain FASTA after all: continue sequentially from the first unread record
         ntl_free(seq.p); ntl_free(names.p); seq = GrowBuf(); names = GrowBuf();
         offs.assign(1, 0); noffs.assign(1, 0);
-        lseek(f->fd, f->ppos, SEEK_SET);
+        if (f->bg) {                                   // BGZF text that is not plain FASTA / 4-line FASTQ: zlib reads on from there
+            delete f->bg;
+            f->bg = nullptr;
+            f->gz = gzopen(f->path.c_str(), "rb");
+            if (f->gz) gzbuffer(f->gz, 1u << 20);
+            if (!f->gz || gzseek(f->gz, (z_off_t)f->ppos, SEEK_SET) < 0) return NTL_ERR_ARG;
+        } else {
+            lseek(f->fd, f->ppos, SEEK_SET);
+        }
         f->pos = f->len = 0; f->eof = false; f->have_pending = false;
     }
     // plain files: what is left of the file bounds the batch, so the buffer never has to grow
@@ -782,7 +953,7 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_
     const uint32_t nseq = (uint32_t)(offs.size() - 1);
     uint64_t* o = (uint64_t*)malloc(offs.size() * 8);
     uint64_t* no = (uint64_t*)malloc(noffs.size() * 8);
-    if (!ok || !o || !no || !seq.reserve(seq.n + 64) || !names.reserve(names.n + 1)) {
+    if (!ok || f->io_error || !o || !no || !seq.reserve(seq.n + 64) || !names.reserve(names.n + 1)) {
         ntl_free(seq.p); ntl_free(names.p); free(o); free(no);
         return NTL_ERR_ARG;
     }
@@ -796,6 +967,7 @@ int ntl_seqfile_read(ntl_seqfile* f, uint64_t max_bases, char** seq_out, uint64_
 void ntl_seqfile_close(ntl_seqfile* f) {
     if (!f) return;
     if (f->gz) gzclose(f->gz);
+    delete f->bg;
     if (f->map) munmap((void*)f->map, (size_t)f->fsize);
     if (f->fd >= 0) ::close(f->fd);
     delete f;
@@ -919,6 +1091,7 @@ int ntl_verbose_read(ntl_verbose_file* f, uint64_t max_hits, int share_repeated,
     while (!f->done) {
         if (f->have_pend) { line.swap(f->pend_line); f->have_pend = false; }
         else if (f->src->getline(lp, ll)) line.assign(lp, ll);
+        else if (f->src->io_error) { f->err = "damaged or truncated gzip input"; return NTL_ERR_ARG; }
         else { f->done = true; break; }
         // line.strip().split('\t') -> exactly 4 fields (pair:449)
         size_t b = 0, e = line.size();
@@ -1023,7 +1196,11 @@ int ntl_tsv_read(ntl_tsv_file* f, uint64_t max_mx, ntl_tsv_out* out) {
     const char* lp = nullptr;
     size_t ll = 0;
     while (!f->done && !(max_mx && hash.size() >= max_mx)) {
-        if (!f->src->getline(lp, ll)) { f->done = true; break; }
+        if (!f->src->getline(lp, ll)) {
+            if (f->src->io_error) { f->err = "damaged or truncated gzip input"; return NTL_ERR_ARG; }
+            f->done = true;
+            break;
+        }
         const char* b = lp;
         const char* e = lp + ll;
         while (b < e && (unsigned char)*b <= ' ') b++;

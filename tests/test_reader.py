@@ -181,3 +181,49 @@ def test_parallel_fastq_reader_equals_sequential(tmp_path, variant):
             assert par_recs == seq_recs
             if variant in ("plain", "crlf", "no_final_newline", "blank_lines"):
                 assert par_sizes == seq_sizes
+
+
+@pytest.mark.parametrize("kind,block", [("fasta", 65280), ("fasta", 900), ("fastq", 65280), ("fastq", 1500), ("fastq_fasta_tail", 4000)])
+def test_bgzf_input_is_inflated_in_parallel(tmp_path, kind, block):
+    """bgzip (BGZF) files: members located by their headers, inflated by several threads, parsed by the parallel parser;
+    same records as the plain file and as zlib's sequential reader, same batch cuts as the plain file"""
+    import gzip as gz
+    rng = np.random.default_rng(block)
+    if kind == "fasta":
+        text = make_text(rng, 4000, False, 60)
+    else:
+        text = fastq_text(rng, 3000)
+        if kind == "fastq_fasta_tail":
+            text += make_text(rng, 40, False, 60)
+    plain = os.path.join(str(tmp_path), "p.txt")
+    with open(plain, "w", newline="") as fout:
+        fout.write(text)
+    bz = os.path.join(str(tmp_path), "p.bgz.gz")
+    util.write_bgzf(bz, text.encode(), block, eof_marker=(block != 900))
+    assert gz.open(bz, "rb").read() == text.encode()                 # a valid multi-member gzip file
+    want = [(n, s.encode()) for n, s in reference_parse(text)]
+    for max_bases in (0, 150_000, 2_500):
+        one, _ = _records(bz, max_bases, 1)                          # one thread: zlib's gzread
+        assert one == want
+        plain_recs, plain_sizes = _records(plain, max_bases, 4)
+        for threads in (2, 6):
+            recs, sizes = _records(bz, max_bases, threads)
+            assert recs == want
+            if kind != "fastq_fasta_tail":
+                assert sizes == plain_sizes
+
+
+def test_bgzf_corruption_is_an_error(tmp_path):
+    rng = np.random.default_rng(9)
+    text = make_text(rng, 3000, False, 60).encode()
+    path = os.path.join(str(tmp_path), "bad.fa.gz")
+    util.write_bgzf(path, text, 20000)
+    raw = bytearray(open(path, "rb").read())
+    raw[len(raw) // 2] ^= 0x55                                       # somewhere inside a member of the middle of the file
+    open(path, "wb").write(bytes(raw))
+    os.environ["NTL_READER_THREADS"] = "4"
+    try:
+        with pytest.raises(Exception):
+            api.read_sequences(path)
+    finally:
+        del os.environ["NTL_READER_THREADS"]

@@ -223,3 +223,23 @@ def load_fasta_batch(path):
         offs[1:] = np.cumsum([len(p) for p in parts])
     seq = np.frombuffer("".join(parts).encode(), dtype=np.uint8)
     return names, seq, offs
+
+
+def write_bgzf(path, data, block=65280, eof_marker=True):
+    "bgzip-style file: independent gzip members of <= `block` input bytes with the BC extra field (SAM spec 4.1)"
+    import struct
+    import zlib
+
+    def member(chunk):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        payload = co.compress(chunk) + co.flush()
+        bsize = 18 + len(payload) + 8
+        assert bsize <= 65536
+        return (b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + payload +
+                struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+    with open(path, "wb") as fout:
+        for i in range(0, len(data), block):
+            fout.write(member(data[i:i + block]))
+        if eof_marker:
+            fout.write(member(b""))
