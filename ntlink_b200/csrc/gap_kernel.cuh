@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(GAP_WARPS * 32) k_gap(const uint32_t* __restri
     __shared__ RollEntry tbl_s[ROLL_TABLE_ENTRIES];
     __shared__ uint64_t sm_h[GAP_WARPS][GAP_TILE];
     __shared__ uint8_t sm_f[GAP_WARPS][GAP_TILE];
+    __shared__ uint64_t sm_gm[GAP_WARPS][GAP_TILE / 8];     // minimum of every group of 8 hashed positions ...
+    __shared__ uint16_t sm_ga[GAP_WARPS][GAP_TILE / 8];     // ... and its rightmost position
     for (uint32_t i = threadIdx.x; i < ROLL_TABLE_ENTRIES; i += blockDim.x) tbl_s[i] = tbl_g[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(GAP_WARPS * 32) k_gap(const uint32_t* __restri
     const uint32_t w = P.w, k = P.k;
     uint64_t* H = sm_h[wv];
     uint8_t* F = sm_f[wv];
+    uint64_t* GM = sm_gm[wv];
+    uint16_t* GA = sm_ga[wv];
     for (uint32_t id = blockIdx.x * GAP_WARPS + wv; id < ng; id += gridDim.x * GAP_WARPS) {
         const GapRec g = gaps[id];
         if (g.max_out == 0) continue;
@@ -84,16 +88,37 @@ __global__ void __launch_bounds__(GAP_WARPS * 32) k_gap(const uint32_t* __restri
                     process_strip<true>(packed, gseq, base + pa, pb - pa, k, tbl_s, 1, 0u, te);
                 }
                 __syncwarp();
+                // minima of aligned groups of 8 positions: a window then costs ~w/8 + 14 probes instead of w
+                for (uint32_t gi = lane; gi * 8 < npt; gi += 32) {
+                    const uint32_t q0 = gi * 8, q1 = min(npt, q0 + 8);
+                    uint64_t m = H[q0];
+                    uint32_t a = q0;
+                    for (uint32_t q = q0 + 1; q < q1; q++) {
+                        const uint64_t hv = H[q];
+                        if (hv <= m) { m = hv; a = q; }
+                    }
+                    GM[gi] = m; GA[gi] = (uint16_t)a;
+                }
+                __syncwarp();
                 for (uint32_t j0 = wb; j0 < we; j0 += 32) {
                     const uint32_t j = j0 + lane;
                     uint32_t amin = NONE32;
                     uint64_t hmin = 0;
                     if (j < we) {
-                        const uint32_t o = j - wb;
+                        const uint32_t o = j - wb, end = o + w;             // window = hashed positions [o, end)
                         hmin = H[o]; amin = o;
-                        for (uint32_t q = 1; q < w; q++) {
-                            const uint64_t hv = H[o + q];
-                            if (hv <= hmin) { hmin = hv; amin = o + q; }
+                        uint32_t q = o + 1;
+                        for (; q < end && (q & 7u); q++) {                  // up to the next group boundary
+                            const uint64_t hv = H[q];
+                            if (hv <= hmin) { hmin = hv; amin = q; }
+                        }
+                        for (; q + 8 <= end; q += 8) {                      // whole groups
+                            const uint64_t hv = GM[q >> 3];
+                            if (hv <= hmin) { hmin = hv; amin = GA[q >> 3]; }
+                        }
+                        for (; q < end; q++) {                              // the rest
+                            const uint64_t hv = H[q];
+                            if (hv <= hmin) { hmin = hv; amin = q; }
                         }
                         amin += base;                                   // sequence position
                     }

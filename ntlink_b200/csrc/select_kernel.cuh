@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_MINB) k_select(const uint64_t
     // staged candidates {h0.lo, h0.hi, valid-k-mer index, staged strip}: scap entries of dynamic shared memory, sized by
     // the host from the expected candidate density so that as many blocks as possible are resident (the kernel waits on
     // global loads while staging; more resident blocks hide that)
-    extern __shared__ uint4 sh_c[];
+    extern __shared__ uint4 sh_c[];               // {h0.lo, h0.hi, valid-k-mer index, staged strip}
     __shared__ uint32_t sh_off[SEL_NL + 1];       // compact offset of every staged strip
     __shared__ uint32_t sh_cnt[SEL_NL];
     __shared__ uint32_t sh_q[SEL_NL], sh_fs[SEL_NL], sh_es[SEL_NL], sh_idx0[SEL_NL], sh_n[SEL_NL], sh_np[SEL_NL];
@@ -120,28 +120,25 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_MINB) k_select(const uint64_t
     __syncthreads();
 
     const uint32_t w = P.w;
-    const int64_t W1 = (int64_t)w - 1;
     if (staged) {
         const uint32_t e_begin = sh_off[b0 - l0], e_end = sh_off[b1 - l0];
-        const int64_t first_idx = V.vbase[l0], end_idx = V.vbase[l1];   // valid k-mers covered by the staged strips
+        const uint32_t first_idx = V.vbase[l0], end_idx = V.vbase[l1];   // valid k-mers covered by the staged strips
         const int32_t w32 = (int32_t)w, W1s = w32 - 1;
         // Uniform trip count for the whole block and explicit reconvergence (__syncwarp) after each scan: the scans
         // have data-dependent lengths, and without the barriers the lanes of a warp run the long tail below one
-        // small group at a time.
+        // small group at a time. Positions inside a sequence are below 2^31 (POS_MASK), so the window arithmetic is 32-bit.
         for (uint32_t eb = e_begin; eb < e_end; eb += SEL_THREADS) {
             const uint32_t e = eb + tid;
             const bool act = e < e_end;
-            uint4 me = make_uint4(0, 0, 0, 0);
-            uint32_t t = 0, e_lo = 0, e_hi = 0;
+            uint32_t idxu = 0, t = 0, e_lo = 0, e_hi = 0;
+            uint64_t val = 0;
             if (act) {
-                me = sh_c[e];
-                t = me.w;
+                const uint4 me = sh_c[e];
+                val = ((uint64_t)me.y << 32) | me.x; idxu = me.z; t = me.w;
                 const uint32_t fs0 = sh_fs[t], es0 = sh_es[t];
                 e_lo = sh_off[(fs0 > l0 ? fs0 : l0) - l0];               // staged candidates of the same sequence
                 e_hi = sh_off[(es0 < l1 ? es0 : l1) - l0];
             }
-            const uint64_t val = ((uint64_t)me.y << 32) | me.x;
-            const uint32_t idxu = me.z;
             // left: first strictly smaller value (single-exit loop)
             int32_t A32 = -1;
             {
@@ -151,8 +148,8 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_MINB) k_select(const uint64_t
                     p--;
                     const uint4 cp = sh_c[p];
                     const int32_t d = (int32_t)(idxu - cp.z);
-                    const bool far = d >= w32;
                     const bool smaller = (((uint64_t)cp.y << 32) | cp.x) < val;
+                    const bool far = d >= w32;
                     if (far | smaller) { A32 = far ? W1s : d - 1; go = false; }
                     else go = p > e_lo;
                 }
@@ -166,8 +163,8 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_MINB) k_select(const uint64_t
                 while (go) {
                     const uint4 cp = sh_c[p];
                     const int32_t d = (int32_t)(cp.z - idxu);
-                    const bool far = d >= w32;
                     const bool smaller = (((uint64_t)cp.y << 32) | cp.x) <= val;
+                    const bool far = d >= w32;
                     if (far | smaller) { B32 = far ? W1s : d - 1; go = false; }
                     else { p++; go = p < e_hi; }
                 }
@@ -176,24 +173,24 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_MINB) k_select(const uint64_t
             if (!act) continue;
             const uint32_t s = l0 + t, j = e - sh_off[t];
             const uint32_t fs = sh_fs[t], es = sh_es[t];
-            const int64_t idx0 = sh_idx0[t], n = sh_n[t];
-            const int64_t idx = idxu, rel = idx - idx0;
+            const uint32_t idx0 = sh_idx0[t];
+            const int32_t n = (int32_t)sh_n[t], rel = (int32_t)(idxu - idx0);
             bool need_fallback = false;
-            int64_t A = A32, B = B32;
+            int32_t A = A32, B = B32;
             if (A32 < 0) {
                 if (fs >= l0) A = rel;                                   // the sequence starts inside the staged range
-                else if (idx - first_idx >= W1) A = W1;                  // everything earlier is out of reach
+                else if (idxu - first_idx >= (uint32_t)W1s) A = W1s;     // everything earlier is out of reach
                 else need_fallback = true;
             }
             // the immediate right neighbour bounds the candidate-free stretch
             uint32_t gap_len = 0, gap_end = 0;
             bool gap_known = true;
             if (e + 1 < e_hi) gap_len = sh_c[e + 1].z - idxu - 1;
-            else if (es <= l1) { gap_len = (uint32_t)(idx0 + n - 1 - idx); gap_end = sh_np[t]; }
+            else if (es <= l1) { gap_len = (uint32_t)(n - 1 - rel); gap_end = sh_np[t]; }
             else gap_known = false;
             if (B32 < 0) {
-                if (es <= l1) B = idx0 + n - 1 - idx;                    // the sequence ends inside the staged range
-                else if (end_idx - idx > W1) B = W1;
+                if (es <= l1) B = n - 1 - rel;                           // the sequence ends inside the staged range
+                else if (end_idx - idxu > (uint32_t)W1s) B = W1s;
                 else need_fallback = true;
             }
             const uint64_t gid = (uint64_t)s * V.cap + j;
@@ -202,8 +199,8 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_MINB) k_select(const uint64_t
                 const SelectResult r = select_candidate(V, s, j, fs, es, w, sh_np[t]);
                 selected = r.selected; gap_len = r.gap_len; gap_end = r.gap_end;
             } else {
-                int64_t lo_w = rel - W1; if (lo_w < 0) lo_w = 0; if (rel - A > lo_w) lo_w = rel - A;
-                int64_t hi_w = rel; if (n - (int64_t)w < hi_w) hi_w = n - (int64_t)w; if (rel + B - W1 < hi_w) hi_w = rel + B - W1;
+                const int32_t lo_w = max(0, max(rel - W1s, rel - A));
+                const int32_t hi_w = min(rel, min(n - w32, rel + B - W1s));
                 selected = lo_w <= hi_w;
                 if (gap_len >= w && e + 1 < e_hi) {                      // position of the neighbour that ends the stretch
                     const uint32_t t2 = sh_c[e + 1].w;
