@@ -263,6 +263,8 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
         c->copy_threads = (int)value;
     } else if (!strcmp(name, "tile")) {
         c->tile_mode = value != 0.0;
+    } else if (!strcmp(name, "small")) {
+        c->small_mode = value != 0.0;
     } else if (!strcmp(name, "graph")) {
         c->graph_mode = value != 0.0;
     } else if (!strcmp(name, "pipeline_min_bases")) {
@@ -1307,6 +1309,7 @@ int ntl_get_stat(ntl_ctx* c, const char* name, double* value) {
     else if (!strcmp(name, "graph_launches")) *value = (double)c->n_graph_launches;
     else if (!strcmp(name, "graph_failures")) *value = (double)c->n_graph_failures;
     else if (!strcmp(name, "tile_batches")) *value = (double)c->n_tile_batches;
+    else if (!strcmp(name, "small_batches")) *value = (double)c->n_small_batches;
     else if (!strcmp(name, "tile_fallbacks")) *value = (double)c->n_tile_fallbacks;
     else { c->err = std::string("unknown stat ") + name; return NTL_ERR_ARG; }
     return NTL_OK;

@@ -175,7 +175,7 @@ __device__ __forceinline__ uint4 tbl_fetch(const unsigned char* tbl_s, uint32_t 
 }
 
 // generic block (8 steps) with bounds and validity checks; identical to the slow branch of process_strip
-template <class Emit>
+template <bool ALL = false, class Emit>
 __device__ __forceinline__ void generic_block(H32& h, uint32_t wi, uint32_t wo, int32_t t, int32_t lead, int32_t T, int32_t k,
                                               int32_t& last_bad, uint32_t& nv, uint32_t p0, uint32_t tau_hi,
                                               const unsigned char* tbl_s, uint32_t lanebase, Emit& emit) {
@@ -189,7 +189,7 @@ __device__ __forceinline__ void generic_block(H32& h, uint32_t wi, uint32_t wo, 
         if (s >= lead && s < T && s - last_bad >= k) {
             const uint64_t fh = ((uint64_t)h.fhi << 32) | h.flo, rh = ((uint64_t)h.rhi << 32) | h.rlo;
             const uint64_t h0 = fh + rh;
-            if ((uint32_t)(h0 >> 32) < tau_hi) emit(h0, p0 + (uint32_t)(s - lead), fh <= rh, nv);
+            if (ALL || (uint32_t)(h0 >> 32) < tau_hi) emit(h0, p0 + (uint32_t)(s - lead), fh <= rh, nv);
             nv++;
         }
     }
@@ -209,7 +209,8 @@ __device__ __forceinline__ void pick5(const uint4 A, const uint4 B, uint32_t r, 
 // warp work on strips that are 128 bytes apart, so every load instruction costs 32 L1 wavefronts whatever its
 // width -- 16-byte loads cut the wavefront count (the limiter of this kernel before) by 4x compared to words.
 // `packed` must be preceded by one readable 16-byte chunk (the leaving stream starts k bases before the strip).
-template <class Emit>
+// ALL = true: every valid k-mer is handed to the emitter (the dense-mode kernel for small windows), tau_hi is ignored.
+template <bool ALL = false, class Emit>
 __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict__ packed, uint64_t gseq, uint32_t p0, uint32_t n,
                                                       uint32_t k, const unsigned char* tbl_s, uint32_t lanebase,
                                                       uint32_t tau_hi, Emit& emit) {
@@ -284,12 +285,12 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
                     roll32(h, tbl_fetch(tbl_s, (j & 1) ? co : ce, lanebase, 0x7604u | ((uint32_t)(j >> 1) << 4)));
                     const uint64_t fh = ((uint64_t)h.fhi << 32) | h.flo, rh = ((uint64_t)h.rhi << 32) | h.rlo;
                     const uint64_t h0 = fh + rh;
-                    emit.push((uint32_t)(h0 >> 32) < tau_hi, h0, pos0 + j, fh <= rh, nv + j);
+                    emit.push(ALL || (uint32_t)(h0 >> 32) < tau_hi, h0, pos0 + j, fh <= rh, nv + j);
                 }
                 emit.flush_block();
                 nv += 8;
             } else {
-                generic_block(h, wi, wo, t, lead, T, (int32_t)k, last_bad, nv, p0, tau_hi, tbl_s, lanebase, emit);
+                generic_block<ALL>(h, wi, wo, t, lead, T, (int32_t)k, last_bad, nv, p0, tau_hi, tbl_s, lanebase, emit);
             }
         }
     }
@@ -403,7 +404,8 @@ __global__ void k_seq_gaps(const uint64_t* __restrict__ seq_off, const uint32_t*
 }  // namespace
 }  // namespace ntl
 #include "gap_kernel.cuh"      // k_gap (one warp per candidate-free stretch)
-#include "tile_kernel.cuh"     // k_tile (the single-pass sketch for w >= 13)
+#include "tile_kernel.cuh"
+#include "small_kernel.cuh"     // k_tile (the single-pass sketch for w >= 13)
 namespace ntl {
 namespace {
 
@@ -651,6 +653,90 @@ retry:
     return NTL_OK;
 }
 
+// The dense-mode sketch for small windows (small_kernel.cuh): pack, tile table, k_small, scan of the tile counts, gather.
+static int sketch_device_small(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
+                               uint32_t k, uint32_t w, DeviceSketch& out, CallState* call_state) {
+    SketchWork& W = c->sw;
+    const uint32_t S = SMALL_S;
+    const uint32_t nstrips_max = (uint32_t)(total_bases / S + nseq + 1);
+    static bool smem_set = false;
+    if (!smem_set) {
+        NTL_CUDA(c, cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
+        smem_set = true;
+    }
+    int attempt = 0;
+retry:
+    const uint32_t out_cap = sketch_out_bound(total_bases, nseq, w, c->mx_density_factor);
+    SmallParams P;
+    P.k = k; P.w = w; P.nseq = nseq; P.mult = second_hash_multiplier(k); P.out_cap = out_cap;
+    // staging segment of a tile: what random sequence needs (2 / (w + 1) of the positions) x the density head room + 25 %
+    P.tcap = (uint32_t)std::min<double>(S, (double)S * c->mx_density_factor / ((double)w + 1.0) * 1.25 + 64.0);
+    NTL_CUDA(c, W.packed.ensure(total_bases / 2 + 512));
+    NTL_CUDA(c, W.scnt.ensure(((size_t)nseq + 2) * 4));
+    NTL_CUDA(c, W.strip_off.ensure(((size_t)nseq + 2) * 4));
+    NTL_CUDA(c, W.strip_seq.ensure(((size_t)nstrips_max + 1) * 4));
+    NTL_CUDA(c, W.tile_state.ensure(((size_t)nstrips_max + 2) * 8));
+    NTL_CUDA(c, W.stage_hash.ensure((size_t)nstrips_max * P.tcap * 8 + 8));
+    NTL_CUDA(c, W.stage_posf.ensure((size_t)nstrips_max * P.tcap * 4 + 4));
+    uint32_t* tile_cnt = W.tile_state.as<uint32_t>();
+    uint32_t* tile_base = tile_cnt + nstrips_max + 1;
+    NTL_CUDA(c, W.status.ensure(sizeof(SketchStatus) + 64));
+    NTL_CUDA(c, c->h_status.ensure(256));
+    NTL_CUDA(c, out.hash.ensure((size_t)out_cap * 8 + 8));
+    NTL_CUDA(c, out.posf.ensure((size_t)out_cap * 4 + 4));
+    SketchStatus* st = W.status.as<SketchStatus>();
+    uint32_t* nseq_dev = (uint32_t*)((char*)W.status.p + sizeof(SketchStatus));
+    NTL_TRY(sketch_prepare(c, k));
+    uint32_t* const d_packed = reinterpret_cast<uint32_t*>(W.packed.as<char>() + 64);
+    {
+        FillSegs fs{};
+        fs.p[0] = st; fs.n[0] = sizeof(SketchStatus) + 64; fs.v[0] = 0;
+        fs.p[1] = W.packed.p; fs.n[1] = 64; fs.v[1] = 0x44;
+        fs.p[2] = W.packed.as<char>() + 64 + total_bases / 2; fs.n[2] = 192; fs.v[2] = 0x44;
+        k_fill_segs<<<1, 256, 0, c->stream>>>(fs);
+        c->launches += 1;
+    }
+    tick(c, T_PACK);
+    k_pack<<<div_up(div_up(total_bases, 16), 256 * PACK_CHUNKS), 256, 0, c->stream>>>(d_seq, total_bases, d_packed);
+    k_strip_count<<<div_up(nseq, 256), 256, 0, c->stream>>>(d_off, nseq, k, w, S, W.scnt.as<uint32_t>(), nseq_dev);
+    c->launches += 2;
+    NTL_TRY(exclusive_scan_u32(c, W.scnt.as<uint32_t>(), W.strip_off.as<uint32_t>(), nseq_dev, nseq, W.blocksums));
+    k_strip_seq<<<div_up(nstrips_max, 256), 256, 0, c->stream>>>(W.strip_off.as<uint32_t>(), nseq, W.strip_seq.as<uint32_t>());
+    c->launches += 1;
+    tock(c, T_PACK);
+    tick(c, T_DENSE);
+    k_small<<<nstrips_max, SMALL_THREADS, SMALL_SMEM, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,
+                                                                    W.tbl.as<RollEntry>(), tile_cnt, W.stage_hash.as<uint64_t>(),
+                                                                    W.stage_posf.as<uint32_t>(), st);
+    tock(c, T_DENSE, total_bases);
+    c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases;
+    tick(c, T_EMIT);
+    NTL_TRY(exclusive_scan_u32(c, tile_cnt, tile_base, W.strip_off.as<uint32_t>() + nseq, nstrips_max, W.blocksums));
+    k_small_gather<<<std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(nstrips_max, div_up((uint64_t)nseq + 1, 256)), 148 * 8)), 256, 0, c->stream>>>(
+        W.strip_off.as<uint32_t>(), P, tile_cnt, tile_base, W.stage_hash.as<uint64_t>(), W.stage_posf.as<uint32_t>(), out.hash.as<uint64_t>(),
+        out.posf.as<uint32_t>(), out.mx_off.as<uint32_t>(), st, call_state, call_state ? 1u : 0u);
+    c->launches += 1;
+    tock(c, T_EMIT);
+    NTL_CUDA(c, cudaGetLastError());
+    out.n_dev = &st->n_mx;
+    c->n_small_batches++;
+    if (call_state) { out.n_mx = out_cap; return NTL_OK; }          // deferred: an overflow sets the call's error bit, the caller repeats synchronously
+    k_publish_sketch<<<1, 32, 0, c->stream>>>(st, W.strip_off.as<uint32_t>() + nseq, nullptr, c->h_status.as<uint32_t>());
+    c->launches += 1;
+    NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+    {
+        const SketchStatus hs = *c->h_status.as<SketchStatus>();
+        if (hs.err) {                                                // denser than the bound (low complexity): more room per tile and overall
+            if (++attempt > 6) { c->err = "sketch: device workspace exhausted"; return NTL_ERR_WORKSPACE; }
+            c->mx_density_factor *= 2.0;
+            goto retry;
+        }
+        out.n_mx = hs.n_mx;
+        note_mx_density(c, hs.n_mx, total_bases, w);
+    }
+    return NTL_OK;
+}
+
 // Sketch `nseq` sequences that are already on the device (ASCII d_seq, offsets d_off). The result stays on the
 // device in `out`. One host synchronisation (to learn the number of minimizers before the final compaction).
 int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
@@ -663,6 +749,7 @@ int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint3
         NTL_CUDA(c, cudaMemsetAsync(out.mx_off.p, 0, ((size_t)nseq + 1) * 4, c->stream));
         return NTL_OK;
     }
+    if (c->small_mode && w >= 2 && w <= SMALL_W_MAX && k <= 2048) return sketch_device_small(c, d_seq, d_off, nseq, total_bases, k, w, out, call_state);
     if (c->tile_mode) {
         const TileShape shape = tile_shape(k, w, c->cand_c);
         if (shape.ok) {

@@ -1,0 +1,213 @@
+// small_kernel.cuh -- k_small: the sketch for small windows (w <= SMALL_W_MAX: the overlap stage `indexlr -k15 -w5`,
+// ntLink:243-251, and gap filling `-k20 -w10`, bin/ntlink_patch_gaps.py:417-420), included by sketch.cu.
+//
+// With windows this small a large share of all k-mers are minimizers (2 / (w + 1)) and every k-mer would be a
+// "candidate" of the sparse path, whose 16-byte candidate round trip per position then dominates. This kernel keeps
+// everything on chip instead. One block per TILE of SMALL_S consecutive k-mer positions of one sequence:
+//   1. hash     the threads roll ntHash (process_strip_dev, the hot loop of k_dense) over sub-strips of the tile plus
+//               w-1 positions of halo on either side and leave all canonical hashes in shared memory;
+//   2. windows  one thread per window: rightmost argmin of its w hashes, marked in a shared-memory byte map (the marked
+//               positions are exactly the positions btllib emits: the argmin sequence is monotone, so "emit when the
+//               argmin changes" and "emit every position that is some window's argmin" are the same set);
+//   3. output   marks of the tile's own positions are counted, scanned and written in position order to the tile's
+//               staging segment; k_small_gather packs the segments after a scan over the tile counts.
+// Windows are defined over VALID k-mers and therefore span runs of N; a tile whose hashed range contains an invalid
+// base cannot use the position arithmetic above and is walked serially by one thread with gap_scan (exact for any
+// content) over a range widened to w-1 valid k-mers on either side. Rare in reads; in scaffolds one tile per N run.
+#pragma once
+
+namespace ntl {
+namespace {
+
+constexpr int SMALL_THREADS = 128;
+constexpr uint32_t SMALL_S = 4096;                                   // k-mer positions per tile
+constexpr uint32_t SMALL_W_MAX = 16;
+constexpr uint32_t SMALL_R = SMALL_S + 2 * (SMALL_W_MAX - 1);        // hashed positions per tile at most
+constexpr size_t SMALL_SMEM = (size_t)ROLL_TABLE_ENTRIES * TBL_STRIDE + (size_t)SMALL_R * 8 + 2 * (((size_t)SMALL_R + 15) & ~(size_t)15) + 64;
+
+struct SmallParams {
+    uint32_t k, w, nseq, tcap, out_cap;
+    uint64_t mult;
+};
+
+struct SmallEmit {                     // process_strip_dev<ALL> emitter: hashes and strands of a sub-strip into shared memory
+    unsigned long long* H; uint8_t* F; uint32_t base;
+    __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd, uint32_t) { H[pos - base] = h0; F[pos - base] = fwd ? 1 : 0; }
+    __device__ __forceinline__ bool room_for_block() const { return true; }
+    __device__ __forceinline__ void push(bool, uint64_t h0, uint32_t pos, bool fwd, uint32_t) { H[pos - base] = h0; F[pos - base] = fwd ? 1 : 0; }
+    __device__ __forceinline__ void flush_block() {}
+};
+
+struct SmallSerialEmit {               // gap_scan emitter of a dirty tile: own positions straight into the staging segment
+    uint64_t* hash; uint32_t* posf; uint32_t count, cap, lo, hi; uint64_t mult;
+    __device__ __forceinline__ void operator()(uint64_t h0, uint32_t pos, bool fwd) {
+        if (pos < lo || pos >= hi) return;
+        if (count < cap) { hash[count] = second_hash(h0, mult); posf[count] = pos | (fwd ? FWD_BIT : 0u); }
+        count++;
+    }
+};
+
+__global__ void __launch_bounds__(SMALL_THREADS) k_small(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
+                                                         const uint32_t* __restrict__ strip_off, const uint32_t* __restrict__ strip_seq,
+                                                         SmallParams P, const RollEntry* __restrict__ tbl_g, uint32_t* __restrict__ tile_cnt,
+                                                         uint64_t* __restrict__ st_hash, uint32_t* __restrict__ st_posf,
+                                                         SketchStatus* __restrict__ st) {
+    extern __shared__ __align__(256) unsigned char sm_raw[];
+    unsigned char* tbl_s = sm_raw;                                                      // entry e, copy c at e*256 + c*16 (as in k_dense)
+    unsigned long long* H = reinterpret_cast<unsigned long long*>(sm_raw + (size_t)ROLL_TABLE_ENTRIES * TBL_STRIDE);
+    uint8_t* F = reinterpret_cast<uint8_t*>(H + SMALL_R);
+    uint8_t* M = F + ((SMALL_R + 15u) & ~15u);
+    __shared__ uint32_t s_part[SMALL_THREADS / 32 + 1];
+    __shared__ int s_dirty;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nstrips = strip_off[P.nseq];
+    const uint32_t t = blockIdx.x;
+    if (t == 0 && tid == 0) st->nstrips = nstrips;
+    if (t >= nstrips) return;
+    const uint32_t k = P.k, w = P.w;
+    const uint32_t q = strip_seq[t];
+    const uint64_t gseq = seq_off[q];
+    const uint32_t L = (uint32_t)(seq_off[q + 1] - gseq);
+    const uint32_t np = L - k + 1;                                   // a tile exists only when seq_npos > 0
+    const uint32_t p0 = (t - strip_off[q]) * SMALL_S;
+    const uint32_t n = min(SMALL_S, np - p0);
+    const uint32_t r_lo = p0 >= w - 1 ? p0 - (w - 1) : 0;            // hashed positions [r_lo, r_hi)
+    const uint32_t r_hi = min(np, p0 + n + (w - 1));
+    const uint32_t R = r_hi - r_lo;
+    uint64_t* const my_hash = st_hash + (uint64_t)t * P.tcap;
+    uint32_t* const my_posf = st_posf + (uint64_t)t * P.tcap;
+
+    if (tid == 0) s_dirty = 0;
+    for (uint32_t i = tid; i < ROLL_TABLE_ENTRIES * TBL_COPIES; i += SMALL_THREADS) {
+        const RollEntry e = tbl_g[i / TBL_COPIES];
+        reinterpret_cast<uint4*>(tbl_s)[i] = make_uint4((uint32_t)e.f, (uint32_t)(e.f >> 32), (uint32_t)e.r, (uint32_t)(e.r >> 32));
+    }
+    for (uint32_t i = tid; i < ((SMALL_R + 15u) & ~15u) / 4; i += SMALL_THREADS) reinterpret_cast<uint32_t*>(M)[i] = 0u;
+    __syncthreads();
+    {   // any invalid base among the bases of the hashed range?
+        const uint32_t nb = R + k - 1;
+        bool dirty = false;
+        for (uint32_t b = tid * 8; b < nb; b += SMALL_THREADS * 8) {
+            uint32_t wd = fetch8(packed, gseq + r_lo + b);
+            const uint32_t left = nb - b;
+            if (left < 8) wd &= (1u << (4 * left)) - 1u;
+            dirty |= (wd & 0x44444444u) != 0u;
+        }
+        if (dirty) s_dirty = 1;
+    }
+    __syncthreads();
+    if (s_dirty) {
+        if (tid == 0) {
+            // widen until the range holds w-1 valid k-mers on either side of the own positions (or reaches the sequence ends)
+            uint32_t a = p0, b = p0 + n;
+            {
+                uint32_t have = 0, nb = NONE32;                      // nb = smallest invalid base index in [a, a + k), if any
+                for (uint32_t j = 0; j < k && a + j < L; j++) if (fetch1(packed, gseq + a + j) >= CODE_INVALID) { nb = a + j; break; }
+                while (a > 0 && have < w - 1) {
+                    a--;
+                    if (fetch1(packed, gseq + a) >= CODE_INVALID) nb = a;
+                    if (nb == NONE32 || nb >= a + k) have++;
+                }
+            }
+            {
+                uint32_t have = 0, run = 0;                          // run = valid bases ending at base b + k - 1: k-mer b valid <=> run >= k
+                for (uint32_t j = 0; j < k && b + j < L; j++) run = fetch1(packed, gseq + b + j) >= CODE_INVALID ? 0u : run + 1;
+                while (b < np && have < w - 1) {
+                    if (run >= k) have++;
+                    b++;
+                    run = (b + k - 1 < L && fetch1(packed, gseq + b + k - 1) < CODE_INVALID) ? run + 1 : 0u;
+                }
+            }
+            SmallSerialEmit em{my_hash, my_posf, 0u, P.tcap, p0, p0 + n, P.mult};
+            gap_scan(packed, tbl_g, gseq, L, k, w, a, b, em);
+            tile_cnt[t] = em.count;
+            if (em.count > P.tcap) atomicOr(&st->err, SKERR_OUT);
+        }
+        return;
+    }
+    // ---- 1: hashes of [r_lo, r_hi) (all valid), sub-strips of equal length
+    {
+        const uint32_t per = (R + SMALL_THREADS - 1) / SMALL_THREADS;
+        const uint32_t pa = min(R, tid * per), pb = min(R, pa + per);
+        if (pb > pa) {
+            SmallEmit em{H, F, r_lo};
+            process_strip_dev<true>(packed, gseq, r_lo + pa, pb - pa, k, tbl_s, (tid & 15u) << 4, 0xFFFFFFFFu, em);
+        }
+    }
+    __syncthreads();
+    // ---- 2: one thread per window of w consecutive positions inside the range: mark its rightmost argmin
+    if (R >= w) {
+        const uint32_t nwin = R - w + 1;
+        for (uint32_t j = tid; j < nwin; j += SMALL_THREADS) {
+            unsigned long long m = H[j];
+            uint32_t a = j;
+            for (uint32_t x = 1; x < w; x++) {
+                const unsigned long long hv = H[j + x];
+                if (hv <= m) { m = hv; a = j + x; }
+            }
+            if (m != 0xFFFFFFFFFFFFFFFFull) M[a] = 1;               // btllib never reports the all-ones hash (its "no minimizer" value)
+        }
+    }
+    __syncthreads();
+    // ---- 3: own marks -> staging segment, in position order. A warp owns a contiguous share of the own positions and
+    //         walks it 32 positions at a time (ballot + popcount give the ranks; byte map read without bank conflicts,
+    //         staging written with consecutive addresses)
+    const uint32_t own0 = p0 - r_lo;                                 // index of the first own position in H / F / M
+    const uint32_t wchunk = ((n + SMALL_THREADS - 1) / SMALL_THREADS) * 32;
+    const uint32_t wa = min(n, wid * wchunk), wb = min(n, wa + wchunk);
+    uint32_t cntw = 0;
+    for (uint32_t base = wa; base < wb; base += 32) {
+        const uint32_t i = base + lane;
+        cntw += __popc(__ballot_sync(0xffffffffu, i < wb && M[own0 + i]));
+    }
+    if (lane == 0) s_part[wid] = cntw;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < SMALL_THREADS / 32; i++) { const uint32_t x = s_part[i]; s_part[i] = run; run += x; }
+        s_part[SMALL_THREADS / 32] = run;
+        tile_cnt[t] = run;
+        if (run > P.tcap) atomicOr(&st->err, SKERR_OUT);
+    }
+    __syncthreads();
+    if (s_part[SMALL_THREADS / 32] > P.tcap) return;
+    uint32_t at = s_part[wid];
+    for (uint32_t base = wa; base < wb; base += 32) {
+        const uint32_t i = base + lane;
+        const bool m = i < wb && M[own0 + i];
+        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        if (m) {
+            const uint32_t r = at + __popc(bal & ((1u << lane) - 1u));
+            my_hash[r] = second_hash(H[own0 + i], P.mult);
+            my_posf[r] = (p0 + i) | (F[own0 + i] ? FWD_BIT : 0u);
+        }
+        at += __popc(bal);
+    }
+}
+
+// staging segments -> packed output, per-sequence offsets, totals, error gating (tile_base = exclusive scan of tile_cnt)
+__global__ void __launch_bounds__(256) k_small_gather(const uint32_t* __restrict__ strip_off, SmallParams P, const uint32_t* __restrict__ tile_cnt,
+                                                      const uint32_t* __restrict__ tile_base, const uint64_t* __restrict__ st_hash,
+                                                      const uint32_t* __restrict__ st_posf, uint64_t* __restrict__ out_hash,
+                                                      uint32_t* __restrict__ out_posf, uint32_t* __restrict__ mx_off, SketchStatus* __restrict__ st,
+                                                      CallState* __restrict__ call, uint32_t deferred) {
+    const uint32_t nstrips = strip_off[P.nseq];
+    const uint32_t total = tile_base[nstrips];
+    const bool bad = st->err != 0 || total > P.out_cap;
+    if (!bad)
+        for (uint32_t t = blockIdx.x; t < nstrips; t += gridDim.x) {
+            const uint32_t n = tile_cnt[t], o = tile_base[t];
+            const uint64_t from = (uint64_t)t * P.tcap;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { out_hash[o + i] = st_hash[from + i]; out_posf[o + i] = st_posf[from + i]; }
+        }
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q <= P.nseq; q += gridDim.x * blockDim.x)
+        mx_off[q] = (bad && deferred) ? 0u : tile_base[q == P.nseq ? nstrips : strip_off[q]];      // an empty sequence starts where the next one does
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->n_mx = (bad && deferred) ? 0u : total;
+        if (total > P.out_cap) atomicOr(&st->err, SKERR_OUT);
+        if (bad && call) atomicOr(&call->err, CALLERR_SKETCH);
+    }
+}
+
+}  // namespace
+}  // namespace ntl
