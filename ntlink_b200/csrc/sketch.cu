@@ -705,9 +705,17 @@ retry:
     c->launches += 1;
     tock(c, T_PACK);
     tick(c, T_DENSE);
-    k_small<<<nstrips_max, SMALL_THREADS, SMALL_SMEM, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,
-                                                                    W.tbl.as<RollEntry>(), tile_cnt, W.stage_hash.as<uint64_t>(),
-                                                                    W.stage_posf.as<uint32_t>(), st);
+    {
+        static int per_sm = 0;
+        if (!per_sm) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_small, SMALL_THREADS * SMALL_GROUPS, SMALL_SMEM);
+            per_sm = std::max(per_sm, 1);
+        }
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(div_up(nstrips_max, SMALL_GROUPS), 148u * (uint32_t)per_sm));
+        k_small<<<grid, SMALL_THREADS * SMALL_GROUPS, SMALL_SMEM, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,
+                                                                 W.tbl.as<RollEntry>(), tile_cnt, nseq_dev + 1, W.stage_hash.as<uint64_t>(),
+                                                                 W.stage_posf.as<uint32_t>(), st);
+    }
     tock(c, T_DENSE, total_bases);
     c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases;
     tick(c, T_EMIT);

@@ -19,11 +19,16 @@
 namespace ntl {
 namespace {
 
-constexpr int SMALL_THREADS = 128;
+constexpr int SMALL_THREADS = 128;                                   // threads of a GROUP: a group works on one tile at a time
+constexpr int SMALL_GROUPS = 2;                                      // groups per block; they share the roll table only
 constexpr uint32_t SMALL_S = 4096;                                   // k-mer positions per tile
 constexpr uint32_t SMALL_W_MAX = 16;
 constexpr uint32_t SMALL_R = SMALL_S + 2 * (SMALL_W_MAX - 1);        // hashed positions per tile at most
-constexpr size_t SMALL_SMEM = (size_t)ROLL_TABLE_ENTRIES * TBL_STRIDE + (size_t)SMALL_R * 8 + 2 * (((size_t)SMALL_R + 15) & ~(size_t)15) + 64;
+constexpr size_t SMALL_GROUP_SMEM = (size_t)SMALL_R * 8 + 2 * (((size_t)SMALL_R + 15) & ~(size_t)15) + 32;     // H, F, M of one tile
+constexpr size_t SMALL_SMEM = (size_t)ROLL_TABLE_ENTRIES * TBL_STRIDE + SMALL_GROUPS * SMALL_GROUP_SMEM;
+
+// barrier of one group (named barrier 1 + group): the groups of a block never wait for each other after the table is loaded
+__device__ __forceinline__ void small_group_sync(uint32_t grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(SMALL_THREADS) : "memory"); }
 
 struct SmallParams {
     uint32_t k, w, nseq, tcap, out_cap;
@@ -47,24 +52,41 @@ struct SmallSerialEmit {               // gap_scan emitter of a dirty tile: own 
     }
 };
 
-__global__ void __launch_bounds__(SMALL_THREADS) k_small(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
+__global__ void __launch_bounds__(SMALL_THREADS * SMALL_GROUPS) k_small(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ seq_off,
                                                          const uint32_t* __restrict__ strip_off, const uint32_t* __restrict__ strip_seq,
                                                          SmallParams P, const RollEntry* __restrict__ tbl_g, uint32_t* __restrict__ tile_cnt,
-                                                         uint64_t* __restrict__ st_hash, uint32_t* __restrict__ st_posf,
-                                                         SketchStatus* __restrict__ st) {
+                                                         uint32_t* __restrict__ ticket, uint64_t* __restrict__ st_hash,
+                                                         uint32_t* __restrict__ st_posf, SketchStatus* __restrict__ st) {
     extern __shared__ __align__(256) unsigned char sm_raw[];
     unsigned char* tbl_s = sm_raw;                                                      // entry e, copy c at e*256 + c*16 (as in k_dense)
-    unsigned long long* H = reinterpret_cast<unsigned long long*>(sm_raw + (size_t)ROLL_TABLE_ENTRIES * TBL_STRIDE);
+    const uint32_t grp = threadIdx.x / SMALL_THREADS;
+    unsigned long long* H = reinterpret_cast<unsigned long long*>(sm_raw + (size_t)ROLL_TABLE_ENTRIES * TBL_STRIDE + grp * SMALL_GROUP_SMEM);
     uint8_t* F = reinterpret_cast<uint8_t*>(H + SMALL_R);
     uint8_t* M = F + ((SMALL_R + 15u) & ~15u);
-    __shared__ uint32_t s_part[SMALL_THREADS / 32 + 1];
-    __shared__ int s_dirty;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ uint32_t s_part_all[SMALL_GROUPS][SMALL_THREADS / 32 + 1];
+    __shared__ uint32_t s_tile_all[SMALL_GROUPS];
+    __shared__ int s_dirty_all[SMALL_GROUPS];
+    uint32_t* const s_part = s_part_all[grp];
+    uint32_t& s_tile = s_tile_all[grp];
+    int& s_dirty = s_dirty_all[grp];
+    const uint32_t tid = threadIdx.x % SMALL_THREADS, lane = tid & 31, wid = tid >> 5;
     const uint32_t nstrips = strip_off[P.nseq];
-    const uint32_t t = blockIdx.x;
-    if (t == 0 && tid == 0) st->nstrips = nstrips;
-    if (t >= nstrips) return;
     const uint32_t k = P.k, w = P.w;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->nstrips = nstrips;
+    for (uint32_t i = threadIdx.x; i < ROLL_TABLE_ENTRIES * TBL_COPIES; i += SMALL_THREADS * SMALL_GROUPS) {
+        const RollEntry e = tbl_g[i / TBL_COPIES];
+        reinterpret_cast<uint4*>(tbl_s)[i] = make_uint4((uint32_t)e.f, (uint32_t)(e.f >> 32), (uint32_t)e.r, (uint32_t)(e.r >> 32));
+    }
+    // persistent blocks: tiles are handed out by a ticket counter (tiles at sequence ends are partial, tiles with invalid
+    // bases are slow), the roll table is loaded once per block
+    __syncthreads();
+  for (;;) {
+    small_group_sync(grp);                                           // the previous tile's buffers are free
+    if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_dirty = 0; }
+    for (uint32_t i = tid; i < ((SMALL_R + 15u) & ~15u) / 4; i += SMALL_THREADS) reinterpret_cast<uint32_t*>(M)[i] = 0u;
+    small_group_sync(grp);
+    const uint32_t t = s_tile;
+    if (t >= nstrips) return;
     const uint32_t q = strip_seq[t];
     const uint64_t gseq = seq_off[q];
     const uint32_t L = (uint32_t)(seq_off[q + 1] - gseq);
@@ -76,14 +98,6 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small(const uint32_t* __restr
     const uint32_t R = r_hi - r_lo;
     uint64_t* const my_hash = st_hash + (uint64_t)t * P.tcap;
     uint32_t* const my_posf = st_posf + (uint64_t)t * P.tcap;
-
-    if (tid == 0) s_dirty = 0;
-    for (uint32_t i = tid; i < ROLL_TABLE_ENTRIES * TBL_COPIES; i += SMALL_THREADS) {
-        const RollEntry e = tbl_g[i / TBL_COPIES];
-        reinterpret_cast<uint4*>(tbl_s)[i] = make_uint4((uint32_t)e.f, (uint32_t)(e.f >> 32), (uint32_t)e.r, (uint32_t)(e.r >> 32));
-    }
-    for (uint32_t i = tid; i < ((SMALL_R + 15u) & ~15u) / 4; i += SMALL_THREADS) reinterpret_cast<uint32_t*>(M)[i] = 0u;
-    __syncthreads();
     {   // any invalid base among the bases of the hashed range?
         const uint32_t nb = R + k - 1;
         bool dirty = false;
@@ -95,7 +109,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small(const uint32_t* __restr
         }
         if (dirty) s_dirty = 1;
     }
-    __syncthreads();
+    small_group_sync(grp);
     if (s_dirty) {
         if (tid == 0) {
             // widen until the range holds w-1 valid k-mers on either side of the own positions (or reaches the sequence ends)
@@ -123,7 +137,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small(const uint32_t* __restr
             tile_cnt[t] = em.count;
             if (em.count > P.tcap) atomicOr(&st->err, SKERR_OUT);
         }
-        return;
+        continue;
     }
     // ---- 1: hashes of [r_lo, r_hi) (all valid), sub-strips of equal length
     {
@@ -134,34 +148,59 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small(const uint32_t* __restr
             process_strip_dev<true>(packed, gseq, r_lo + pa, pb - pa, k, tbl_s, (tid & 15u) << 4, 0xFFFFFFFFu, em);
         }
     }
-    __syncthreads();
-    // ---- 2: one thread per window of w consecutive positions inside the range: mark its rightmost argmin
+    small_group_sync(grp);
+    // ---- 2: one thread per window of w consecutive positions inside the range: mark its rightmost argmin. The scan
+    //         compares the HIGH hash words only (one 32-bit load per probe, unrolled by four); a tie of two high words
+    //         sends the window through the full 64-bit scan (identical k-mers: low-complexity sequence).
     if (R >= w) {
         const uint32_t nwin = R - w + 1;
-        for (uint32_t j = tid; j < nwin; j += SMALL_THREADS) {
-            unsigned long long m = H[j];
-            uint32_t a = j;
+        const uint32_t* const Hw = reinterpret_cast<const uint32_t*>(H);
+        // two windows per thread and step: two independent compare chains keep the few resident warps issuing
+        for (uint32_t j = tid; j < nwin; j += 2 * SMALL_THREADS) {
+            const uint32_t j2 = j + SMALL_THREADS;
+            const bool two = j2 < nwin;
+            const uint32_t* hp = Hw + 2 * j + 1;                     // high word of H[j + x] at hp[2 * x]
+            const uint32_t* hq = Hw + 2 * (two ? j2 : j) + 1;
+            uint32_t m = hp[0], a = 0, m2 = hq[0], a2 = 0;
+            bool tie = false, tie2 = false;
             for (uint32_t x = 1; x < w; x++) {
-                const unsigned long long hv = H[j + x];
-                if (hv <= m) { m = hv; a = j + x; }
+                const uint32_t hv = hp[2 * x], hv2 = hq[2 * x];
+                tie |= hv == m; tie2 |= hv2 == m2;
+                if (hv <= m) { m = hv; a = x; }
+                if (hv2 <= m2) { m2 = hv2; a2 = x; }
             }
-            if (m != 0xFFFFFFFFFFFFFFFFull) M[a] = 1;               // btllib never reports the all-ones hash (its "no minimizer" value)
+            unsigned long long mv = H[j + a], mv2 = H[(two ? j2 : j) + a2];
+            if (tie | tie2) {
+                mv = H[j]; a = 0; mv2 = H[two ? j2 : j]; a2 = 0;
+                for (uint32_t y = 1; y < w; y++) {
+                    const unsigned long long hv = H[j + y], hv2 = H[(two ? j2 : j) + y];
+                    if (hv <= mv) { mv = hv; a = y; }
+                    if (hv2 <= mv2) { mv2 = hv2; a2 = y; }
+                }
+            }
+            if (mv != 0xFFFFFFFFFFFFFFFFull) M[j + a] = 1;           // btllib never reports the all-ones hash (its "no minimizer" value)
+            if (two && mv2 != 0xFFFFFFFFFFFFFFFFull) M[j2 + a2] = 1;
         }
     }
-    __syncthreads();
-    // ---- 3: own marks -> staging segment, in position order. A warp owns a contiguous share of the own positions and
-    //         walks it 32 positions at a time (ballot + popcount give the ranks; byte map read without bank conflicts,
-    //         staging written with consecutive addresses)
+    small_group_sync(grp);
+    // ---- 3: own marks -> staging segment, in position order. A warp owns a contiguous share of the own positions:
+    //         pass 1 turns the byte map into ballot words (32 positions each, one word per lane at the end), a warp
+    //         scan and a four-entry block scan place every word, pass 2 lets every lane write the marks of its word
     const uint32_t own0 = p0 - r_lo;                                 // index of the first own position in H / F / M
-    const uint32_t wchunk = ((n + SMALL_THREADS - 1) / SMALL_THREADS) * 32;
+    const uint32_t wchunk = ((n + SMALL_THREADS - 1) / SMALL_THREADS) * 32;        // <= 1024 positions = 32 words per warp
     const uint32_t wa = min(n, wid * wchunk), wb = min(n, wa + wchunk);
-    uint32_t cntw = 0;
-    for (uint32_t base = wa; base < wb; base += 32) {
+    uint32_t myword = 0;
+    for (uint32_t base = wa, it = 0; base < wb; base += 32, it++) {
         const uint32_t i = base + lane;
-        cntw += __popc(__ballot_sync(0xffffffffu, i < wb && M[own0 + i]));
+        const uint32_t bal = __ballot_sync(0xffffffffu, i < wb && M[own0 + i]);
+        if (lane == it) myword = bal;
     }
-    if (lane == 0) s_part[wid] = cntw;
-    __syncthreads();
+    const uint32_t mine = __popc(myword);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
+    if (lane == 31) s_part[wid] = incl;
+    small_group_sync(grp);
     if (tid == 0) {
         uint32_t run = 0;
         for (uint32_t i = 0; i < SMALL_THREADS / 32; i++) { const uint32_t x = s_part[i]; s_part[i] = run; run += x; }
@@ -169,20 +208,18 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small(const uint32_t* __restr
         tile_cnt[t] = run;
         if (run > P.tcap) atomicOr(&st->err, SKERR_OUT);
     }
-    __syncthreads();
-    if (s_part[SMALL_THREADS / 32] > P.tcap) return;
-    uint32_t at = s_part[wid];
-    for (uint32_t base = wa; base < wb; base += 32) {
-        const uint32_t i = base + lane;
-        const bool m = i < wb && M[own0 + i];
-        const uint32_t bal = __ballot_sync(0xffffffffu, m);
-        if (m) {
-            const uint32_t r = at + __popc(bal & ((1u << lane) - 1u));
-            my_hash[r] = second_hash(H[own0 + i], P.mult);
-            my_posf[r] = (p0 + i) | (F[own0 + i] ? FWD_BIT : 0u);
+    small_group_sync(grp);
+    if (s_part[SMALL_THREADS / 32] <= P.tcap) {
+        uint32_t at = s_part[wid] + incl - mine;
+        const uint32_t first = wa + lane * 32;                       // own position of bit 0 of this lane's word
+        for (uint32_t bits = myword; bits; bits &= bits - 1) {
+            const uint32_t i = first + (uint32_t)__ffs(bits) - 1;
+            my_hash[at] = second_hash(H[own0 + i], P.mult);
+            my_posf[at] = (p0 + i) | (F[own0 + i] ? FWD_BIT : 0u);
+            at++;
         }
-        at += __popc(bal);
     }
+  }
 }
 
 // staging segments -> packed output, per-sequence offsets, totals, error gating (tile_base = exclusive scan of tile_cnt)
