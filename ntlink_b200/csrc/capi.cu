@@ -264,7 +264,7 @@ int ntl_set_option(ntl_ctx* c, const char* name, double value) {
     } else if (!strcmp(name, "tile")) {
         c->tile_mode = value != 0.0;
     } else if (!strcmp(name, "small")) {
-        c->small_mode = value != 0.0;
+        c->small_mode = (int)value;                        // 0 off, 1 automatic, 2 tile kernel, 3 streaming kernel
     } else if (!strcmp(name, "graph")) {
         c->graph_mode = value != 0.0;
     } else if (!strcmp(name, "pipeline_min_bases")) {

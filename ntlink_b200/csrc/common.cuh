@@ -182,7 +182,7 @@ struct ntl_ctx {
     double mx_density_factor = 2.6;        // minimizers per base * (w + 1), upper estimate (see sketch_out_bound)
     int copy_threads = -1;                 // host threads of the pageable->pinned bounce copy (-1 auto, 0 = off)
     uint64_t n_tile_batches = 0, n_tile_fallbacks = 0;   // ntl_get_stat "tile_batches" / "tile_fallbacks"
-    int small_mode = 1;                    // dense-mode kernel (small_kernel.cuh) for w <= 16 (option "small")
+    int small_mode = 1;                    // dense-mode kernels (small_kernel.cuh) for w <= 16: option "small" = 0 off, 1 auto, 2 tile, 3 streaming
     uint64_t n_small_batches = 0;          // ntl_get_stat "small_batches"
     int tile_mode = 0;                     // single-pass sketch kernel (tile_kernel.cuh) where the window size allows (option "tile")
     int graph_mode = 1;                    // sync-free ntl_map_reads: one CUDA graph per chunk (option "graph")

@@ -287,11 +287,12 @@ __device__ __forceinline__ uint32_t process_strip_dev(const uint32_t* __restrict
                     const uint64_t h0 = fh + rh;
                     emit.push(ALL || (uint32_t)(h0 >> 32) < tau_hi, h0, pos0 + j, fh <= rh, nv + j);
                 }
-                emit.flush_block();
+                if (!ALL) emit.flush_block();
                 nv += 8;
             } else {
                 generic_block<ALL>(h, wi, wo, t, lead, T, (int32_t)k, last_bad, nv, p0, tau_hi, tbl_s, lanebase, emit);
             }
+            if (ALL) emit.flush_block();                              // one copy of the emitter's per-block work for all three kinds of block
         }
     }
     return nv;
@@ -657,11 +658,15 @@ retry:
 static int sketch_device_small(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
                                uint32_t k, uint32_t w, DeviceSketch& out, CallState* call_state) {
     SketchWork& W = c->sw;
-    const uint32_t S = SMALL_S;
+    // option small: 1 = automatic (measured, DESIGN.md 8: the tile kernel wins for w <= 6, where a third of all positions are
+    // minimizers and the streaming kernel's per-position mark logic costs most), 2 = tile kernel, 3 = streaming kernel
+    const bool stream = c->small_mode == 3 || (c->small_mode == 1 && w > 6);
+    const uint32_t S = stream ? STREAM_S : SMALL_S;
     const uint32_t nstrips_max = (uint32_t)(total_bases / S + nseq + 1);
     static bool smem_set = false;
     if (!smem_set) {
         NTL_CUDA(c, cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
+        NTL_CUDA(c, cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STREAM_SMEM));
         smem_set = true;
     }
     int attempt = 0;
@@ -670,7 +675,7 @@ retry:
     SmallParams P;
     P.k = k; P.w = w; P.nseq = nseq; P.mult = second_hash_multiplier(k); P.out_cap = out_cap;
     // staging segment of a tile: what random sequence needs (2 / (w + 1) of the positions) x the density head room + 25 %
-    P.tcap = (uint32_t)std::min<double>(S, (double)S * c->mx_density_factor / ((double)w + 1.0) * 1.25 + 64.0);
+    P.tcap = (uint32_t)std::min<double>(S, (double)S * c->mx_density_factor / ((double)w + 1.0) * 1.25 + (stream ? 8.0 : 64.0));
     NTL_CUDA(c, W.packed.ensure(total_bases / 2 + 512));
     NTL_CUDA(c, W.scnt.ensure(((size_t)nseq + 2) * 4));
     NTL_CUDA(c, W.strip_off.ensure(((size_t)nseq + 2) * 4));
@@ -705,7 +710,17 @@ retry:
     c->launches += 1;
     tock(c, T_PACK);
     tick(c, T_DENSE);
-    {
+    if (stream) {
+        static int per_sm = 0;
+        if (!per_sm) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream, STREAM_THREADS, STREAM_SMEM);
+            per_sm = std::max(per_sm, 1);
+        }
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(div_up(nstrips_max, STREAM_THREADS), 148u * (uint32_t)per_sm));
+        k_stream<<<grid, STREAM_THREADS, STREAM_SMEM, c->stream>>>(d_packed, d_off, W.strip_off.as<uint32_t>(), W.strip_seq.as<uint32_t>(), P,
+                                                                    W.tbl.as<RollEntry>(), tile_cnt, W.stage_hash.as<uint64_t>(),
+                                                                    W.stage_posf.as<uint32_t>(), st);
+    } else {
         static int per_sm = 0;
         if (!per_sm) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_small, SMALL_THREADS * SMALL_GROUPS, SMALL_SMEM);
@@ -720,9 +735,14 @@ retry:
     c->launches += 1; c->dense_launches += 1; c->dense_bases += total_bases;
     tick(c, T_EMIT);
     NTL_TRY(exclusive_scan_u32(c, tile_cnt, tile_base, W.strip_off.as<uint32_t>() + nseq, nstrips_max, W.blocksums));
-    k_small_gather<<<std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(nstrips_max, div_up((uint64_t)nseq + 1, 256)), 148 * 8)), 256, 0, c->stream>>>(
-        W.strip_off.as<uint32_t>(), P, tile_cnt, tile_base, W.stage_hash.as<uint64_t>(), W.stage_posf.as<uint32_t>(), out.hash.as<uint64_t>(),
-        out.posf.as<uint32_t>(), out.mx_off.as<uint32_t>(), st, call_state, call_state ? 1u : 0u);
+    if (stream)
+        k_stream_gather<<<std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(div_up(nstrips_max, 8), div_up((uint64_t)nseq + 1, 256)), 148 * 8)), 256, 0, c->stream>>>(
+            W.strip_off.as<uint32_t>(), P, tile_cnt, tile_base, W.stage_hash.as<uint64_t>(), W.stage_posf.as<uint32_t>(), out.hash.as<uint64_t>(),
+            out.posf.as<uint32_t>(), out.mx_off.as<uint32_t>(), st, call_state, call_state ? 1u : 0u);
+    else
+        k_small_gather<<<std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(nstrips_max, div_up((uint64_t)nseq + 1, 256)), 148 * 8)), 256, 0, c->stream>>>(
+            W.strip_off.as<uint32_t>(), P, tile_cnt, tile_base, W.stage_hash.as<uint64_t>(), W.stage_posf.as<uint32_t>(), out.hash.as<uint64_t>(),
+            out.posf.as<uint32_t>(), out.mx_off.as<uint32_t>(), st, call_state, call_state ? 1u : 0u);
     c->launches += 1;
     tock(c, T_EMIT);
     NTL_CUDA(c, cudaGetLastError());

@@ -1,4 +1,4 @@
-"""The dense-mode sketch kernel for small windows (csrc/small_kernel.cuh, w <= 16: the overlap stage k15/w5 and gap
+"""The dense-mode sketch kernels for small windows (csrc/small_kernel.cuh: k_small, option small=2, and k_stream, small=3; small=1 picks by w; w <= 16: the overlap stage k15/w5 and gap
 filling k20/w10) against the C oracle: tile boundaries (tiles of 4096 k-mer positions), runs of N in and next to the halo,
 low-complexity sequence that overflows the staging segments, sequences shorter than a window, and the generic sparse
 path on the same input."""
@@ -39,6 +39,8 @@ def test_small_windows_random_and_tile_edges(ctx, k, w):
     before = small_batches(ctx)
     compare(ctx, seq, offs, k, w, small=1)
     assert small_batches(ctx) > before, "the dense-mode kernel did not run"
+    compare(ctx, seq, offs, k, w, small=2)                      # the tile form of the dense-mode kernel
+    compare(ctx, seq, offs, k, w, small=3)                      # the streaming form
     compare(ctx, seq, offs, k, w, small=0)                      # the sparse path on the same input
 
 
@@ -56,6 +58,10 @@ def test_small_windows_with_runs_of_n(ctx, k, w):
     dense_n = acgt[rng.integers(0, 4, 20000)].copy()
     dense_n[rng.random(20000) < 0.03] = ord("N")
     compare(ctx, dense_n, np.array([0, 5000, 5000, 20000], np.uint64), k, w, small=1)
+    compare(ctx, dense_n, np.array([0, 5000, 5000, 20000], np.uint64), k, w, small=2)
+    compare(ctx, dense_n, np.array([0, 5000, 5000, 20000], np.uint64), k, w, small=3)
+    compare(ctx, s, np.array([0, len(s)], np.uint64), k, w, small=3)
+    compare(ctx, s, np.array([0, len(s)], np.uint64), k, w, small=2)
 
 
 def test_small_windows_low_complexity_overflows_staging(ctx):
@@ -66,6 +72,8 @@ def test_small_windows_low_complexity_overflows_staging(ctx):
     offs[1:] = np.cumsum([len(p) for p in parts])
     for k, w in [(15, 5), (8, 3), (20, 10)]:
         compare(ctx, seq, offs, k, w, small=1)
+        compare(ctx, seq, offs, k, w, small=2)
+        compare(ctx, seq, offs, k, w, small=3)
 
 
 def test_small_windows_larger_batch_equals_sparse_path(ctx):
@@ -73,10 +81,10 @@ def test_small_windows_larger_batch_equals_sparse_path(ctx):
     gen = synth.genome(3_000_000, 77)
     reads = synth.reads(gen, 4, 78)
     for k, w in [(15, 5), (20, 10)]:
-        ctx.set_option("small", 1)
-        a = ctx.sketch(reads, k, w)
         ctx.set_option("small", 0)
         b = ctx.sketch(reads, k, w)
-        ctx.set_option("small", 1)
-        assert np.array_equal(a.seq_off, b.seq_off) and np.array_equal(a.hash, b.hash) and np.array_equal(a.pos_strand, b.pos_strand)
+        for mode in (2, 3, 1):
+            ctx.set_option("small", mode)
+            a = ctx.sketch(reads, k, w)
+            assert np.array_equal(a.seq_off, b.seq_off) and np.array_equal(a.hash, b.hash) and np.array_equal(a.pos_strand, b.pos_strand)
         assert len(a.hash) > 0.25 * len(reads.seq) * 2 / (w + 1)

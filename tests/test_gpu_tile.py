@@ -22,6 +22,7 @@ def check(ctx, seq, offs, k, w, c=7.0, allow_fallback=False):
     from ntlink_b200 import SeqBatch
     ctx.set_option("cand_c", c)
     ctx.set_option("tile", 1)
+    ctx.set_option("small", 0)                 # w <= 16 would otherwise go to the dense-mode kernels (tests/test_gpu_small.py)
     t0, f0 = ctx.stat("tile_batches"), ctx.stat("tile_fallbacks")
     batch = SeqBatch(seq, offs, [f"s{i}" for i in range(len(offs) - 1)])
     sk = ctx.sketch(batch, k, w)
