@@ -42,7 +42,8 @@ void ntl_destroy(ntl_ctx* ctx);
 const char* ntl_last_error(const ntl_ctx* ctx);
 int ntl_version(void);
 /* tuning knobs: "strip_len" (k-mer positions per thread, multiple of 8; 0 = chosen per batch, the default), "tile" (1: the
- * single-pass tile kernel where the window size allows it), "cand_c" (candidate threshold,
+ * single-pass tile kernel where the window size allows it), "small" (dense-mode kernels for windows of w <= 16: 0 off,
+ * 1 automatic (default), 2 tile form, 3 streaming form), "cand_c" (candidate threshold,
  * expected candidates per window), "batch_bases" (bases per device batch), "pipeline_min_bases" (4x the chunk size of
  * the pipelined ntl_map_reads), "async" (1: ntl_map_reads / ntl_map_resident enqueue the whole call without waiting for
  * the device and synchronise once; 0: the step-by-step path the sync-free one falls back to), "graph" (1: each chunk of

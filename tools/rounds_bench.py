@@ -159,6 +159,7 @@ def main():
     if world > 1:
         import datetime
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=10))
 
     def barrier():
