@@ -289,9 +289,7 @@ def run_gpu(args, rank, world, local_rank):
     dist = None
     torch.cuda.set_device(local_rank)
     if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own banner must not share stdout with the JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = nd.init_nccl(local_rank)                              # NCCL's own banner must not share stdout with the JSON line
 
     def barrier():
         if dist is not None:

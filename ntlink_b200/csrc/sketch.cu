@@ -928,7 +928,7 @@ emit:
     P.out_cap = out_cap;
     out.n_dev = &st->n_mx;
     {
-        int G = mu <= 12 ? 4 : mu <= 40 ? 8 : mu <= 96 ? 16 : 32;
+        int G = mu <= 24 ? 4 : mu <= 40 ? 8 : mu <= 96 ? 16 : 32;      // lanes per strip; configs[2] (mu = 21.5): G = 4 0.93 ms, 8 0.99, 16 1.22, 32 1.64
         if (const char* eg = getenv("NTL_EMIT_G")) G = atoi(eg);
 #define NTL_EMIT(GG)                                                                                                              \
         k_emit<GG><<<div_up((uint64_t)nstrips_max * GG, EMIT_THREADS), EMIT_THREADS, 0, c->stream>>>(                               \

@@ -13,6 +13,28 @@ import numpy as np
 import torch
 
 
+def init_nccl(local_rank, timeout_minutes=10):
+    """torch.distributed over NCCL for this rank's GPU. The communicator is created here (one barrier) with file
+    descriptor 1 pointed at stderr meanwhile: NCCL prints its version banner to stdout when it comes up, and the callers
+    of this module (bench.py, pair.py, tools/) promise one JSON line / a byte-exact stream there."""
+    import datetime
+    import os
+    import sys
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=timeout_minutes))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return dist
+
+
 def contig_shard(offsets, rank, world):
     "contigs [a, b) of this rank: split by cumulative length so every rank sketches about the same number of bases"
     cum = np.asarray(offsets, dtype=np.int64)

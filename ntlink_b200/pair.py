@@ -436,12 +436,11 @@ def main(argv=None):
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         import torch
-        import torch.distributed as dist
+        from . import dist as nd
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         args.device = local
-        import datetime as _dt
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=_dt.timedelta(minutes=10))
+        dist = nd.init_nccl(local)
         try:
             NtLink(args, rank=rank, world=world, dist=dist).main()
         finally:

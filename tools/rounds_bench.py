@@ -157,10 +157,7 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        import datetime
-        import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=10))
+        dist = nd.init_nccl(local)
 
     def barrier():
         if dist is not None:
