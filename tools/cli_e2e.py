@@ -2,7 +2,10 @@
 """T_e2e-file: wall time of the drop-in command line on FILES, the way ntLink's make recipe calls it --
 target FASTA + read FASTA (optionally .gz) in, <p>.n1.scaffold.dot / .pairs.tsv (/ .verbose_mapping.tsv / .paf) out.
 
-    python tools/cli_e2e.py [--config c1|c2] [--scale 0.25] [--gz] [--gpus N]
+    python tools/cli_e2e.py [--config c1|c2] [--scale 0.25] [--gz | --bgzf] [--gpus N]
+
+--gz: reads as single-stream gzip (`gzip -1`), inflated by one zlib thread; --bgzf: reads as bgzip-style members (what
+`bgzip` writes), inflated in parallel by the reader.
 
 Inputs are the bench workloads (generated on the device, written as FASTA to tmpfs before the clock starts)."""
 import argparse
@@ -20,11 +23,27 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "oracle"))
 
 
+def write_bgzf(src, dst, level=1, block=65280):
+    "bgzip-style file: independent gzip members of <= 64 KiB with the BC extra field (SAM spec 4.1)"
+    import struct
+    import zlib
+    with open(src, "rb") as fin, open(dst, "wb") as fout:
+        while True:
+            chunk = fin.read(block)
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            payload = co.compress(chunk) + co.flush()
+            fout.write(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 18 + len(payload) + 8 - 1) +
+                       payload + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+            if not chunk:
+                break
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c1")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--gz", action="store_true")
+    ap.add_argument("--bgzf", action="store_true")
     ap.add_argument("--gpus", type=int, default=1)
     a = ap.parse_args()
     import bench
@@ -47,6 +66,10 @@ def main():
         if a.gz:
             subprocess.check_call(["gzip", "-1", rd])
             rd += ".gz"
+        elif a.bgzf:
+            write_bgzf(rd, rd + ".bgz.gz")
+            os.remove(rd)
+            rd += ".bgz.gz"
         bases = int(reads.offsets[-1])
         for mode, extra in (("scaffold.dot + pairs.tsv", []), ("+ verbose_mapping.tsv + paf", ["--verbose", "--paf"])):
             times = []
@@ -64,7 +87,7 @@ def main():
                     if os.path.exists(prefix + suffix):
                         os.remove(prefix + suffix)
             best = min(times)
-            print(json.dumps({"T_e2e_file": "python -m ntlink_b200.pair --sketch-target --reads-fasta reads.fa" + (".gz" if a.gz else ""),
+            print(json.dumps({"T_e2e_file": "python -m ntlink_b200.pair --sketch-target --reads-fasta reads.fa" + (".gz" if a.gz else ".bgz.gz (BGZF)" if a.bgzf else ""),
                               "workload": cfg["workload"], "outputs": mode, "gpus": a.gpus, "read_bases": bases, "target_bases": int(contigs.offsets[-1]),
                               "wall_s": [round(t, 3) for t in times], "gbp_per_s_best": round(bases / best / 1e9, 3)}), flush=True)
     finally:
