@@ -964,9 +964,24 @@ int events_import_device(ntl_ctx* c, const void* d_src, uint32_t world, uint64_t
 
 // Pair table over the whole device event log.
 int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>& gaps) {
-    const uint64_t n = c->tl_n_events;
+    uint64_t n = c->tl_n_events;
     pairs.clear(); gaps.clear();
     if (n == 0) return NTL_OK;
+    if (c->tl_count_on_device) {
+        // After a sync-free event exchange the host only knows the capacity of the exchange buffers (ranks x 4 x the largest
+        // count seen); the exact number of events is a word on the device. Fetch it first -- one short synchronisation, and
+        // the tally ends with one anyway -- so that the pair table, its fills, scans and the per-slot kernels are sized by
+        // the events and not by that bound (N = 8, configs[3]: 137 k events against a bound of ~1.1 M).
+        NTL_CUDA(c, c->tw.h_stage.ensure(64));
+        uint32_t* cw = c->tw.h_stage.as<uint32_t>();
+        NTL_CUDA(c, cudaMemcpyAsync(cw, c->tl_count.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        NTL_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->tl_count_on_device = false;
+        if (cw[1]) { c->tl_n_events = 0; c->err = "a rank sent more events than the exchange buffer holds (ntl_events_import_device)"; return NTL_ERR_WORKSPACE; }
+        n = std::min<uint64_t>(n, cw[0]);
+        c->tl_n_events = n;
+        if (n == 0) return NTL_OK;
+    }
     if (n >= (1ull << 31)) { c->err = "tally: too many events"; return NTL_ERR_WORKSPACE; }
     uint64_t slots = 1024;
     while (slots < 2 * n) slots <<= 1;
@@ -1051,24 +1066,17 @@ int tally_device(ntl_ctx* c, std::vector<ntl_pair>& pairs, std::vector<int32_t>&
     memcpy(gaps.data(), hs + pair_bytes, gap_bytes_copy);
 #undef TL_CUDA
     cleanup();
-    // first-seen order (the reference's dict order). Sorted as (key, index) records on a few host threads and then permuted:
-    // at human scale the table has > 10^5 pairs and a plain sort of the 40-byte rows was most of rank 0's tally time.
+    // first-seen order (the reference's dict order): radix-sorted permutation of the first-seen keys, then one pass that moves
+    // the 40-byte rows (a comparison sort of the rows, later of (key, index) records on four threads, was most of rank 0's
+    // tally time at human scale)
     {
         const size_t np_ = pairs.size();
-        std::vector<std::pair<uint64_t, uint32_t>> key(np_);
-        for (size_t i = 0; i < np_; i++) key[i] = {pairs[i].first_key, (uint32_t)i};
-        const int nt = np_ >= 65536 ? 4 : 1;
-        std::vector<size_t> cut(nt + 1);
-        for (int t = 0; t <= nt; t++) cut[t] = np_ * t / nt;
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back([&, t]() { std::sort(key.begin() + cut[t], key.begin() + cut[t + 1]); });
-        std::sort(key.begin() + cut[0], key.begin() + cut[1]);
-        for (auto& x : th) x.join();
-        for (int step = 1; step < nt; step *= 2)
-            for (int t = 0; t + step < nt; t += 2 * step)
-                std::inplace_merge(key.begin() + cut[t], key.begin() + cut[t + step], key.begin() + cut[std::min(nt, t + 2 * step)]);
+        std::vector<uint64_t> key(np_);
+        std::vector<uint32_t> perm(np_);
+        for (size_t i = 0; i < np_; i++) key[i] = pairs[i].first_key;
+        order_first_seen(key.data(), (uint32_t)np_, perm.data());
         std::vector<ntl_pair> sorted(np_);
-        for (size_t i = 0; i < np_; i++) sorted[i] = pairs[key[i].second];
+        for (size_t i = 0; i < np_; i++) sorted[i] = pairs[perm[i]];
         pairs.swap(sorted);
     }
     return NTL_OK;

@@ -11,6 +11,8 @@
 // tests (tests/emu/) can check it against the oracle without a GPU. The product only runs it on the device.
 #pragma once
 #include <stdint.h>
+#include <algorithm>
+#include <vector>
 #include "nthash.cuh"
 
 namespace ntl {
@@ -289,6 +291,34 @@ NTL_HD uint32_t tally_read(const Hit* hits, const Run* runs, uint32_t nr, uint32
         prev = i;
     }
     return ne;
+}
+
+// Host side of the pair table: the permutation that puts the pairs in first-seen order (the reference's dict order),
+// i.e. a stable ascending sort of their 64-bit first-seen keys. LSD radix sort on the bytes that actually differ: at
+// human scale (2 x 10^5 pairs on rank 0) a comparison sort of the records was the largest part of the tally time.
+inline void order_first_seen(const uint64_t* keys, uint32_t n, uint32_t* perm) {
+    if (n < 2) { if (n) perm[0] = 0; return; }
+    struct Rec { uint64_t k; uint64_t i; };
+    std::vector<Rec> a(n), b(n);
+    uint64_t differ = 0;
+    for (uint32_t i = 0; i < n; i++) { a[i].k = keys[i]; a[i].i = i; differ |= keys[i] ^ keys[0]; }
+    Rec* src = a.data();
+    Rec* dst = b.data();
+    int lo = 0, hi = 63;                                            // bits that differ between the keys
+    while (lo < 64 && !((differ >> lo) & 1ull)) lo++;
+    while (hi > lo && !((differ >> hi) & 1ull)) hi--;
+    constexpr int DIGIT = 11;                                       // 2048 buckets: four passes over a 44-bit span
+    std::vector<uint32_t> count((1u << DIGIT) + 1);
+    for (int shift = lo; shift <= hi && differ; shift += DIGIT) {
+        const uint64_t mask = (1ull << DIGIT) - 1;
+        if (((differ >> shift) & mask) == 0) continue;
+        std::fill(count.begin(), count.end(), 0u);
+        for (uint32_t i = 0; i < n; i++) count[((src[i].k >> shift) & mask) + 1]++;
+        for (uint32_t d = 0; d < (1u << DIGIT); d++) count[d + 1] += count[d];
+        for (uint32_t i = 0; i < n; i++) dst[count[(src[i].k >> shift) & mask]++] = src[i];
+        Rec* t = src; src = dst; dst = t;
+    }
+    for (uint32_t i = 0; i < n; i++) perm[i] = (uint32_t)src[i].i;
 }
 
 }  // namespace ntl

@@ -265,4 +265,7 @@ uint32_t emu_liftover(const uint32_t* hit_off, const uint32_t* nruns, const Run*
     return err;
 }
 
+// the host-side ordering of the pair table (map_logic.cuh)
+void emu_order_first_seen(const uint64_t* keys, uint32_t n, uint32_t* perm) { order_first_seen(keys, n, perm); }
+
 }  // extern "C"

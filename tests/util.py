@@ -139,6 +139,8 @@ def emu_lib():
         lib.emu_sketch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                    ctypes.c_uint32, ctypes.c_double, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+        lib.emu_order_first_seen.restype = None
+        lib.emu_order_first_seen.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         lib.emu_map.restype = ctypes.c_int64
         lib.emu_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
