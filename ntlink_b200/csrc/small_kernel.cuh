@@ -236,7 +236,10 @@ __global__ void __launch_bounds__(SMALL_THREADS * SMALL_GROUPS) k_small(const ui
 constexpr uint32_t STREAM_S = 256;
 constexpr int STREAM_THREADS = 128;
 constexpr uint32_t STREAM_RING = 32;                                 // hashes kept per thread: the previous block, the current one, 8 not yet decided
-constexpr size_t STREAM_SMEM = (size_t)ROLL_TABLE_ENTRIES * TBL_STRIDE + (size_t)STREAM_RING * STREAM_THREADS * 8;
+// a clean strip only meets base codes 0..3 and the virtual leaving base 4: roll-table entries (in << 3 | out) <= 28. Loading just
+// those leaves room for five blocks per SM instead of four.
+constexpr uint32_t STREAM_TBL_ENTRIES = 29;
+constexpr size_t STREAM_SMEM = (size_t)STREAM_TBL_ENTRIES * TBL_STRIDE + (size_t)STREAM_RING * STREAM_THREADS * 8;
 
 // The unrolled rolling loop only stores (push); the window logic runs once per 8-step block over the stored positions
 // (flush_block) so that it exists once in the instruction stream -- inlined into every unrolled step the kernel outgrew the
@@ -313,8 +316,8 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_stream(const uint32_t* __res
                                                            SketchStatus* __restrict__ st) {
     extern __shared__ __align__(256) unsigned char sm_raw[];
     unsigned char* tbl_s = sm_raw;
-    unsigned long long* ring = reinterpret_cast<unsigned long long*>(sm_raw + (size_t)ROLL_TABLE_ENTRIES * TBL_STRIDE) + threadIdx.x;
-    for (uint32_t i = threadIdx.x; i < ROLL_TABLE_ENTRIES * TBL_COPIES; i += STREAM_THREADS) {
+    unsigned long long* ring = reinterpret_cast<unsigned long long*>(sm_raw + (size_t)STREAM_TBL_ENTRIES * TBL_STRIDE) + threadIdx.x;
+    for (uint32_t i = threadIdx.x; i < STREAM_TBL_ENTRIES * TBL_COPIES; i += STREAM_THREADS) {
         const RollEntry e = tbl_g[i / TBL_COPIES];
         reinterpret_cast<uint4*>(tbl_s)[i] = make_uint4((uint32_t)e.f, (uint32_t)(e.f >> 32), (uint32_t)e.r, (uint32_t)(e.r >> 32));
     }
