@@ -83,6 +83,20 @@ class _CBuffer:
             self.ptr = None
 
 
+def _text_out(lib, out, n, copy):
+    """Text produced by the library's emitters: bytes (copy=True), or a memoryview straight over the library's buffer for
+    callers that only write it to a file -- the buffer goes back to the emitters' pool (ntl_buf_free) when the view dies,
+    so the next batch is formatted into memory that is already mapped."""
+    if copy or n == 0:
+        data = C.string_at(out, n)
+        lib.ntl_buf_free(out)
+        return data
+    import weakref
+    arr = (C.c_char * n).from_address(out.value)
+    weakref.finalize(arr, lib.ntl_buf_free, C.c_void_p(out.value))
+    return memoryview(arr)
+
+
 def _np_view(lib, ptr, n, dtype):
     "numpy array over a library buffer WITHOUT copying"
     if n == 0 or not ptr:
@@ -283,8 +297,8 @@ class Sketch:
         s.seq_off = C.cast(self.seq_off.ctypes.data, C.POINTER(C.c_uint64))
         return s
 
-    def to_tsv(self, batch, with_len=False, with_pos=True, with_strand=True, threads=4):
-        "the bytes `indexlr --long [--pos] [--strand] [--len]` writes for these sequences"
+    def to_tsv(self, batch, with_len=False, with_pos=True, with_strand=True, threads=4, copy=True):
+        "the bytes `indexlr --long [--pos] [--strand] [--len]` writes for these sequences (copy=False: see _text_out)"
         lib = _lib.load()
         blob, noff = batch.name_blob()
         lens = batch.lengths if with_len else None
@@ -294,9 +308,7 @@ class Sketch:
                                       threads, C.byref(out))
         if n < 0:
             raise NtlError(n, "ntl_format_sketch_tsv")
-        data = C.string_at(out, n)
-        lib.ntl_buf_free(out)
-        return data
+        return _text_out(lib, out, n, copy)
 
 
 class MapResult:
@@ -327,8 +339,8 @@ class MapResult:
         m.events = C.cast(self.events.ctypes.data, C.POINTER(_lib.Event))
         return m
 
-    def verbose_bytes(self, reads, contigs, threads=4):
-        "verbose_mapping.tsv lines (bin/ntlink_pair.py:382-388)"
+    def verbose_bytes(self, reads, contigs, threads=4, copy=True):
+        "verbose_mapping.tsv lines (bin/ntlink_pair.py:382-388); copy=False: see _text_out"
         lib = _lib.load()
         rb, ro = reads.name_blob()
         cb, co = contigs.name_blob()
@@ -337,11 +349,9 @@ class MapResult:
         n = lib.ntl_format_verbose(C.byref(st), _ptr(rb), _ptr(ro), _ptr(cb), _ptr(co), threads, C.byref(out))
         if n < 0:
             raise NtlError(n, "ntl_format_verbose")
-        data = C.string_at(out, n)
-        lib.ntl_buf_free(out)
-        return data
+        return _text_out(lib, out, n, copy)
 
-    def paf_bytes(self, reads, read_len, contigs, k, threads=4):
+    def paf_bytes(self, reads, read_len, contigs, k, threads=4, copy=True):
         "PAF-like lines (bin/ntlink_paf_output.py:103-135); raises where the reference asserts"
         lib = _lib.load()
         rb, ro = reads.name_blob()
@@ -354,9 +364,7 @@ class MapResult:
                                C.byref(out))
         if n < 0:
             raise NtlError(n, "ntl_format_paf: a PAF assertion of the reference failed")
-        data = C.string_at(out, n)
-        lib.ntl_buf_free(out)
-        return data
+        return _text_out(lib, out, n, copy)
 
 
 class Context:

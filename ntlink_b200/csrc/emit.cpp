@@ -56,13 +56,94 @@ void parallel_chunks(uint64_t n, int threads, F&& body /* (chunk_index, begin, e
     for (auto& x : th) x.join();
 }
 
+// The emitters are called once per batch with outputs of tens to hundreds of megabytes. Fresh memory of that size costs
+// more in page faults than formatting the text into it (and the faults of concurrent threads queue on the address-space
+// lock), so the per-thread part buffers and the joined output buffers are recycled: parts keep their capacity in a pool,
+// ntl_buf_free() parks up to two output buffers for the next call.
+struct TextPool {
+    std::mutex mu;
+    std::vector<std::string> parts;                       // cleared strings that keep their capacity
+    std::unordered_map<char*, size_t> live;               // output buffers handed out (ptr -> capacity)
+    std::vector<std::pair<char*, size_t>> parked;
+    static constexpr size_t MAX_PARKED = 2, MAX_BYTES = (size_t)2 << 30;
+};
+TextPool& text_pool() { static TextPool* p = new TextPool(); return *p; }
+
+std::vector<std::string> take_parts(size_t n) {
+    TextPool& P = text_pool();
+    std::vector<std::string> out;
+    std::lock_guard<std::mutex> lk(P.mu);
+    // largest capacities first: chunk t of this call is about as large as chunk t of the last one
+    std::sort(P.parts.begin(), P.parts.end(), [](const std::string& a, const std::string& b) { return a.capacity() < b.capacity(); });
+    while (out.size() < n && !P.parts.empty()) { out.emplace_back(std::move(P.parts.back())); P.parts.pop_back(); }
+    out.resize(n);
+    return out;
+}
+void give_parts(std::vector<std::string>& parts) {
+    TextPool& P = text_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    size_t held = 0;
+    for (auto& s : P.parts) held += s.capacity();
+    for (auto& s : parts) {
+        if (P.parts.size() >= 64 || held + s.capacity() > TextPool::MAX_BYTES) continue;
+        held += s.capacity();
+        s.clear();
+        P.parts.emplace_back(std::move(s));
+    }
+    parts.clear();
+}
+char* take_out(size_t total) {
+    TextPool& P = text_pool();
+    const size_t want = total ? total : 1;
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        for (size_t i = 0; i < P.parked.size(); i++)
+            if (P.parked[i].second >= want && P.parked[i].second <= 2 * want + (64u << 20)) {
+                char* p = P.parked[i].first;
+                P.live[p] = P.parked[i].second;
+                P.parked.erase(P.parked.begin() + (long)i);
+                return p;
+            }
+    }
+    const size_t cap = want + want / 8 + 4096;                  // a little head room: the next batch is rarely the same size
+    char* p = (char*)malloc(cap);
+    if (p) { std::lock_guard<std::mutex> lk(P.mu); P.live[p] = cap; }
+    return p;
+}
+void release_out(char* p) {
+    if (!p) return;
+    TextPool& P = text_pool();
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        auto it = P.live.find(p);
+        if (it != P.live.end()) {
+            const size_t cap = it->second;
+            P.live.erase(it);
+            size_t held = cap;
+            for (auto& q : P.parked) held += q.second;
+            if (P.parked.size() < TextPool::MAX_PARKED && held <= TextPool::MAX_BYTES) { P.parked.emplace_back(p, cap); return; }
+        }
+    }
+    free(p);
+}
+
 int64_t join_out(std::vector<std::string>& parts, char** out_buf) {
     size_t total = 0;
     for (auto& p : parts) total += p.size();
-    char* buf = (char*)malloc(total ? total : 1);
-    if (!buf) return NTL_ERR_ARG;
-    size_t o = 0;
-    for (auto& p : parts) { memcpy(buf + o, p.data(), p.size()); o += p.size(); }
+    char* buf = take_out(total);
+    if (!buf) { give_parts(parts); return NTL_ERR_ARG; }
+    // every part is copied by its own thread (the parts were written by as many threads)
+    std::vector<size_t> at(parts.size() + 1, 0);
+    for (size_t i = 0; i < parts.size(); i++) at[i + 1] = at[i] + parts[i].size();
+    if (total < (8u << 20) || parts.size() < 2) {
+        for (size_t i = 0; i < parts.size(); i++) memcpy(buf + at[i], parts[i].data(), parts[i].size());
+    } else {
+        std::vector<std::thread> th;
+        for (size_t i = 1; i < parts.size(); i++) th.emplace_back([&, i]() { memcpy(buf + at[i], parts[i].data(), parts[i].size()); });
+        memcpy(buf, parts[0].data(), parts[0].size());
+        for (auto& x : th) x.join();
+    }
+    give_parts(parts);
     *out_buf = buf;
     return (int64_t)total;
 }
@@ -130,9 +211,12 @@ int64_t ntl_format_sketch_tsv(const ntl_sketch_out* sk, const char* names, const
                               const uint64_t* seq_len, int with_pos, int with_strand, int threads, char** out_buf) {
     if (!sk || !names || !name_off || !out_buf) return NTL_ERR_ARG;
     int nch = 1;
-    std::vector<std::string> parts((size_t)(threads < 1 ? 1 : threads));
+    std::vector<std::string> parts = take_parts((size_t)(threads < 1 ? 1 : threads));
     parallel_chunks(sk->nseq, threads, [&](int t, uint64_t b, uint64_t e) {
-        std::string& s = parts[(size_t)t];
+        // a thread formats into a string of its own: the string objects of `parts` sit side by side in memory, and every
+        // push_back updates the size field -- two threads per cache line is false sharing that serialises them all
+        std::string s = std::move(parts[(size_t)t]);
+        struct PutBack { std::string& from; std::string& to; ~PutBack() { to = std::move(from); } } put_back{s, parts[(size_t)t]};
         s.reserve((size_t)((sk->seq_off[e] - sk->seq_off[b]) * 30 + (e - b) * 48));
         for (uint64_t i = b; i < e; i++) {
             s.append(names + name_off[i], (size_t)(name_off[i + 1] - name_off[i]));
@@ -154,9 +238,26 @@ int64_t ntl_format_verbose(const ntl_map_out* m, const char* read_names, const u
                            const char* ctg_names, const uint64_t* ctg_name_off, int threads, char** out_buf) {
     if (!m || !read_names || !read_name_off || !ctg_names || !ctg_name_off || !out_buf) return NTL_ERR_ARG;
     int nch = 1;
-    std::vector<std::string> parts((size_t)(threads < 1 ? 1 : threads));
+    std::vector<std::string> parts = take_parts((size_t)(threads < 1 ? 1 : threads));
     parallel_chunks(m->n_reads, threads, [&](int t, uint64_t b, uint64_t e) {
-        std::string& s = parts[(size_t)t];
+        // a thread formats into a string of its own: the string objects of `parts` sit side by side in memory, and every
+        // push_back updates the size field -- two threads per cache line is false sharing that serialises them all
+        std::string s = std::move(parts[(size_t)t]);
+        struct PutBack { std::string& from; std::string& to; ~PutBack() { to = std::move(from); } } put_back{s, parts[(size_t)t]};
+        {   // room for the whole chunk up front (a line is two names + a count + <= 26 bytes per hit): a string that grows by
+            // doubling re-maps its buffer again and again, and the threads then queue on the address-space lock
+            size_t need = 64;
+            for (uint64_t r = b; r < e; r++) {
+                const uint32_t nr = m->nruns[r];
+                const uint32_t base = m->hit_off[r];
+                for (uint32_t i = 0; i < nr; i++) {
+                    const ntl_run run = m->runs[base + i];
+                    need += (size_t)(read_name_off[r + 1] - read_name_off[r]) + (size_t)(ctg_name_off[run.ctg + 1] - ctg_name_off[run.ctg]) +
+                            16 + (size_t)run.count * 26;
+                }
+            }
+            s.reserve(need);
+        }
         for (uint64_t r = b; r < e; r++) {
             const uint32_t nr = m->nruns[r];
             if (!nr) continue;
@@ -193,10 +294,13 @@ int64_t ntl_format_paf(const ntl_map_out* m, const char* read_names, const uint6
     if (!m || !read_names || !read_name_off || !read_len || !ctg_names || !ctg_name_off || !ctg_len || !out_buf)
         return NTL_ERR_ARG;
     int nch = 1;
-    std::vector<std::string> parts((size_t)(threads < 1 ? 1 : threads));
+    std::vector<std::string> parts = take_parts((size_t)(threads < 1 ? 1 : threads));
     std::vector<int> failed((size_t)(threads < 1 ? 1 : threads), 0);
     parallel_chunks(m->n_reads, threads, [&](int t, uint64_t b, uint64_t e) {
-        std::string& s = parts[(size_t)t];
+        // a thread formats into a string of its own: the string objects of `parts` sit side by side in memory, and every
+        // push_back updates the size field -- two threads per cache line is false sharing that serialises them all
+        std::string s = std::move(parts[(size_t)t]);
+        struct PutBack { std::string& from; std::string& to; ~PutBack() { to = std::move(from); } } put_back{s, parts[(size_t)t]};
         std::vector<PHit> hits, srt;
         std::vector<std::vector<PHit>> blocks;
         for (uint64_t r = b; r < e; r++) {
@@ -252,11 +356,11 @@ int64_t ntl_format_paf(const ntl_map_out* m, const char* read_names, const uint6
             }
         }
     }, &nch);
-    for (int f : failed) if (f) return NTL_ERR_ASSERT;
+    for (int f : failed) if (f) { give_parts(parts); return NTL_ERR_ASSERT; }
     return join_out(parts, out_buf);
 }
 
-void ntl_buf_free(char* buf) { free(buf); }
+void ntl_buf_free(char* buf) { release_out(buf); }
 void ntl_free(void* p) { if (!ntl_pool_release(p)) free(p); }
 
 }  // extern "C"

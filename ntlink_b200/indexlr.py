@@ -37,7 +37,7 @@ def main(argv=None):
         # streamed in chunks; the next chunk is read / decompressed while this one is sketched and printed
         for batch in api.prefetch_batches([a.FILE], int(a.chunk_bases)):
             sk = ctx.sketch(batch, a.k, a.w)
-            out.write(sk.to_tsv(batch, with_len=a.len, with_pos=a.pos, with_strand=a.strand, threads=a.t))
+            out.write(sk.to_tsv(batch, with_len=a.len, with_pos=a.pos, with_strand=a.strand, threads=a.t, copy=False))
     except OSError as exc:
         sys.exit(f"indexlr: {exc}")
     finally:

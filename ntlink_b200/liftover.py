@@ -101,7 +101,7 @@ def liftover_file(ctx, mappings_path, agp_lines, k, out_path, threads=4, batch_h
             res = ctx.liftover_mappings(hit_off, nruns, runs, hits, rows, k)
             reads = api.SeqBatch(np.empty(0, np.uint8), np.zeros(len(ids) + 1, np.uint64), ids)
             contigs = api.SeqBatch(np.empty(0, np.uint8), np.zeros(len(new_names) + 1, np.uint64), new_names)
-            fout.write(res.verbose_bytes(reads, contigs, threads=threads))
+            fout.write(res.verbose_bytes(reads, contigs, threads=threads, copy=False))
 
 
 def liftover_and_tally(ctx, mapping_lines, agp_lines, k, scaffold_lengths, prm):

@@ -246,7 +246,7 @@ class NtLink:
                 sk = self.ctx.build_index_from_sequences(self.contigs, a.k, a.w, want_sketch=bool(a.write_target_tsv))
                 if a.write_target_tsv and self.rank == 0:
                     with open(a.write_target_tsv, "wb") as fout:
-                        fout.write(sk.to_tsv(self.contigs, with_len=False, threads=a.t))
+                        fout.write(sk.to_tsv(self.contigs, with_len=False, threads=a.t, copy=False))
         else:
             idx = {n: i for i, n in enumerate(self.contigs.names)}
             hs, ps, cs = [], [], []
@@ -365,9 +365,9 @@ class NtLink:
 
     def _emit(self, res, reads, read_len, vf, pf):
         if vf is not None:
-            vf.write(res.verbose_bytes(reads, self.contigs, threads=self.args.t))
+            vf.write(res.verbose_bytes(reads, self.contigs, threads=self.args.t, copy=False))
         if pf is not None:
-            pf.write(res.paf_bytes(reads, read_len, self.contigs, self.args.k, threads=self.args.t))
+            pf.write(res.paf_bytes(reads, read_len, self.contigs, self.args.k, threads=self.args.t, copy=False))
 
     def main(self):
         a = self.args
