@@ -36,8 +36,18 @@ def reverse_orientation(ori):
 
 
 def gap_estimate(gaps):
-    "PairInfo.get_gap_estimate (pair:70-74): int() of numpy's median -> truncation toward zero"
-    return int(np.median(gaps))
+    """PairInfo.get_gap_estimate (pair:70-74): int() of numpy's median -> truncation toward zero. Computed without numpy:
+    the lists are a few integers long and np.median costs ~20 us a call, which at human scale (2 x 10^5 pairs, three
+    calls each) was most of the pairing stage's host time. For an even count numpy averages the two middle values in
+    float64, exactly what (a + b) / 2 does for integers of this size."""
+    n = len(gaps)
+    if n == 1:
+        return int(gaps[0])
+    s = sorted(gaps)
+    m = n >> 1
+    if n & 1:
+        return int(s[m])
+    return int((s[m - 1] + s[m]) / 2)
 
 
 def pairs_dict(gpu_pairs, names):
@@ -46,7 +56,7 @@ def pairs_dict(gpu_pairs, names):
     out = {}
     for src, tgt, flags, _, anchor, gaps in gpu_pairs:
         key = (names[src], "+" if flags & 1 else "-", names[tgt], "+" if flags & 2 else "-")
-        out[key] = ([int(g) for g in gaps], int(anchor))
+        out[key] = (gaps.tolist() if hasattr(gaps, "tolist") else [int(g) for g in gaps], int(anchor))
     return out
 
 
