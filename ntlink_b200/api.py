@@ -31,13 +31,39 @@ def name_ranks(names):
 
 
 class SeqBatch:
-    """Sequences back to back: seq uint8[total], offsets uint64[n+1], names list[str]."""
+    """Sequences back to back: seq uint8[total], offsets uint64[n+1], names list[str]. Batches that come from the native
+    reader carry the names as one blob (`from_blob`): the text emitters take that blob as it is, and the Python strings are
+    only made if somebody asks for `.names` (a million reads are a million small string objects otherwise)."""
 
     def __init__(self, seq, offsets, names):
         self.seq = np.ascontiguousarray(seq, dtype=np.uint8)
         self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-        self.names = list(names)
-        assert len(self.offsets) == len(self.names) + 1
+        self._names = list(names)
+        assert len(self.offsets) == len(self._names) + 1
+        self._name_blob = None
+
+    @classmethod
+    def from_blob(cls, seq, offsets, blob, name_off):
+        "names given as bytes back to back (blob) + offsets uint64[n+1]"
+        out = cls.__new__(cls)
+        out.seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        out.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        assert len(out.offsets) == len(name_off)
+        out._names = None
+        out._name_blob = (np.frombuffer(bytes(blob) + b"\0", dtype=np.uint8), np.ascontiguousarray(name_off, dtype=np.uint64))
+        return out
+
+    @property
+    def names(self):
+        if self._names is None:
+            blob, off = self._name_blob
+            raw, no = blob.tobytes(), off.tolist()
+            self._names = [raw[no[i]:no[i + 1]].decode() for i in range(len(no) - 1)]
+        return self._names
+
+    @names.setter
+    def names(self, value):
+        self._names = list(value)
         self._name_blob = None
 
     @classmethod
@@ -53,7 +79,7 @@ class SeqBatch:
         return cls(seq, np.array(offs, np.uint64), names)
 
     def __len__(self):
-        return len(self.names)
+        return len(self.offsets) - 1
 
     @property
     def lengths(self):
@@ -61,7 +87,7 @@ class SeqBatch:
 
     def name_blob(self):
         if self._name_blob is None:
-            enc = [n.encode() for n in self.names]
+            enc = [n.encode() for n in self._names]
             off = np.zeros(len(enc) + 1, np.uint64)
             if enc:
                 off[1:] = np.cumsum([len(e) for e in enc])
@@ -136,9 +162,7 @@ class SeqFile:
             self.lib.ntl_free(seq)
             return None
         s = _np_view(self.lib, seq.value, total, np.uint8)
-        no = name_off.tolist()
-        nm = [nb[no[i]:no[i + 1]].decode() for i in range(nseq)]
-        return SeqBatch(s, offsets, nm)
+        return SeqBatch.from_blob(s, offsets, nb, name_off)
 
     def close(self):
         if self.h:
