@@ -513,8 +513,8 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=70)          # configs[2]: 70 x 15 ms = a timed region of ~1 s for the resident arm
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ntlink_b200", choices=["ntlink_b200", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="default: c2 (configs[2]) up to 4 GPUs, c3 (configs[3]) at 8")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink genome and reads (smoke runs)")
