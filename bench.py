@@ -513,8 +513,8 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=70)          # configs[2]: 70 x 15 ms = a timed region of ~1 s for the resident arm
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="default: 70 (configs[2]: 70 x 15 ms = a timed region of ~1 s for the resident arm); 10 for --impl reference (a CPU step is ~2 s)")
+    ap.add_argument("--warmup", type=int, default=None, help="default: 5 (3 for --impl reference)")
     ap.add_argument("--impl", default="ntlink_b200", choices=["ntlink_b200", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="default: c2 (configs[2]) up to 4 GPUs, c3 (configs[3]) at 8")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink genome and reads (smoke runs)")
@@ -527,6 +527,10 @@ def main():
     ap.add_argument("--shard-target", default="auto", choices=["auto", "always", "never"],
                     help="N>1: sketch the target in contig shards + NCCL all-gather (auto: targets >= 256 Mbp)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 10 if args.impl == "reference" else 70
+    if args.warmup is None:
+        args.warmup = 3 if args.impl == "reference" else 5
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # started without a launcher: one process per GPU through torchrun, as the harness does
         import socket
