@@ -654,13 +654,29 @@ retry:
     return NTL_OK;
 }
 
-// The dense-mode sketch for small windows (small_kernel.cuh): pack, tile table, k_small, scan of the tile counts, gather.
+// The dense-mode sketch for small windows (small_kernel.cuh): pack, tile table, k_small / k_stream, scan of the counts, gather.
+// Returns SMALL_SKIP when the batch should take the sparse path instead.
+constexpr int SMALL_SKIP = 1;
+constexpr double SMALL_STAGE_LIMIT = 48e9;
 static int sketch_device_small(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint32_t nseq, uint64_t total_bases,
                                uint32_t k, uint32_t w, DeviceSketch& out, CallState* call_state) {
     SketchWork& W = c->sw;
     // option small: 1 = automatic (measured, DESIGN.md 8: the tile kernel wins for w <= 6, where a third of all positions are
     // minimizers and the streaming kernel's per-position mark logic costs most), 2 = tile kernel, 3 = streaming kernel
-    const bool stream = c->small_mode == 3 || (c->small_mode == 1 && w > 6);
+    bool stream = c->small_mode == 3 || (c->small_mode == 1 && w > 6);
+    // Staging is one segment per tile / strip, and every sequence adds a partial one: a batch of very many short sequences
+    // (or a density head room that doubled after low-complexity input) would ask for more staging than the result is worth.
+    // Beyond SMALL_STAGE_LIMIT the batch takes the other form if that fits (automatic mode), else the sparse path.
+    auto stage_bytes = [&](bool st) {
+        const double s_ = st ? (double)STREAM_S : (double)SMALL_S;
+        const double n_ = (double)(total_bases / (uint64_t)s_ + nseq + 1);
+        const double tc = std::min<double>(s_, s_ * c->mx_density_factor / ((double)w + 1.0) * 1.25 + (st ? 8.0 : 64.0));
+        return n_ * tc * 12.0;
+    };
+    if (stage_bytes(stream) > SMALL_STAGE_LIMIT) {
+        if (c->small_mode == 1 && stage_bytes(!stream) <= SMALL_STAGE_LIMIT) stream = !stream;
+        else return SMALL_SKIP;
+    }
     const uint32_t S = stream ? STREAM_S : SMALL_S;
     const uint32_t nstrips_max = (uint32_t)(total_bases / S + nseq + 1);
     static bool smem_set = false;
@@ -757,6 +773,7 @@ retry:
         if (hs.err) {                                                // denser than the bound (low complexity): more room per tile and overall
             if (++attempt > 6) { c->err = "sketch: device workspace exhausted"; return NTL_ERR_WORKSPACE; }
             c->mx_density_factor *= 2.0;
+            if (stage_bytes(stream) > SMALL_STAGE_LIMIT) return SMALL_SKIP;      // the sparse path sizes its buffers by what it finds
             goto retry;
         }
         out.n_mx = hs.n_mx;
@@ -777,7 +794,10 @@ int sketch_device(ntl_ctx* c, const uint8_t* d_seq, const uint64_t* d_off, uint3
         NTL_CUDA(c, cudaMemsetAsync(out.mx_off.p, 0, ((size_t)nseq + 1) * 4, c->stream));
         return NTL_OK;
     }
-    if (c->small_mode && w >= 2 && w <= SMALL_W_MAX && k <= 2048) return sketch_device_small(c, d_seq, d_off, nseq, total_bases, k, w, out, call_state);
+    if (c->small_mode && w >= 2 && w <= SMALL_W_MAX && k <= 2048) {
+        const int rc = sketch_device_small(c, d_seq, d_off, nseq, total_bases, k, w, out, call_state);
+        if (rc != SMALL_SKIP) return rc;
+    }
     if (c->tile_mode) {
         const TileShape shape = tile_shape(k, w, c->cand_c);
         if (shape.ok) {
